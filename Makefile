@@ -1,0 +1,41 @@
+# Build of the B200-native Krylov hot path.  `make` builds everything in-tree:
+#   slepc_b200/lib/libb200krylov.so  CUDA kernels + C ABI (include/b2k.h), sm_100a only
+#   slepc_b200/lib/libb2kslepc.so    C host side mirroring SLEPc's BV/DS/ST/EPS/SVD API (include/b2kslepc.h)
+#   oracle/_build/liboraclecpu.so    CPU BV/Mat plugin used ONLY as test oracle / timed CPU baseline
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+PYTHON    ?= python
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -Islepc_b200/csrc
+CFLAGS    := -O2 -g -fPIC -std=gnu11 -Wall -Wno-unused-function -Iinclude -Islepc_b200/host
+OPENBLAS  := $(shell $(PYTHON) -c "import scipy,os,glob;print(os.path.realpath(glob.glob(os.path.join(os.path.dirname(scipy.__file__),'..','scipy.libs','libscipy_openblas*.so'))[0]))")
+OPENBLAS_DIR := $(dir $(OPENBLAS))
+
+LIBDIR    := slepc_b200/lib
+KSRC      := $(wildcard slepc_b200/csrc/*.cu)
+KHDR      := $(wildcard slepc_b200/csrc/*.h) include/b2k.h
+HSRC      := $(wildcard slepc_b200/host/*.c)
+HHDR      := $(wildcard slepc_b200/host/*.h) include/b2kslepc.h include/b2k.h
+OSRC      := $(wildcard oracle/*.c)
+
+all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so oracle/_build/liboraclecpu.so
+
+$(LIBDIR)/libb200krylov.so: $(KSRC) $(KHDR)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(KSRC) -ldl
+
+$(LIBDIR)/libb2kslepc.so: $(HSRC) $(HHDR) $(LIBDIR)/libb200krylov.so
+	$(CC) $(CFLAGS) -shared -o $@ $(HSRC) -L$(LIBDIR) -lb200krylov -Wl,-rpath,'$$ORIGIN' \
+	    $(OPENBLAS) -Wl,-rpath,$(OPENBLAS_DIR) -lm -ldl
+
+oracle/_build/liboraclecpu.so: $(OSRC) $(HHDR) $(LIBDIR)/libb2kslepc.so
+	@mkdir -p oracle/_build
+	$(CC) $(CFLAGS) -O3 -march=x86-64-v3 -fopenmp -shared -o $@ $(OSRC) -L$(LIBDIR) -lb2kslepc \
+	    -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' $(OPENBLAS) -Wl,-rpath,$(OPENBLAS_DIR) -lm
+
+kernels: $(LIBDIR)/libb200krylov.so
+
+clean:
+	rm -f $(LIBDIR)/*.so oracle/_build/*.so
+
+.PHONY: all clean kernels

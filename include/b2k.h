@@ -1,0 +1,154 @@
+/*
+ * b2k.h — C ABI of libb200krylov.so: sm_100a CUDA kernels for SLEPc's Krylov hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one function of the
+ * reference's CUDA BV backend (src/sys/classes/bv/impls/cuda/bvcuda.cu, cuBLAS wrappers) or the
+ * PETSc MatMult it calls (src/sys/classes/bv/interface/bvops.c:879).  File:line citations are
+ * relative to the SLEPc 3.22 tree.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / PETSc types;
+ *   - every function returns 0 (B2K_OK) or a B2K_ERR_* code; b2k_last_error() gives the text;
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - basis blocks are column-major, leading dimension `ld` in elements, 64-bit offsets
+ *     (m*ld exceeds 2^31 at 1.3e8 rows, cf. the PetscIntMultError guard at svec.c:425);
+ *   - all work is queued on the context's stream; nothing synchronises unless stated;
+ *   - reductions are LOCAL to this GPU (the caller all-reduces the k+1 doubles, b2k_comm_*);
+ *   - results are bit-reproducible run to run (fixed-order two-stage reductions, no atomics).
+ */
+#ifndef B2K_H
+#define B2K_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2K_OK        0
+#define B2K_ERR_CUDA  1   /* a CUDA runtime call failed */
+#define B2K_ERR_ARG   2   /* invalid argument */
+#define B2K_ERR_NOGPU 3   /* no CUDA device: the product path has no CPU fallback */
+#define B2K_ERR_COMM  4   /* NCCL / peer-memory failure */
+#define B2K_ERR_MEM   5
+
+typedef struct b2k_ctx_s  *b2k_ctx;    /* one per process/GPU: device, stream, scratch */
+typedef struct b2k_csr_s  *b2k_csr;    /* FP64 CSR matrix resident in HBM */
+typedef struct b2k_comm_s *b2k_comm;   /* row-partition communicator (NCCL over NVLink) */
+
+const char *b2k_last_error(void);
+int  b2k_version(void);
+int  b2k_device_count(int *count);
+
+/* ---- context / memory ----------------------------------------------------------------- */
+int  b2k_ctx_create(int device, b2k_ctx *ctx);
+int  b2k_ctx_destroy(b2k_ctx ctx);
+int  b2k_ctx_sync(b2k_ctx ctx);
+void *b2k_ctx_stream(b2k_ctx ctx);                       /* cudaStream_t */
+int  b2k_ctx_sm_count(b2k_ctx ctx);
+int  b2k_ctx_launches(b2k_ctx ctx, uint64_t *count);     /* kernels launched through this ctx */
+int  b2k_malloc(b2k_ctx ctx, void **dptr, size_t bytes);
+int  b2k_free(b2k_ctx ctx, void *dptr);
+int  b2k_memset0(b2k_ctx ctx, void *dptr, size_t bytes);
+int  b2k_h2d(b2k_ctx ctx, void *dst, const void *src_host, size_t bytes);        /* blocking */
+int  b2k_d2h(b2k_ctx ctx, void *dst_host, const void *src, size_t bytes);        /* blocking */
+int  b2k_h2d_async(b2k_ctx ctx, void *dst, const void *src_host, size_t bytes);
+int  b2k_d2h_async(b2k_ctx ctx, void *dst_host, const void *src, size_t bytes);
+int  b2k_d2d(b2k_ctx ctx, void *dst, const void *src, size_t bytes);             /* async */
+int  b2k_host_alloc(void **hptr, size_t bytes);                                  /* pinned */
+int  b2k_host_free(void *hptr);
+int  b2k_mem_info(b2k_ctx ctx, size_t *free_bytes, size_t *total_bytes);
+/* CUDA-event timing on the context's stream (bench / roofline) */
+int  b2k_timer_start(b2k_ctx ctx);
+int  b2k_timer_stop_ms(b2k_ctx ctx, double *ms);                                 /* blocking */
+
+/* ---- BV level-1/2/3 (replace bvcuda.cu) ------------------------------------------------------ */
+/* q[0:k] = V(:,0:k)^T y                      — BVDotVec_BLAS_CUDA  bvcuda.cu:204-264 (gemv 'C')  */
+int  b2k_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *y, double *q);
+/* y = beta*y + alpha*V(:,0:k) q              — BVMultVec_BLAS_CUDA bvcuda.cu:45-60   (gemv 'N')  */
+int  b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta,
+                 double *y, const double *q);
+/* out[0] = sum of squares of the n x k block  — BVNorm_BLAS_CUDA    bvcuda.cu:290-303 (nrm2)      */
+int  b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out);
+/* out[0] = max_j sum_i |X(i,j)| (local part of NORM_1), out[1] = max |X(i,j)| … used by BVNorm   */
+int  b2k_colabssum(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out_k);
+/* X = alpha*X on an n x k block               — BVScale_BLAS_CUDA   bvcuda.cu:269-285 (scal)      */
+int  b2k_scale(b2k_ctx ctx, double *X, int64_t ld, int64_t n, int k, double alpha);
+/* Y = X on an n x k block                     — BVCopy_Svec_CUDA    sveccuda.cu:305-330           */
+int  b2k_copy(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int k);
+/* Y = alpha*X + beta*Y on an n x k block      — BVAXPY_BLAS_CUDA    bvcuda.cu:117-135 (geam)      */
+int  b2k_axpby(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int k,
+               double alpha, double beta);
+/* Y(n x ky) = beta*Y + alpha*X(n x kx) Q(kx x ky) — BVMult_BLAS_CUDA bvcuda.cu:22-40 (gemm)       */
+int  b2k_mult(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx,
+              double alpha, double beta, const double *Q, int ldq);
+/* V(:,s:e) = V(:,0:k) Q(0:k,s:e)  (Q^T if trans) in place, no workspace, no copy-back
+                                               — BVMultInPlace_BLAS_CUDA bvcuda.cu:65-112          */
+int  b2k_mult_inplace(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, int s, int e,
+                      const double *Q, int ldq, int trans);
+/* M(ky x kx) = Y^T X (local)                  — BVDot_BLAS_CUDA     bvcuda.cu:140-199 (gemm 'C')  */
+int  b2k_dot(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx,
+             double *M, int ldm);
+/* x[i] = hash_uniform(row0+i, seed) in [-1,1): deterministic stand-in for BVSetRandomColumn
+   (bvops.c:482, PetscRandom) shared bit-for-bit with the oracle and the host code              */
+int  b2k_set_random(b2k_ctx ctx, double *x, int64_t n, int64_t row0, uint64_t seed);
+int  b2k_fill(b2k_ctx ctx, double *x, int64_t n, double value);
+
+/* ---- fused classical Gram-Schmidt sweeps (replace bvorthog.c:91-132 + bvcuda.cu:345-548) ---- */
+/* c[0:k] = V(:,0:k)^T w, c[k] = w^T w        — BVDotColumnInc bvorthog.c:32-47: one sweep, one
+   reduction (h and ||w||^2 together)                                                            */
+int  b2k_gs_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *w, double *c);
+/* w -= V(:,0:k) cin ; cout[0:k] = V^T w_new ; cout[k] = ||w_new||^2 — update of pass p fused
+   with the dot sweep of pass p+1 (DGKS refinement) and with the explicit norm: V is read ONCE  */
+int  b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w,
+                       const double *cin, double *cout);
+/* x *= 1/sqrt(sumsq[0]) guarded (no-op if sumsq is 0 or 1): normalisation with the norm still on
+   the device                                  — BVOrthonormalizeColumn bvorthog.c:417-422        */
+int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
+/* select the single-sweep (1) or the two-sweep (0) implementation of b2k_gs_update_dot (default 1; env B2K_GS_FUSED) */
+int  b2k_gs_set_fused(int on);
+
+/* ---- sparse matrix-vector product (replaces PETSc MatMult behind bvops.c:879 / stsolve.c:22) -- */
+/* CSR with int32 indices.  Column indices < ncols_local address x, the rest address
+   xghost[col-ncols_local] (halo entries received from the neighbouring GPUs).                     */
+int  b2k_csr_create(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t nghost,
+                    const int *rowptr_host, const int *colidx_host, const double *val_host, b2k_csr *A);
+/* same, adopting arrays that already live in HBM (device generators)                              */
+int  b2k_csr_adopt(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t nghost, int64_t nnz,
+                   int *rowptr, int *colidx, double *val, b2k_csr *A);
+int  b2k_csr_destroy(b2k_ctx ctx, b2k_csr A);
+int  b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncols_local, int64_t *nghost, int64_t *nnz);
+/* y = A [x ; xghost]                                                                               */
+int  b2k_csr_spmv(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y);
+/* y = A x - sigma*xdiag   (shifted operator of STSHIFT, shift.c:79; xdiag = x rows owned here)    */
+int  b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y, double sigma);
+/* device generator: rows [row0,row0+nrows) of the d-dimensional Laplacian stencil (d=1,2,3) on an
+   nx*ny*nz grid, natural ordering, slab partition along the slowest index: ex1.c:37-48, ex2.c:39-54.
+   Ghost layout: [lower neighbour plane | upper neighbour plane].                                   */
+int  b2k_csr_laplacian(b2k_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, int64_t row0, int64_t nrows,
+                       b2k_csr *A, int64_t *nghost_lo, int64_t *nghost_hi);
+/* gather: out[i] = x[idx[i]] (packs halo send buffers)                                             */
+int  b2k_gather(b2k_ctx ctx, double *out, const double *x, const int *idx, int64_t count);
+
+/* ---- row-partition communicator (replaces MPIU_Allreduce bvcuda.cu:228-248, VecScatter) -------- */
+#define B2K_COMM_ID_BYTES 128
+int  b2k_comm_unique_id(void *id_host /* B2K_COMM_ID_BYTES */);
+int  b2k_comm_create(b2k_ctx ctx, int rank, int size, const void *id_host, b2k_comm *comm);
+int  b2k_comm_destroy(b2k_comm comm);
+int  b2k_comm_rank(b2k_comm comm, int *rank, int *size);
+/* in-place sum over ranks of count doubles in HBM, queued on the ctx stream                        */
+int  b2k_comm_allreduce_sum(b2k_comm comm, double *buf, int count);
+int  b2k_comm_allreduce_max(b2k_comm comm, double *buf, int count);
+/* neighbour halo exchange: send `nsend` doubles to `peer`, receive `nrecv` from it (either may be 0) */
+int  b2k_comm_sendrecv(b2k_comm comm, const double *sendbuf, int64_t nsend, int send_peer,
+                       double *recvbuf, int64_t nrecv, int recv_peer);
+int  b2k_comm_group_start(b2k_comm comm);
+int  b2k_comm_group_end(b2k_comm comm);
+int  b2k_comm_allgather(b2k_comm comm, const double *sendbuf, double *recvbuf, int64_t count_per_rank);
+int  b2k_comm_reduce_scatter_sum(b2k_comm comm, const double *sendbuf, double *recvbuf, int64_t count_per_rank);
+int  b2k_comm_barrier(b2k_comm comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,624 @@
+/*
+ * b2k_bv.cu — hand-written sm_100a kernels for the BV (basis-vector) operations on SLEPc's
+ * Krylov hot path.  They replace the cuBLAS wrappers of
+ *   /root/reference/src/sys/classes/bv/impls/cuda/bvcuda.cu
+ * (gemv 'C' :204-264, gemv 'N' :45-60, nrm2 :290-303, scal :269-285, gemm :22-40 / :65-112 /
+ * :140-199, geam :117-135) and the coefficient micro-kernels (:345-548).
+ *
+ * Everything here is FP64 and HBM-bandwidth bound (AI <= 0.25 flop/B for the level-2 sweeps):
+ * the design rules are coalesced 16-byte loads, enough independent loads in flight per SM to
+ * cover HBM latency, grids sized in multiples of the SM count, and fixed-order two-stage
+ * reductions (no atomics) so that results are bit-reproducible.
+ */
+#include "b2k_internal.h"
+
+#define WARP 32
+
+/* streaming 16-byte load: read-only path, do not allocate in L1 (V is touched once per sweep) */
+__device__ __forceinline__ double2 ld_stream2(const double2 *p)
+{
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream1(const double *p)
+{
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * dotvec: part[blk][c0+c] = sum over this block's rows of V(r,c0+c)*w(r), one column tile of
+ * <= CT columns per blockIdx.y; optional extra column k: w^T w (tile 0 only).
+ * Each thread keeps CT accumulators and walks row PAIRS (16-byte loads) with a grid stride, so a
+ * thread has up to CT independent 16 B loads in flight and V is read exactly once.
+ * ---------------------------------------------------------------------------------------------- */
+template <int CT, bool VEC2>
+__global__ void __launch_bounds__(256, 2) k_dotvec(const double *__restrict__ V, int64_t ld, int64_t n, int k, int ctile,
+                                                 const double *__restrict__ w, double *__restrict__ part, int pstride,
+                                                 int with_ww)
+{
+  const int tile = blockIdx.y;
+  const int c0 = tile * ctile;
+  const int nc = min(ctile, k - c0);
+  double acc[CT];
+#pragma unroll
+  for (int c = 0; c < CT; c++) acc[c] = 0.0;
+  double aw = 0.0;
+  const bool do_ww = with_ww && tile == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *Vc = V + (int64_t)c0 * ld;
+
+  if (VEC2) {
+    const int64_t npair = n >> 1;
+    const double2 *w2 = reinterpret_cast<const double2 *>(w);
+    for (int64_t p = t0; p < npair; p += stride) {
+      const double2 wv = w2[p];
+      double2 v[CT];
+#pragma unroll
+      for (int c = 0; c < CT; c++)
+        if (c < nc) v[c] = ld_stream2(reinterpret_cast<const double2 *>(Vc + (int64_t)c * ld) + p);
+#pragma unroll
+      for (int c = 0; c < CT; c++)
+        if (c < nc) { acc[c] = fma(v[c].x, wv.x, acc[c]); acc[c] = fma(v[c].y, wv.y, acc[c]); }
+      if (do_ww) { aw = fma(wv.x, wv.x, aw); aw = fma(wv.y, wv.y, aw); }
+    }
+    if ((n & 1) && t0 == 0) {   /* odd tail row */
+      const int64_t r = n - 1;
+      const double wv = w[r];
+#pragma unroll
+      for (int c = 0; c < CT; c++)
+        if (c < nc) acc[c] = fma(Vc[(int64_t)c * ld + r], wv, acc[c]);
+      if (do_ww) aw = fma(wv, wv, aw);
+    }
+  } else {
+    for (int64_t r = t0; r < n; r += stride) {
+      const double wv = w[r];
+#pragma unroll
+      for (int c = 0; c < CT; c++)
+        if (c < nc) acc[c] = fma(ld_stream1(Vc + (int64_t)c * ld + r), wv, acc[c]);
+      if (do_ww) aw = fma(wv, wv, aw);
+    }
+  }
+
+  /* block reduction: shuffle inside warps, then 8 warps through shared memory, fixed order */
+  __shared__ double red[8][CT + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    double s = warp_sum(acc[c]);
+    if (lane == 0) red[wid][c] = s;
+  }
+  {
+    double s = warp_sum(aw);
+    if (lane == 0) red[wid][CT] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += red[q][threadIdx.x];
+    part[(int64_t)blockIdx.x * pstride + c0 + threadIdx.x] = s;
+  }
+  if (do_ww && threadIdx.x == 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += red[q][CT];
+    part[(int64_t)blockIdx.x * pstride + k] = s;
+  }
+}
+
+/* second stage: out[c] = sum_b part[b][c] in block order, one warp per column */
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ part, int nblk, int pstride, int ncols,
+                                                         double *__restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int b = lane; b < nblk; b += 32) s += part[(int64_t)b * pstride + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * multvec: y = beta*y + alpha * V(:,0:k) q, optionally emitting partial sums of ||y_new||^2.
+ * One thread per row pair, coefficients in shared memory (broadcast reads), 8 independent 16 B
+ * loads per batch.  No cross-thread reduction is needed for y itself.
+ * ---------------------------------------------------------------------------------------------- */
+template <bool VEC2, bool NRM>
+__global__ void __launch_bounds__(256) k_multvec(const double *__restrict__ V, int64_t ld, int64_t n, int k, double alpha,
+                                                  double beta, double *__restrict__ y, const double *__restrict__ q,
+                                                  double *__restrict__ part, int pstride, int pcol)
+{
+  extern __shared__ double qs[];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) qs[i] = q[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double nrm = 0.0;
+  if (VEC2) {
+    const int64_t npair = n >> 1;
+    double2 *y2 = reinterpret_cast<double2 *>(y);
+    for (int64_t p = t0; p < npair; p += stride) {
+      double ax = 0.0, ay = 0.0;
+      int c = 0;
+      for (; c + 8 <= k; c += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = ld_stream2(reinterpret_cast<const double2 *>(V + (int64_t)(c + u) * ld) + p);
+#pragma unroll
+        for (int u = 0; u < 8; u++) { ax = fma(v[u].x, qs[c + u], ax); ay = fma(v[u].y, qs[c + u], ay); }
+      }
+      for (; c < k; c++) {
+        const double2 v = ld_stream2(reinterpret_cast<const double2 *>(V + (int64_t)c * ld) + p);
+        ax = fma(v.x, qs[c], ax); ay = fma(v.y, qs[c], ay);
+      }
+      double2 o;
+      if (beta == 0.0) { o.x = alpha * ax; o.y = alpha * ay; }
+      else { const double2 yo = y2[p]; o.x = fma(beta, yo.x, alpha * ax); o.y = fma(beta, yo.y, alpha * ay); }
+      y2[p] = o;
+      if (NRM) { nrm = fma(o.x, o.x, nrm); nrm = fma(o.y, o.y, nrm); }
+    }
+    if ((n & 1) && t0 == 0) {
+      const int64_t r = n - 1;
+      double a = 0.0;
+      for (int c = 0; c < k; c++) a = fma(V[(int64_t)c * ld + r], qs[c], a);
+      const double o = (beta == 0.0) ? alpha * a : fma(beta, y[r], alpha * a);
+      y[r] = o;
+      if (NRM) nrm = fma(o, o, nrm);
+    }
+  } else {
+    for (int64_t r = t0; r < n; r += stride) {
+      double a = 0.0;
+      for (int c = 0; c < k; c++) a = fma(ld_stream1(V + (int64_t)c * ld + r), qs[c], a);
+      const double o = (beta == 0.0) ? alpha * a : fma(beta, y[r], alpha * a);
+      y[r] = o;
+      if (NRM) nrm = fma(o, o, nrm);
+    }
+  }
+  if (NRM) {
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double s = warp_sum(nrm);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t += red[i];
+      part[(int64_t)blockIdx.x * pstride + pcol] = t;
+    }
+  }
+}
+
+/* ---- elementwise n x k block kernels (blockIdx.y = column) ------------------------------------ */
+__global__ void __launch_bounds__(256) k_scale(double *__restrict__ X, int64_t ld, int64_t n, double alpha)
+{
+  double *x = X + (int64_t)blockIdx.y * ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] *= alpha;
+}
+__global__ void __launch_bounds__(256) k_scale_rsqrt(double *__restrict__ x, int64_t n, const double *__restrict__ sumsq)
+{
+  const double s = sumsq[0];
+  if (s == 0.0 || s == 1.0) return;
+  const double a = 1.0 / sqrt(s);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] *= a;
+}
+__global__ void __launch_bounds__(256) k_copy(double *__restrict__ Y, int64_t ldy, const double *__restrict__ X, int64_t ldx,
+                                               int64_t n)
+{
+  double *y = Y + (int64_t)blockIdx.y * ldy;
+  const double *x = X + (int64_t)blockIdx.y * ldx;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = x[r];
+}
+__global__ void __launch_bounds__(256) k_axpby(double *__restrict__ Y, int64_t ldy, const double *__restrict__ X, int64_t ldx,
+                                                int64_t n, double alpha, double beta)
+{
+  double *y = Y + (int64_t)blockIdx.y * ldy;
+  const double *x = X + (int64_t)blockIdx.y * ldx;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (beta == 0.0)
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = alpha * x[r];
+  else
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = fma(alpha, x[r], beta * y[r]);
+}
+__global__ void __launch_bounds__(256) k_fill(double *__restrict__ x, int64_t n, double v)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] = v;
+}
+/* splitmix64-finaliser hash → uniform [-1,1): identical to oracle/slepc_oracle.py:hash_uniform */
+__host__ __device__ __forceinline__ double b2k_hash_uniform(uint64_t idx, uint64_t seed)
+{
+  uint64_t x = (idx + 1ull) * 0x9E3779B97F4A7C15ull + seed * 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return 2.0 * ((double)(x >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+__global__ void __launch_bounds__(256) k_set_random(double *__restrict__ x, int64_t n, int64_t row0, uint64_t seed)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride)
+    x[r] = b2k_hash_uniform((uint64_t)(row0 + r), seed);
+}
+/* per-block partial of sum of squares of column blockIdx.y → part[blk][col] */
+__global__ void __launch_bounds__(256) k_sumsq(const double *__restrict__ X, int64_t ld, int64_t n, double *__restrict__ part,
+                                                int pstride)
+{
+  const double *x = X + (int64_t)blockIdx.y * ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) { const double v = x[r]; s = fma(v, v, s); }
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i];
+    part[(int64_t)blockIdx.x * pstride + blockIdx.y] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_colabssum(const double *__restrict__ X, int64_t ld, int64_t n, double *__restrict__ part,
+                                                    int pstride)
+{
+  const double *x = X + (int64_t)blockIdx.y * ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) s += fabs(x[r]);
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i];
+    part[(int64_t)blockIdx.x * pstride + blockIdx.y] = t;
+  }
+}
+/* out[0] = sum_c in[c] (single thread; tiny) */
+__global__ void k_sum_small(const double *__restrict__ in, int ncols, double *__restrict__ out)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int c = 0; c < ncols; c++) s += in[c];
+    out[0] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * tall-skinny GEMM  Out(n x nout) = beta*Out + alpha * In(n x kin) * Qe(kin x nout)
+ * with Qe(i,c) = Q[i + c*ldq] (qtrans=0) or Q[c + i*ldq] (qtrans=1).
+ * One CTA owns RB rows: it stages the whole RB x kin input tile in shared memory FIRST and only
+ * then writes its output columns, so Out may alias columns of In (BVMultInPlace, bvcuda.cu:65-112:
+ * no lda x (e-s) workspace, no cudaMemcpy2D copy-back → half the reference's traffic).
+ * Threads form a (RB/4) x 16 grid; each computes a 4 x 4 register tile of a 64-column output panel.
+ * ---------------------------------------------------------------------------------------------- */
+#define GEMM_KC 32
+template <int RB>
+__global__ void __launch_bounds__((RB / 4) * 16) k_gemm_ts(double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n,
+                                                           int kin, int nout, const double *__restrict__ Q, int ldq,
+                                                           int qtrans, double alpha, double beta)
+{
+  extern __shared__ double sm[];
+  double *Vs = sm;                    /* [kin][RB]      */
+  double *Qs = sm + (size_t)kin * RB; /* [GEMM_KC][64]  */
+  const int tr = threadIdx.x;         /* 0..RB/4-1 : row group   */
+  const int tc = threadIdx.y;         /* 0..15     : col group   */
+  const int tid = tc * (RB / 4) + tr;
+  const int nthr = (RB / 4) * 16;
+  const int64_t row0 = (int64_t)blockIdx.x * RB;
+
+  for (int idx = tid; idx < kin * RB; idx += nthr) {
+    const int i = idx / RB, r = idx - i * RB;
+    const int64_t gr = row0 + r;
+    Vs[idx] = (gr < n) ? In[(int64_t)i * ldi + gr] : 0.0;
+  }
+  for (int p0 = 0; p0 < nout; p0 += 64) {
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < kin; k0 += GEMM_KC) {
+      __syncthreads();
+      const int kc = min(GEMM_KC, kin - k0);
+      for (int idx = tid; idx < GEMM_KC * 64; idx += nthr) {
+        const int i = idx >> 6, c = idx & 63;
+        double v = 0.0;
+        if (i < kc && p0 + c < nout)
+          v = qtrans ? Q[(int64_t)(p0 + c) + (int64_t)(k0 + i) * ldq] : Q[(int64_t)(k0 + i) + (int64_t)(p0 + c) * ldq];
+        Qs[idx] = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int i = 0; i < kc; i++) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(&Vs[(size_t)(k0 + i) * RB + 4 * tr]);
+        const double2 a23 = *reinterpret_cast<const double2 *>(&Vs[(size_t)(k0 + i) * RB + 4 * tr + 2]);
+        const double2 b01 = *reinterpret_cast<const double2 *>(&Qs[i * 64 + 4 * tc]);
+        const double2 b23 = *reinterpret_cast<const double2 *>(&Qs[i * 64 + 4 * tc + 2]);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+          for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+      }
+    }
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+      const int c = p0 + 4 * tc + y;
+      if (c < nout) {
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const int64_t gr = row0 + 4 * tr + x;
+          if (gr < n) {
+            double *o = Out + (int64_t)c * ldo + gr;
+            *o = (beta == 0.0) ? alpha * acc[x][y] : fma(beta, *o, alpha * acc[x][y]);
+          }
+        }
+      }
+    }
+  }
+}
+
+/* =================================== host-side launchers ======================================== */
+int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, double *out)
+{
+  k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+static inline int grid_rows(b2k_ctx ctx, int64_t work_items, int per_sm)
+{
+  int64_t need = (work_items + 255) / 256;
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+static int launch_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *w, double *out, int with_ww)
+{
+  ARGCHK(k >= 0 && k <= B2K_MAX_K, "k out of range");
+  const int ncols = k + (with_ww ? 1 : 0);
+  if (ncols == 0) return B2K_OK;
+  if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(double) * ncols, ctx->stream)); return B2K_OK; }
+  const int CT = 16;
+  int ntiles = (k + CT - 1) / CT;
+  if (ntiles < 1) ntiles = 1;
+  const int ctile = (k + ntiles - 1) / ntiles > 0 ? (k + ntiles - 1) / ntiles : 1;
+  const bool vec2 = b2k_is_aligned16(V) && b2k_is_aligned16(w) && (ld % 2 == 0);
+  /* exactly one wave: 2 resident CTAs per SM (launch bounds), shared among the column tiles */
+  int64_t items = vec2 ? (n >> 1) : n;
+  int gx = (ctx->sm_count * 2) / ntiles;
+  if (gx < 1) gx = 1;
+  int64_t need = (items + 255) / 256;
+  if (need < 1) need = 1;
+  if (gx > need) gx = (int)need;
+  if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
+  const int pstride = ncols;
+  dim3 grid(gx, ntiles);
+  if (vec2) k_dotvec<16, true><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
+  else      k_dotvec<16, false><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
+  CKLAUNCH(ctx);
+  k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, pstride, ncols, out);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+extern "C" int b2k_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *y, double *q)
+{
+  return launch_dotvec(ctx, V, ld, n, k, y, q, 0);
+}
+extern "C" int b2k_gs_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *w, double *c)
+{
+  return launch_dotvec(ctx, V, ld, n, k, w, c, 1);
+}
+
+static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
+                          const double *q, double *nrm_out)
+{
+  ARGCHK(k >= 0 && k <= B2K_MAX_K, "k out of range");
+  if (n == 0) { if (nrm_out) CK(cudaMemsetAsync(nrm_out, 0, sizeof(double), ctx->stream)); return B2K_OK; }
+  const bool vec2 = b2k_is_aligned16(V) && b2k_is_aligned16(y) && (ld % 2 == 0);
+  const int64_t items = vec2 ? (n >> 1) : n;
+  int gx = grid_rows(ctx, items > 0 ? items : 1, 6);
+  if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
+  const size_t shm = sizeof(double) * (size_t)(k > 0 ? k : 1);
+  if (nrm_out) {
+    if (vec2) k_multvec<true, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
+    else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
+    CKLAUNCH(ctx);
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, gx, 1, 1, nrm_out);
+    CKLAUNCH(ctx);
+  } else {
+    if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
+    else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
+    CKLAUNCH(ctx);
+  }
+  return B2K_OK;
+}
+
+extern "C" int b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
+                           const double *q)
+{
+  return launch_multvec(ctx, V, ld, n, k, alpha, beta, y, q, nullptr);
+}
+
+int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                            double *cout);   /* b2k_gs_fused.cu */
+int b2k_gs_fused_enabled(void);
+
+extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                                 double *cout)
+{
+  if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
+    int rc = b2k_gs_update_dot_fused(ctx, V, ld, n, k, w, cin, cout);
+    if (rc != -1) return rc;       /* -1: shape not supported by the fused kernel → two-sweep path */
+  }
+  /* two-sweep path: update sweep, then dot sweep (V read twice) */
+  int rc = launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nullptr);
+  if (rc) return rc;
+  return launch_dotvec(ctx, V, ld, n, k, w, cout, 1);
+}
+
+extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out)
+{
+  ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
+  if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream)); return B2K_OK; }
+  int gx = grid_rows(ctx, n, 4);
+  if ((int64_t)gx * k > (int64_t)ctx->sm_count * 8) gx = (ctx->sm_count * 8 + k - 1) / k;
+  if (gx < 1) gx = 1;
+  if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
+  dim3 grid(gx, k);
+  k_sumsq<<<grid, 256, 0, ctx->stream>>>(X, ld, n, ctx->partials, k);
+  CKLAUNCH(ctx);
+  double *tmp = ctx->dscratch;           /* per-column sums */
+  k_reduce_partials<<<(k + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, k, k, tmp);
+  CKLAUNCH(ctx);
+  k_sum_small<<<1, 32, 0, ctx->stream>>>(tmp, k, out);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+extern "C" int b2k_colabssum(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out_k)
+{
+  ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
+  if (n == 0) { CK(cudaMemsetAsync(out_k, 0, sizeof(double) * k, ctx->stream)); return B2K_OK; }
+  int gx = grid_rows(ctx, n, 4);
+  if ((int64_t)gx * k > (int64_t)ctx->sm_count * 8) gx = (ctx->sm_count * 8 + k - 1) / k;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, k);
+  k_colabssum<<<grid, 256, 0, ctx->stream>>>(X, ld, n, ctx->partials, k);
+  CKLAUNCH(ctx);
+  k_reduce_partials<<<(k + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, k, k, out_k);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+static inline dim3 grid2d(b2k_ctx ctx, int64_t n, int k)
+{
+  int64_t need = (n + 255) / 256;
+  int64_t cap = ((int64_t)ctx->sm_count * 8 + k - 1) / k;
+  if (cap < 1) cap = 1;
+  if (need < 1) need = 1;
+  return dim3((unsigned)(need < cap ? need : cap), (unsigned)k);
+}
+
+extern "C" int b2k_scale(b2k_ctx ctx, double *X, int64_t ld, int64_t n, int k, double alpha)
+{
+  if (n == 0 || k == 0) return B2K_OK;
+  if (alpha == 0.0) {   /* bvcuda.cu:277: memset */
+    CK(cudaMemset2DAsync(X, ld * sizeof(double), 0, n * sizeof(double), k, ctx->stream));
+    return B2K_OK;
+  }
+  k_scale<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(X, ld, n, alpha);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq)
+{
+  if (n == 0) return B2K_OK;
+  k_scale_rsqrt<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, sumsq);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_copy(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int k)
+{
+  if (n == 0 || k == 0) return B2K_OK;
+  k_copy<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(Y, ldy, X, ldx, n);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_axpby(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int k, double alpha,
+                         double beta)
+{
+  if (n == 0 || k == 0) return B2K_OK;
+  k_axpby<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(Y, ldy, X, ldx, n, alpha, beta);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_fill(b2k_ctx ctx, double *x, int64_t n, double v)
+{
+  if (n == 0) return B2K_OK;
+  k_fill<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, v);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_set_random(b2k_ctx ctx, double *x, int64_t n, int64_t row0, uint64_t seed)
+{
+  if (n == 0) return B2K_OK;
+  k_set_random<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, row0, seed);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout,
+                          const double *Q, int ldq, int qtrans, double alpha, double beta)
+{
+  if (n == 0 || nout == 0) return B2K_OK;
+  ARGCHK(kin >= 0 && kin <= 2048, "kin out of range");
+  if (kin == 0) return b2k_scale(ctx, Out, ldo, n, nout, beta);
+  const size_t qbytes = sizeof(double) * GEMM_KC * 64;
+  const size_t lim = 200 * 1024;
+#define LAUNCH_GEMM(RB)                                                                                         \
+  do {                                                                                                          \
+    const size_t shm = sizeof(double) * (size_t)kin * RB + qbytes;                                              \
+    CK(cudaFuncSetAttribute(k_gemm_ts<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));             \
+    dim3 blk(RB / 4, 16);                                                                                       \
+    const int64_t gx = (n + RB - 1) / RB;                                                                       \
+    k_gemm_ts<RB><<<(unsigned)gx, blk, shm, ctx->stream>>>(Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta); \
+    CKLAUNCH(ctx);                                                                                              \
+  } while (0)
+  if (sizeof(double) * (size_t)kin * 64 + qbytes <= 96 * 1024) LAUNCH_GEMM(64);
+  else if (sizeof(double) * (size_t)kin * 32 + qbytes <= lim) LAUNCH_GEMM(32);
+  else if (sizeof(double) * (size_t)kin * 8 + qbytes <= lim) LAUNCH_GEMM(8);
+  else { b2k_set_error("b2k gemm: kin=%d too large for the shared-memory row tile", kin); return B2K_ERR_ARG; }
+#undef LAUNCH_GEMM
+  return B2K_OK;
+}
+
+extern "C" int b2k_mult(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx, double alpha,
+                        double beta, const double *Q, int ldq)
+{
+  return launch_gemm_ts(ctx, Y, ldy, X, ldx, n, kx, ky, Q, ldq, 0, alpha, beta);
+}
+
+extern "C" int b2k_mult_inplace(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, int s, int e, const double *Q, int ldq,
+                                int trans)
+{
+  ARGCHK(s >= 0 && e >= s, "bad column range");
+  if (e == s) return B2K_OK;
+  const double *Qb = trans ? Q + s : Q + (int64_t)s * ldq;
+  return launch_gemm_ts(ctx, V + (int64_t)s * ld, ld, V, ld, n, k, e - s, Qb, ldq, trans, 1.0, 0.0);
+}
+
+extern "C" int b2k_dot(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx, double *M,
+                       int ldm)
+{
+  /* M(:,j) = Y^T X(:,j): kx fused-reduction sweeps (not on the Krylov hot path; tests + block GS) */
+  for (int j = 0; j < kx; j++) {
+    int rc = launch_dotvec(ctx, Y, ldy, n, ky, X + (int64_t)j * ldx, M + (int64_t)j * ldm, 0);
+    if (rc) return rc;
+  }
+  return B2K_OK;
+}

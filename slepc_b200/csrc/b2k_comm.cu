@@ -1,0 +1,177 @@
+/*
+ * b2k_comm.cu — row-partition communicator over NCCL / NVLink.
+ * Replaces the MPI layer the reference uses on this path:
+ *   MPIU_Allreduce of the k-vector per Gram-Schmidt pass   bvcuda.cu:228-248 (host-staged there),
+ *   MPIU_LAPY2 norm reduction                              bvlapack.c:50,
+ *   PETSc VecScatter halo exchange inside MatMult_MPIAIJ   (PETSc, reached from bvops.c:879).
+ * One process per GPU; the process group rendezvous (exchange of the NCCL unique id) is done by
+ * the caller, normally torch.distributed in slepc_b200/dist.py.  NCCL is resolved at run time with
+ * dlopen so that the library also loads on a box without NCCL (the symbol test on CPU).
+ */
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b2k_internal.h"
+
+/* minimal NCCL ABI (stable since 2.x): enough to avoid a build-time dependency on nccl.h */
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
+
+struct nccl_api {
+  void *h;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)(void);
+  ncclResult_t (*GroupEnd)(void);
+  const char *(*GetErrorString)(ncclResult_t);
+};
+static nccl_api g_nccl;
+
+static int load_nccl(void)
+{
+  if (g_nccl.h) return B2K_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", NULL};
+  void *h = NULL;
+  const char *env = getenv("B2K_NCCL_LIB");
+  if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  for (int i = 0; !h && names[i]; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { b2k_set_error("cannot dlopen libnccl.so.2 (set B2K_NCCL_LIB): %s", dlerror()); return B2K_ERR_COMM; }
+#define SYM(field, name)                                                               \
+  do {                                                                                 \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                        \
+    if (!g_nccl.field) { b2k_set_error("NCCL symbol %s missing", name); return B2K_ERR_COMM; } \
+  } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(ReduceScatter, "ncclReduceScatter");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.h = h;
+  return B2K_OK;
+}
+
+#define NK(call)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != 0) {                                                                                \
+      b2k_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_));     \
+      return B2K_ERR_COMM;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+struct b2k_comm_s {
+  b2k_ctx    ctx;
+  int        rank, size;
+  ncclComm_t nccl;
+};
+
+extern "C" int b2k_comm_unique_id(void *id_host)
+{
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(id_host, &id, sizeof(id));
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_create(b2k_ctx ctx, int rank, int size, const void *id_host, b2k_comm *out)
+{
+  ARGCHK(size >= 1 && rank >= 0 && rank < size, "bad rank/size");
+  b2k_comm c = (b2k_comm)calloc(1, sizeof(*c));
+  if (!c) return B2K_ERR_MEM;
+  c->ctx = ctx; c->rank = rank; c->size = size; c->nccl = NULL;
+  if (size > 1) {
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id_host, sizeof(id));
+    CK(cudaSetDevice(ctx->device));
+    NK(g_nccl.CommInitRank(&c->nccl, size, id, rank));
+  }
+  *out = c;
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_destroy(b2k_comm c)
+{
+  if (!c) return B2K_OK;
+  if (c->nccl) { cudaStreamSynchronize(c->ctx->stream); g_nccl.CommDestroy(c->nccl); }
+  free(c);
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_rank(b2k_comm c, int *rank, int *size)
+{
+  if (rank) *rank = c ? c->rank : 0;
+  if (size) *size = c ? c->size : 1;
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_allreduce_sum(b2k_comm c, double *buf, int count)
+{
+  if (!c || c->size == 1 || count == 0) return B2K_OK;
+  NK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, c->nccl, c->ctx->stream));
+  return B2K_OK;
+}
+extern "C" int b2k_comm_allreduce_max(b2k_comm c, double *buf, int count)
+{
+  if (!c || c->size == 1 || count == 0) return B2K_OK;
+  NK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclMax, c->nccl, c->ctx->stream));
+  return B2K_OK;
+}
+extern "C" int b2k_comm_group_start(b2k_comm c) { if (c && c->size > 1) NK(g_nccl.GroupStart()); return B2K_OK; }
+extern "C" int b2k_comm_group_end(b2k_comm c) { if (c && c->size > 1) NK(g_nccl.GroupEnd()); return B2K_OK; }
+
+extern "C" int b2k_comm_sendrecv(b2k_comm c, const double *sendbuf, int64_t nsend, int send_peer, double *recvbuf, int64_t nrecv,
+                                 int recv_peer)
+{
+  if (!c || c->size == 1) return B2K_OK;
+  if (nsend > 0) NK(g_nccl.Send(sendbuf, (size_t)nsend, ncclFloat64, send_peer, c->nccl, c->ctx->stream));
+  if (nrecv > 0) NK(g_nccl.Recv(recvbuf, (size_t)nrecv, ncclFloat64, recv_peer, c->nccl, c->ctx->stream));
+  return B2K_OK;
+}
+extern "C" int b2k_comm_allgather(b2k_comm c, const double *sendbuf, double *recvbuf, int64_t cnt)
+{
+  if (!c || c->size == 1) {
+    if (sendbuf != recvbuf && cnt) CK(cudaMemcpyAsync(recvbuf, sendbuf, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToDevice,
+                                                      c ? c->ctx->stream : 0));
+    return B2K_OK;
+  }
+  NK(g_nccl.AllGather(sendbuf, recvbuf, (size_t)cnt, ncclFloat64, c->nccl, c->ctx->stream));
+  return B2K_OK;
+}
+extern "C" int b2k_comm_reduce_scatter_sum(b2k_comm c, const double *sendbuf, double *recvbuf, int64_t cnt)
+{
+  if (!c || c->size == 1) {
+    if (sendbuf != recvbuf && cnt) CK(cudaMemcpyAsync(recvbuf, sendbuf, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToDevice,
+                                                      c ? c->ctx->stream : 0));
+    return B2K_OK;
+  }
+  NK(g_nccl.ReduceScatter(sendbuf, recvbuf, (size_t)cnt, ncclFloat64, ncclSum, c->nccl, c->ctx->stream));
+  return B2K_OK;
+}
+extern "C" int b2k_comm_barrier(b2k_comm c)
+{
+  if (!c || c->size == 1) return B2K_OK;
+  int rc = b2k_comm_allreduce_sum(c, c->ctx->dscratch + (c->ctx->dscratch_elems - 1), 1);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->ctx->stream));
+  return B2K_OK;
+}
