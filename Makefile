@@ -18,7 +18,10 @@ HSRC      := $(wildcard slepc_b200/host/*.c)
 HHDR      := $(wildcard slepc_b200/host/*.h) include/b2kslepc.h include/b2k.h
 OSRC      := $(wildcard oracle/*.c)
 
-all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so oracle/_build/liboraclecpu.so
+ifneq ($(strip $(OSRC)),)
+ORACLE_LIB := oracle/_build/liboraclecpu.so
+endif
+all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so $(ORACLE_LIB)
 
 $(LIBDIR)/libb200krylov.so: $(KSRC) $(KHDR)
 	@mkdir -p $(LIBDIR)
@@ -30,7 +33,7 @@ $(LIBDIR)/libb2kslepc.so: $(HSRC) $(HHDR) $(LIBDIR)/libb200krylov.so
 
 oracle/_build/liboraclecpu.so: $(OSRC) $(HHDR) $(LIBDIR)/libb2kslepc.so
 	@mkdir -p oracle/_build
-	$(CC) $(CFLAGS) -O3 -march=x86-64-v3 -fopenmp -shared -o $@ $(OSRC) -L$(LIBDIR) -lb2kslepc \
+	$(CC) $(CFLAGS) -O3 -march=x86-64-v3 -fopenmp -B/usr/lib/gcc/x86_64-linux-gnu/13/ -shared -o $@ $(OSRC) -L$(LIBDIR) -lb2kslepc \
 	    -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' $(OPENBLAS) -Wl,-rpath,$(OPENBLAS_DIR) -lm
 
 kernels: $(LIBDIR)/libb200krylov.so

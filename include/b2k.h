@@ -102,6 +102,10 @@ int  b2k_gs_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, cons
    with the dot sweep of pass p+1 (DGKS refinement) and with the explicit norm: V is read ONCE  */
 int  b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w,
                        const double *cin, double *cout);
+/* w -= V(:,0:k) cin ; nrm2_out[0] = ||w_new||^2 — update sweep with the explicit norm of bvorthog.c:126
+   folded in (used when no refinement pass is expected)                                              */
+int  b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w,
+                        const double *cin, double *nrm2_out);
 /* x *= 1/sqrt(sumsq[0]) guarded (no-op if sumsq is 0 or 1): normalisation with the norm still on
    the device                                  — BVOrthonormalizeColumn bvorthog.c:417-422        */
 int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
@@ -118,6 +122,8 @@ int  b2k_csr_adopt(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t ngho
                    int *rowptr, int *colidx, double *val, b2k_csr *A);
 int  b2k_csr_destroy(b2k_ctx ctx, b2k_csr A);
 int  b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncols_local, int64_t *nghost, int64_t *nnz);
+/* device pointers of the CSR arrays (owned by A)                                                    */
+int  b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val);
 /* y = A [x ; xghost]                                                                               */
 int  b2k_csr_spmv(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y);
 /* y = A x - sigma*xdiag   (shifted operator of STSHIFT, shift.c:79; xdiag = x rows owned here)    */

@@ -53,12 +53,14 @@ SIGNATURES = {
     "b2k_fill": [c_vp, c_vp, c_i64, c_dbl],
     "b2k_gs_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     "b2k_gs_update_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
+    "b2k_gs_update_norm": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
     "b2k_scale_rsqrt": [c_vp, c_vp, c_i64, c_vp],
     "b2k_gs_set_fused": [c_int],
     "b2k_csr_create": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_adopt": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_destroy": [c_vp, c_vp],
     "b2k_csr_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "b2k_csr_arrays": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)],
     "b2k_csr_spmv": [c_vp, c_vp, c_vp, c_vp, c_vp],
     "b2k_csr_spmv_shift": [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl],
     "b2k_csr_laplacian": [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),

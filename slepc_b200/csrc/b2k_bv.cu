@@ -481,6 +481,13 @@ extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64
   return launch_dotvec(ctx, V, ld, n, k, w, cout, 1);
 }
 
+/* w -= V cin ; out[0] = ||w_new||^2 : the update sweep with the explicit norm folded in (one read of V) */
+extern "C" int b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                                  double *nrm2_out)
+{
+  return launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nrm2_out);
+}
+
 extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out)
 {
   ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");

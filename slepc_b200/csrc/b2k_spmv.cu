@@ -172,6 +172,14 @@ extern "C" int b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncl, int64_t *ng
   return B2K_OK;
 }
 
+extern "C" int b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val)
+{
+  if (rowptr) *rowptr = A->rowptr;
+  if (colidx) *colidx = A->colidx;
+  if (val) *val = A->val;
+  return B2K_OK;
+}
+
 extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y, double sigma)
 {
   if (A->nrows == 0) return B2K_OK;

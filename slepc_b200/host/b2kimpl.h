@@ -63,6 +63,7 @@ struct _p_B2KComm {
 /* ---- Vec / Mat ------------------------------------------------------------------------------------ */
 struct _p_Vec {
   PetscInt     n, N;
+  PetscInt     rstart;     /* global index of the first local entry (PetscLayout rstart) */
   B2KMemType   mem;
   PetscScalar *array;
   PetscScalar *saved;      /* VecPlaceArray / VecResetArray */
@@ -114,7 +115,7 @@ typedef struct _BVOps {
   PetscErrorCode (*destroy)(BV);
   /* extensions of this build (NULL is always allowed) */
   PetscErrorCode (*setrandomcolumn)(BV, PetscInt);        /* deterministic hash fill          */
-  PetscErrorCode (*vecnorm2)(BV, Vec, PetscReal *);       /* ||v||_2, collective               */
+  PetscErrorCode (*duplicate)(BV, BV);                    /* bvimpl.h:56                      */
 } BVOps;
 
 struct _p_BV {
@@ -140,10 +141,19 @@ struct _p_BV {
   uint64_t           state;         /* PetscObjectState stand-in           */
   int64_t            n_gs_passes, n_matmult;
   PetscBool          sizes_set, type_set;
+  PetscErrorCode   (*ctor)(BV);   /* constructor deferred until the sizes are known (bvbasic.c:56-62) */
+  PetscScalar       *work;        /* BVAllocateWork_Private (bvfunc.c:654) */
+  size_t             lwork;
   void              *data;
 };
 #define BV_BUF(bv, i, j) ((bv)->buffer[(size_t)(i) + (size_t)(j) * ((bv)->nc + (bv)->m)])
 PetscErrorCode BVCreate_B200(BV bv);
+/* h += c on rows 0..nc+j-1 (NULL = the buffer: column j += column 0) — BV_AddCoefficients bvimpl.h:308-322 */
+static inline void BV_AddCoefficients(BV bv, PetscInt j, PetscScalar *h, PetscScalar *c)
+{
+  if (!h) { h = bv->buffer + (size_t)j * (size_t)(bv->nc + bv->m); c = bv->buffer; }
+  for (PetscInt i = 0; i < bv->nc + j; i++) h[i] += c[i];
+}
 
 /* ---- DS -------------------------------------------------------------------------------------------- */
 struct _p_DS {
@@ -196,7 +206,11 @@ struct _p_EPS {
   PetscBool    started;
   EPSMonitorFn monitor;
   void        *monitorctx;
-  Vec          work[3];
+  Vec          work[5];
+  PetscBool    solved;
+  PetscInt     allocated;        /* size of eigr/eigi/errest/perm */
+  struct { SlepcEigenvalueComparisonFn fn; void *ctx; PetscScalar sigma; } sc;   /* SlepcSC with map = STBackTransform */
+  int64_t      n_restarts_bv, n_dssolve;
 };
 
 /* ---- SVD ------------------------------------------------------------------------------------------- */
@@ -215,7 +229,10 @@ struct _p_SVD {
   PetscInt     nconv, its;
   SVDConvergedReason reason;
   Vec          iniV, iniU;
-  PetscBool    setup_done;
+  PetscBool    setup_done, solved, started;
+  PetscInt     l;                /* state of a solve in progress */
+  PetscInt     allocated;
+  Vec          work[4];
 };
 
 /* helpers shared between the files */

@@ -1,0 +1,427 @@
+/*
+ * bvb200.c — BV type "b200": the basis lives in HBM as one column-major n x (nc+m) array
+ * (the layout of BVSVEC, src/sys/classes/bv/impls/svec/svec.c:397-563) and every ops-table slot is
+ * a short shim over the sm_100a kernels of libb200krylov (include/b2k.h), the way
+ * impls/svec/sveccuda/sveccuda.cu:18-499 shims cuBLAS.  Differences from the reference's CUDA BV:
+ *   - the `gramschmidt` slot (bvimpl.h:53) is filled: one classical GS pass = ONE reduction sweep
+ *     (V^T w and w^T w together) + ONE update sweep that already emits ||w_new||^2 and, when a DGKS
+ *     refinement is expected, the next pass' V^T w_new, so a refined orthogonalisation reads V three
+ *     times instead of four and needs one host synchronisation per pass instead of 3 blocking 8-byte
+ *     copies + 5 micro-kernels (bvcuda.cu:345-548);
+ *   - coefficients are reduced across GPUs on the device (NCCL) and land in pinned host memory with a
+ *     single copy; no per-call cudaMalloc (bvcuda.cu:217,231,90-92);
+ *   - BVMultInPlace runs in place (no lda x (e-s) workspace + cudaMemcpy2D, bvcuda.cu:90-94).
+ */
+#include "b2kimpl.h"
+
+typedef struct {
+  double  *V;            /* device: (nc+m) columns of ld doubles                                  */
+  double  *dco;          /* device coefficient staging: 4 slots of `slot` doubles                 */
+  double  *hco;          /* pinned host mirror of dco                                             */
+  PetscInt slot;
+  double  *dQ;           /* device scratch for small dense blocks (Q, M)                          */
+  size_t   dQ_elems;
+  double  *hQ;           /* host staging for compacted Q blocks                                   */
+  /* second-pass cache filled by the fused update sweep */
+  PetscBool pend_valid;
+  PetscInt  pend_j;
+  uint64_t  pend_state;
+  PetscReal pend_nrm2;
+  double   *pend_c;      /* host copy of V^T w_new                                                */
+  int       fuse_mode;   /* 0 never, 1 always, 2 adaptive (env B2K_BV_FUSE)                       */
+  PetscBool expect_refine;
+  PetscInt  last_j;      /* column and state of the last uncached pass: a repeat means DGKS refined  */
+  uint64_t  last_state;
+} BV_B200;
+
+#define CTX() B2KGetContext()
+#define COL(bv, d, j) ((d)->V + (size_t)((bv)->nc + (j)) * (size_t)(bv)->ld)
+#define SLOT(d, i) ((d)->dco + (size_t)(i) * (size_t)(d)->slot)
+#define HSLOT(d, i) ((d)->hco + (size_t)(i) * (size_t)(d)->slot)
+
+static PetscErrorCode BVAllocScratch_B200(BV bv, BV_B200 *d)
+{
+  b2k_ctx ctx = CTX();
+  const PetscInt cols = bv->nc + bv->m;
+  d->slot = (cols + 9) & ~1;
+  B2KCall(b2k_malloc(ctx, (void **)&d->dco, sizeof(double) * 4 * (size_t)d->slot));
+  B2KCall(b2k_memset0(ctx, d->dco, sizeof(double) * 4 * (size_t)d->slot));
+  B2KCall(b2k_host_alloc((void **)&d->hco, sizeof(double) * 4 * (size_t)d->slot));
+  d->dQ_elems = (size_t)cols * (size_t)cols + 16;
+  B2KCall(b2k_malloc(ctx, (void **)&d->dQ, sizeof(double) * d->dQ_elems));
+  d->hQ = (double *)malloc(sizeof(double) * d->dQ_elems);
+  d->pend_c = (double *)calloc((size_t)cols + 2, sizeof(double));
+  PetscCheck(d->hQ && d->pend_c, PETSC_ERR_MEM, "out of memory");
+  d->pend_valid = PETSC_FALSE;
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVFreeScratch_B200(BV_B200 *d)
+{
+  b2k_ctx ctx = CTX();
+  if (ctx) { b2k_free(ctx, d->dco); b2k_free(ctx, d->dQ); }
+  b2k_host_free(d->hco);
+  free(d->hQ); free(d->pend_c);
+  d->dco = d->dQ = d->hco = d->hQ = d->pend_c = NULL;
+  return PETSC_SUCCESS;
+}
+
+/* sum over ranks of `count` doubles in slot memory, then bring them to the pinned mirror and wait */
+static PetscErrorCode BVFetch_B200(BV bv, BV_B200 *d, double *dptr, PetscInt count, PetscBool reduce, double **hptr)
+{
+  b2k_ctx ctx = CTX();
+  if (reduce) PetscCall(B2KCommAllreduce(bv->comm, dptr, count, 0, B2K_MEM_DEVICE));
+  double *hp = d->hco + (dptr - d->dco);
+  B2KCall(b2k_d2h_async(ctx, hp, dptr, sizeof(double) * (size_t)count));
+  B2KCall(b2k_ctx_sync(ctx));
+  *hptr = hp;
+  return PETSC_SUCCESS;
+}
+
+/* ---- dotvec / multvec: svec.c:38-52,109-129, sveccuda.cu:45-69,126-143 --------------------------- */
+static PetscErrorCode BVDotVec_B200_Private(BV X, Vec y, PetscScalar *q, PetscBool reduce)
+{
+  BV_B200 *d = (BV_B200 *)X->data;
+  const PetscInt k = X->k - X->l;
+  PetscScalar *qq = q ? q : X->buffer;
+  if (k <= 0) return PETSC_SUCCESS;
+  PetscCheck(y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors");
+  B2KCall(b2k_dotvec(CTX(), COL(X, d, X->l), X->ld, X->n, k, y->array, SLOT(d, 0)));
+  double *hp;
+  PetscCall(BVFetch_B200(X, d, SLOT(d, 0), k, reduce, &hp));
+  memcpy(qq, hp, sizeof(double) * (size_t)k);
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVDotVec_B200(BV X, Vec y, PetscScalar *q) { return BVDotVec_B200_Private(X, y, q, PETSC_TRUE); }
+static PetscErrorCode BVDotVec_Local_B200(BV X, Vec y, PetscScalar *q) { return BVDotVec_B200_Private(X, y, q, PETSC_FALSE); }
+
+static PetscErrorCode BVMultVec_B200(BV X, PetscScalar alpha, PetscScalar beta, Vec y, PetscScalar *q)
+{
+  BV_B200 *d = (BV_B200 *)X->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt k = X->k - X->l;
+  const PetscScalar *qq = q ? q : X->buffer;
+  PetscCheck(y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors");
+  if (k > 0) B2KCall(b2k_h2d_async(ctx, SLOT(d, 2), qq, sizeof(double) * (size_t)k));   /* pageable source: staged before return */
+  B2KCall(b2k_multvec(ctx, COL(X, d, X->l), X->ld, X->n, k > 0 ? k : 0, alpha, beta, y->array, SLOT(d, 2)));
+  return PETSC_SUCCESS;
+}
+
+/* ---- the fused Gram-Schmidt pass: replaces BVOrthogonalizeCGS1 (bvorthog.c:91-132) ------------------ */
+static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *which, PetscScalar *h, PetscScalar *c, PetscReal *onorm,
+                                         PetscReal *norm)
+{
+  (void)which;
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt kk = bv->nc + j;                 /* columns to project against: physical 0..kk-1 (l = -nc) */
+  PetscScalar *cc = c ? c : bv->buffer;
+  double *w, *hp;
+  if (v) { PetscCheck(v->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors"); w = v->array; }
+  else w = COL(bv, d, j);
+  bv->k = j;                                      /* as bvorthog.c:99 */
+
+  if (kk == 0) {                                  /* nothing to project: only the norm */
+    if (onorm || norm) {
+      PetscReal beta;
+      B2KCall(b2k_sumsq(ctx, w, bv->ld, bv->n, 1, SLOT(d, 0)));
+      PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 1, PETSC_TRUE, &hp));
+      beta = sqrt(hp[0]);
+      if (onorm) *onorm = beta;
+      if (norm) *norm = beta;
+    }
+    return PETSC_SUCCESS;
+  }
+
+  if (!v && d->pend_valid && d->pend_j == j && d->pend_state == bv->state) {
+    /* refinement pass: V^T w and ||w||^2 of the CURRENT w came out of the previous fused sweep */
+    d->pend_valid = PETSC_FALSE;
+    d->expect_refine = PETSC_TRUE;
+    memcpy(cc, d->pend_c, sizeof(double) * (size_t)kk);
+    const PetscReal beta2 = d->pend_nrm2;
+    const PetscBool need_norm = norm ? PETSC_TRUE : PETSC_FALSE;
+    if (need_norm) {
+      B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 1), SLOT(d, 3)));   /* c2 still sits in slot 1 */
+      PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, &hp));
+      *norm = sqrt(hp[0]);
+    } else {
+      B2KCall(b2k_multvec(ctx, d->V, bv->ld, bv->n, kk, -1.0, 1.0, w, SLOT(d, 1)));
+    }
+    if (onorm) *onorm = sqrt(beta2 > 0.0 ? beta2 : 0.0);
+    BV_AddCoefficients(bv, j, h, c);
+    return PETSC_SUCCESS;
+  }
+  if (d->pend_valid) d->expect_refine = PETSC_FALSE;   /* the cached second pass was never asked for */
+  d->pend_valid = PETSC_FALSE;
+  const PetscBool repeat = (!v && d->last_j == j && d->last_state == bv->state) ? PETSC_TRUE : PETSC_FALSE;
+  if (repeat) d->expect_refine = PETSC_TRUE;           /* refinement happened although we did not prepare for it */
+  d->last_j = v ? -1 : j; d->last_state = bv->state;
+
+  /* sweep 1: c = V^T w and w^T w in one reduction (BVDotColumnInc bvorthog.c:32-47) */
+  B2KCall(b2k_gs_dot(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0)));
+  PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0), kk + 1, 0, B2K_MEM_DEVICE));
+  const PetscBool fuse = (!v && !repeat && (d->fuse_mode == 1 || (d->fuse_mode == 2 && (d->expect_refine || bv->orthog_ref == BV_ORTHOG_REFINE_ALWAYS)))) ? PETSC_TRUE : PETSC_FALSE;
+  if (fuse) {
+    /* sweep 2: w -= V c, and from the same read of V the next pass' V^T w_new and ||w_new||^2 */
+    B2KCall(b2k_gs_update_dot(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 1)));
+    PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 1), kk + 1, 0, B2K_MEM_DEVICE));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 2 * d->slot, PETSC_FALSE, &hp));
+    memcpy(d->pend_c, hp + d->slot, sizeof(double) * (size_t)(kk + 1));
+    d->pend_nrm2 = hp[d->slot + kk];
+    d->pend_j = j; d->pend_state = bv->state; d->pend_valid = PETSC_TRUE;
+  } else {
+    /* sweep 2: w -= V c with the explicit ||w_new||^2 folded in */
+    B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 0) + kk + 1));
+    PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0) + kk + 1, 1, 0, B2K_MEM_DEVICE));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), kk + 2, PETSC_FALSE, &hp));
+    d->pend_nrm2 = hp[kk + 1];
+  }
+  memcpy(cc, hp, sizeof(double) * (size_t)kk);
+  if (!c) cc[kk] = hp[kk];                        /* the buffer keeps (w,w) next to the coefficients, bvorthog.c:40 */
+  if (onorm || norm) {
+    const PetscReal deftol = 10 * PETSC_MACHINE_EPSILON;
+    PetscCheck(hp[kk] > -deftol, PETSC_ERR_FP, "The inner product is not well defined: indefinite matrix %g", hp[kk]);   /* BV_SafeSqrt */
+    if (onorm) *onorm = sqrt(hp[kk] > 0.0 ? hp[kk] : 0.0);
+    if (norm) *norm = sqrt(d->pend_nrm2 > 0.0 ? d->pend_nrm2 : 0.0);   /* explicit, not the beta^2 - sum c^2 estimate of :124 */
+  }
+  BV_AddCoefficients(bv, j, h, c);
+  return PETSC_SUCCESS;
+}
+
+/* ---- scale / norm / normalize: svec.c:150-175, sveccuda.cu:164-214, bvglobal.c:836 ----------------- */
+static PetscErrorCode BVScale_B200(BV bv, PetscInt j, PetscScalar alpha)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  if (j < 0) B2KCall(b2k_scale(CTX(), COL(bv, d, bv->l), bv->ld, bv->n, bv->k - bv->l, alpha));
+  else B2KCall(b2k_scale(CTX(), COL(bv, d, j), bv->ld, bv->n, 1, alpha));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVNorm_B200_Private(BV bv, PetscInt j, NormType type, PetscReal *val, PetscBool reduce)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  const double *X = (j < 0) ? COL(bv, d, bv->l) : COL(bv, d, j);
+  const PetscInt k = (j < 0) ? bv->k - bv->l : 1;
+  double *hp;
+  if (k <= 0) { *val = 0.0; return PETSC_SUCCESS; }
+  if (type == NORM_2 || type == NORM_FROBENIUS) {
+    B2KCall(b2k_sumsq(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, reduce, &hp));
+    *val = sqrt(hp[0]);
+  } else if (type == NORM_1) {
+    B2KCall(b2k_colabssum(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), k, reduce, &hp));
+    PetscReal mx = 0.0;
+    for (PetscInt i = 0; i < k; i++) mx = PetscMax(mx, hp[i]);
+    *val = mx;
+  } else SETERRQ(PETSC_ERR_SUP, "NORM_INFINITY is not implemented for BV type b200 (not on the Krylov path)");
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVNorm_B200(BV bv, PetscInt j, NormType type, PetscReal *val) { return BVNorm_B200_Private(bv, j, type, val, PETSC_TRUE); }
+static PetscErrorCode BVNorm_Local_B200(BV bv, PetscInt j, NormType type, PetscReal *val) { return BVNorm_B200_Private(bv, j, type, val, PETSC_FALSE); }
+
+static PetscErrorCode BVNormalize_B200(BV bv, PetscScalar *eigi)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  double *hp;
+  for (PetscInt i = bv->l; i < bv->k; i++) {
+    const PetscInt cols = (eigi && eigi[i] != 0.0 && i + 1 < bv->k) ? 2 : 1;   /* complex conjugate pair stored as two columns */
+    B2KCall(b2k_sumsq(ctx, COL(bv, d, i), bv->ld, bv->n, cols, SLOT(d, 3)));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, &hp));
+    const PetscReal nrm = sqrt(hp[0]);
+    if (nrm != 0.0 && nrm != 1.0) B2KCall(b2k_scale(ctx, COL(bv, d, i), bv->ld, bv->n, cols, 1.0 / nrm));
+    i += cols - 1;
+  }
+  return PETSC_SUCCESS;
+}
+
+/* ---- level-3: svec.c:17-36,54-107, sveccuda.cu:18-124 ---------------------------------------------- */
+static PetscErrorCode BVUploadBlock_B200(BV_B200 *d, const PetscScalar *Q, PetscInt ldq, PetscInt r0, PetscInt c0, PetscInt nr, PetscInt ncol)
+{
+  PetscCheck((size_t)nr * (size_t)ncol <= d->dQ_elems, PETSC_ERR_ARG_SIZ, "dense block %d x %d larger than the scratch area", nr, ncol);
+  for (PetscInt cidx = 0; cidx < ncol; cidx++)
+    memcpy(d->hQ + (size_t)cidx * (size_t)nr, Q + (size_t)(c0 + cidx) * (size_t)ldq + r0, sizeof(double) * (size_t)nr);
+  if (nr * ncol > 0) B2KCall(b2k_h2d_async(CTX(), d->dQ, d->hQ, sizeof(double) * (size_t)nr * (size_t)ncol));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVMult_B200(BV Y, PetscScalar alpha, PetscScalar beta, BV X, Mat Q)
+{
+  BV_B200 *y = (BV_B200 *)Y->data, *x = (BV_B200 *)X->data;
+  const PetscInt ky = Y->k - Y->l, kx = X->k - X->l;
+  if (ky <= 0) return PETSC_SUCCESS;
+  if (!Q) {                                       /* BVAXPY bvblas.c:112 */
+    B2KCall(b2k_axpby(CTX(), COL(Y, y, Y->l), Y->ld, COL(X, x, X->l), X->ld, Y->n, ky, alpha, beta));
+    return PETSC_SUCCESS;
+  }
+  PetscCall(BVUploadBlock_B200(y, Q->dense, Q->lda, X->l, Y->l, kx, ky));   /* rows from X->l, columns from Y->l: svec.c:29 */
+  B2KCall(b2k_mult(CTX(), COL(Y, y, Y->l), Y->ld, COL(X, x, X->l), X->ld, Y->n, ky, kx, alpha, beta, y->dQ, kx > 0 ? kx : 1));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVMultInPlace_B200(BV V, Mat Q, PetscInt s, PetscInt e)
+{
+  BV_B200 *d = (BV_B200 *)V->data;
+  const PetscInt l = V->l, k = V->k - V->l;
+  if (s >= e) return PETSC_SUCCESS;
+  PetscCall(BVUploadBlock_B200(d, Q->dense, Q->lda, l, l, k, e - l));        /* Q(l:k, l:e) compacted, ld = k */
+  B2KCall(b2k_mult_inplace(CTX(), COL(V, d, l), V->ld, V->n, k, s - l, e - l, d->dQ, k > 0 ? k : 1, 0));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVMultInPlaceHermitianTranspose_B200(BV V, Mat Q, PetscInt s, PetscInt e)
+{
+  BV_B200 *d = (BV_B200 *)V->data;
+  const PetscInt l = V->l, k = V->k - V->l;
+  if (s >= e) return PETSC_SUCCESS;
+  PetscCall(BVUploadBlock_B200(d, Q->dense, Q->lda, l, l, e - l, k));        /* Q(l:e, l:k) compacted, ld = e-l */
+  B2KCall(b2k_mult_inplace(CTX(), COL(V, d, l), V->ld, V->n, k, s - l, e - l, d->dQ, e - l, 1));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVDot_B200(BV X, BV Y, Mat M)
+{
+  BV_B200 *x = (BV_B200 *)X->data, *y = (BV_B200 *)Y->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt ky = Y->k - Y->l, kx = X->k - X->l;
+  PetscCheck((size_t)ky * (size_t)kx <= x->dQ_elems, PETSC_ERR_ARG_SIZ, "result block larger than the scratch area");
+  B2KCall(b2k_dot(ctx, COL(Y, y, Y->l), Y->ld, COL(X, x, X->l), X->ld, X->n, ky, kx, x->dQ, ky));
+  PetscCall(B2KCommAllreduce(X->comm, x->dQ, ky * kx, 0, B2K_MEM_DEVICE));
+  B2KCall(b2k_d2h(ctx, x->hQ, x->dQ, sizeof(double) * (size_t)ky * (size_t)kx));
+  for (PetscInt jx = 0; jx < kx; jx++)             /* M(ly:ky, lx:kx), svec.c:101 */
+    memcpy(M->dense + (size_t)(X->l + jx) * (size_t)M->lda + Y->l, x->hQ + (size_t)jx * (size_t)ky, sizeof(double) * (size_t)ky);
+  return PETSC_SUCCESS;
+}
+
+/* column loop of sveccuda.cu:269-303 */
+static PetscErrorCode BVMatMult_B200(BV V, Mat A, BV W)
+{
+  BV_B200 *v = (BV_B200 *)V->data, *w = (BV_B200 *)W->data;
+  Vec x, y;
+  PetscCall(VecCreateWithArray(B2K_MEM_DEVICE, V->n, V->N, NULL, &x));
+  PetscCall(VecCreateWithArray(B2K_MEM_DEVICE, W->n, W->N, NULL, &y));
+  x->rstart = V->row0; y->rstart = W->row0;
+  PetscErrorCode ierr = PETSC_SUCCESS;
+  for (PetscInt j = 0; j < V->k - V->l && !ierr; j++) {
+    x->array = COL(V, v, V->l + j);
+    y->array = COL(W, w, W->l + j);
+    ierr = MatMult(A, x, y);
+  }
+  PetscCall(VecDestroy(&x));
+  PetscCall(VecDestroy(&y));
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVCopy_B200(BV V, BV W)
+{
+  BV_B200 *v = (BV_B200 *)V->data, *w = (BV_B200 *)W->data;
+  B2KCall(b2k_copy(CTX(), COL(W, w, W->l), W->ld, COL(V, v, V->l), V->ld, V->n, V->k - V->l));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVCopyColumn_B200(BV V, PetscInt j, PetscInt i)
+{
+  BV_B200 *d = (BV_B200 *)V->data;
+  B2KCall(b2k_copy(CTX(), COL(V, d, i), V->ld, COL(V, d, j), V->ld, V->n, 1));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVResize_B200(BV bv, PetscInt m, PetscBool copy)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  double *Vnew = NULL;
+  const size_t bytes = sizeof(double) * (size_t)(bv->nc + m) * (size_t)bv->ld;
+  B2KCall(b2k_malloc(ctx, (void **)&Vnew, bytes));
+  B2KCall(b2k_memset0(ctx, Vnew, bytes));
+  if (copy) B2KCall(b2k_copy(ctx, Vnew, bv->ld, d->V, bv->ld, bv->n, bv->nc + PetscMin(m, bv->m)));
+  B2KCall(b2k_free(ctx, d->V));
+  d->V = Vnew;
+  const PetscInt msave = bv->m;
+  PetscCall(BVFreeScratch_B200(d));
+  bv->m = m;
+  PetscErrorCode ierr = BVAllocScratch_B200(bv, d);
+  bv->m = msave;                                  /* the front-end updates m after we return */
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVGetColumn_B200(BV bv, PetscInt j, Vec *v)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  const int l = (bv->ci[0] == j) ? 0 : 1;         /* the front-end recorded the slot (svec.c:292-303) */
+  (void)v;
+  PetscCall(VecPlaceArray(bv->cv[l], COL(bv, d, j)));
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVRestoreColumn_B200(BV bv, PetscInt j, Vec *v)
+{
+  const int l = (bv->ci[0] == j) ? 0 : 1;
+  (void)v;
+  PetscCall(VecResetArray(bv->cv[l]));
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVGetArray_B200(BV bv, PetscScalar **a) { *a = ((BV_B200 *)bv->data)->V; return PETSC_SUCCESS; }
+
+static PetscErrorCode BVSetRandomColumn_B200(BV bv, PetscInt j)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  B2KCall(b2k_set_random(CTX(), COL(bv, d, j), bv->n, bv->row0, bv->rng_seed + (uint64_t)j));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVDestroy_B200(BV bv)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  if (!d) return PETSC_SUCCESS;
+  if (CTX()) b2k_free(CTX(), d->V);
+  PetscCall(BVFreeScratch_B200(d));
+  free(d);
+  bv->data = NULL;
+  return PETSC_SUCCESS;
+}
+
+/* constructor registered with BVRegister("b200", …): what BVCreate_Svec does at svec.c:397-563 */
+PetscErrorCode BVCreate_B200(BV bv)
+{
+  b2k_ctx ctx = CTX();
+  PetscCheck(ctx, PETSC_ERR_ORDER, "BV type b200 needs a GPU context: call B2KInitialize() first (there is no CPU fallback)");
+  BV_B200 *d = (BV_B200 *)calloc(1, sizeof(*d));
+  PetscCheck(d, PETSC_ERR_MEM, "out of memory");
+  bv->data = d;
+  bv->mem = B2K_MEM_DEVICE;
+  const size_t bytes = sizeof(double) * (size_t)(bv->nc + bv->m) * (size_t)bv->ld;   /* 64-bit: m*ld overflows int32, svec.c:425 */
+  B2KCall(b2k_malloc(ctx, (void **)&d->V, bytes));
+  B2KCall(b2k_memset0(ctx, d->V, bytes));
+  PetscCall(BVAllocScratch_B200(bv, d));
+  const char *e = getenv("B2K_BV_FUSE");
+  d->fuse_mode = e ? atoi(e) : 2;
+  d->expect_refine = PETSC_TRUE;
+  d->last_j = -1;
+
+  bv->ops.mult = BVMult_B200;
+  bv->ops.multvec = BVMultVec_B200;
+  bv->ops.multinplace = BVMultInPlace_B200;
+  bv->ops.multinplacetrans = BVMultInPlaceHermitianTranspose_B200;
+  bv->ops.dot = BVDot_B200;
+  bv->ops.dotvec = BVDotVec_B200;
+  bv->ops.dotvec_local = BVDotVec_Local_B200;
+  bv->ops.scale = BVScale_B200;
+  bv->ops.norm = BVNorm_B200;
+  bv->ops.norm_local = BVNorm_Local_B200;
+  bv->ops.normalize = BVNormalize_B200;
+  bv->ops.matmult = BVMatMult_B200;
+  bv->ops.copy = BVCopy_B200;
+  bv->ops.copycolumn = BVCopyColumn_B200;
+  bv->ops.resize = BVResize_B200;
+  bv->ops.getcolumn = BVGetColumn_B200;
+  bv->ops.restorecolumn = BVRestoreColumn_B200;
+  bv->ops.getarray = BVGetArray_B200;
+  bv->ops.gramschmidt = BVGramSchmidt_B200;
+  bv->ops.destroy = BVDestroy_B200;
+  bv->ops.setrandomcolumn = BVSetRandomColumn_B200;
+  return PETSC_SUCCESS;
+}

@@ -1,0 +1,279 @@
+/*
+ * matb200.c — Mat type "b200csr": the operator of the eigen/singular-value problem as FP64 CSR rows
+ * resident in HBM, row-partitioned over the GPUs of one box.  It supplies what SLEPc reaches through
+ *   BVMatMultColumn → MatMult            src/sys/classes/bv/interface/bvops.c:862-885
+ *   STApply_Generic → MatMult(st->M,x,y) src/sys/classes/st/interface/stsolve.c:16-25
+ *   SVDTwoSideLanczos → MatMult(A|AT)    src/svd/impls/lanczos/gklanczos.c:67,80,90,103
+ * i.e. PETSc's MatMult_MPIAIJ(CUSPARSE): VecScatter halo exchange + local SpMV.  Here the halo moves
+ * GPU-to-GPU over NVLink (NCCL send/recv on the compute stream) and the SpMV is b2k_csr_spmv.
+ * With a real PETSc the same object is a MatShell (MATOP_MULT) or a registered Mat type, INTEGRATION.md.
+ */
+#include "b2kimpl.h"
+
+typedef struct {
+  b2k_csr   A;
+  PetscInt  nghost;
+  PetscInt *ghosts;          /* sorted global column indices outside [cstart,cend)            */
+  double   *xghost;          /* device, nghost doubles: halo values in ghost order             */
+  /* halo plan */
+  PetscBool halo_set;
+  PetscInt  nrecv, nsend;
+  PetscInt *recvrank, *recvcount, *sendrank, *sendcount;
+  PetscInt *sendoff;         /* contiguous sends: offset into x (sendidx == NULL)              */
+  int      *d_sendidx;       /* device: local indices to pack (general plan)                   */
+  double   *sendbuf;         /* device pack buffer                                             */
+  PetscInt  nsendtot;
+  int64_t   nnz;
+} Mat_B200CSR;
+
+#define CTX() B2KGetContext()
+
+static PetscErrorCode MatHaloExchange_B200CSR(Mat A, const double *x)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  B2KComm comm = B2KCommWorld();
+  int size = 1;
+  PetscCall(B2KCommGetRank(comm, NULL, &size));
+  if (size == 1 || a->nghost == 0) {
+    PetscCheck(a->nghost == 0, PETSC_ERR_ARG_WRONGSTATE, "matrix has %d ghost columns but the communicator has a single rank", a->nghost);
+    return PETSC_SUCCESS;
+  }
+  PetscCheck(a->halo_set, PETSC_ERR_ORDER, "MatB200CSRSetHalo() must be called before MatMult() on more than one rank");
+  PetscCheck(comm->kind == 1, PETSC_ERR_SUP, "b200csr needs the NCCL communicator (B2KCommInitNCCL)");
+  if (a->d_sendidx && a->nsendtot > 0) B2KCall(b2k_gather(CTX(), a->sendbuf, x, a->d_sendidx, a->nsendtot));
+  B2KCall(b2k_comm_group_start(comm->nccl));
+  PetscInt soff = 0, roff = 0;
+  for (PetscInt q = 0; q < a->nsend; q++) {
+    const double *sb = a->d_sendidx ? a->sendbuf + soff : x + a->sendoff[q];
+    B2KCall(b2k_comm_sendrecv(comm->nccl, sb, a->sendcount[q], a->sendrank[q], NULL, 0, 0));
+    soff += a->sendcount[q];
+  }
+  for (PetscInt p = 0; p < a->nrecv; p++) {
+    B2KCall(b2k_comm_sendrecv(comm->nccl, NULL, 0, 0, a->xghost + roff, a->recvcount[p], a->recvrank[p]));
+    roff += a->recvcount[p];
+  }
+  B2KCall(b2k_comm_group_end(comm->nccl));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode MatMult_B200CSR(Mat A, Vec x, Vec y)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  PetscCheck(x->mem == B2K_MEM_DEVICE && y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "b200csr needs device vectors");
+  PetscCall(MatHaloExchange_B200CSR(A, x->array));
+  B2KCall(b2k_csr_spmv(CTX(), a->A, x->array, a->xghost, y->array));
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode MatDestroy_B200CSR(Mat A)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  if (!a) return PETSC_SUCCESS;
+  b2k_ctx ctx = CTX();
+  if (ctx) {
+    b2k_csr_destroy(ctx, a->A);
+    b2k_free(ctx, a->xghost); b2k_free(ctx, a->d_sendidx); b2k_free(ctx, a->sendbuf);
+  }
+  free(a->ghosts); free(a->recvrank); free(a->recvcount); free(a->sendrank); free(a->sendcount); free(a->sendoff);
+  free(a);
+  A->data = NULL;
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode MatSetUp_B200CSR(Mat A, PetscInt M, PetscInt N, PetscInt rstart, PetscInt rend, PetscInt cstart, PetscInt cend, Mat_B200CSR **out)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)calloc(1, sizeof(*a));
+  PetscCheck(a, PETSC_ERR_MEM, "out of memory");
+  strcpy(A->type, "b200csr");
+  A->M = M; A->N = N; A->m = rend - rstart; A->n = cend - cstart;
+  A->rstart = rstart; A->rend = rend; A->cstart = cstart; A->cend = cend;
+  A->mem = B2K_MEM_DEVICE;
+  A->data = a;
+  A->ops.mult = MatMult_B200CSR;
+  A->ops.destroy = MatDestroy_B200CSR;
+  *out = a;
+  return PETSC_SUCCESS;
+}
+
+static int cmp_int(const void *x, const void *y) { const PetscInt a = *(const PetscInt *)x, b = *(const PetscInt *)y; return (a > b) - (a < b); }
+
+PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscInt rend, const PetscInt *rowptr, const PetscInt *colidx,
+                                const PetscScalar *val, PetscInt cstart, PetscInt cend, Mat *out)
+{
+  b2k_ctx ctx = CTX();
+  PetscCheck(ctx, PETSC_ERR_ORDER, "Mat type b200csr needs a GPU context: call B2KInitialize() first (there is no CPU fallback)");
+  PetscCheck(rstart >= 0 && rend >= rstart && rend <= M, PETSC_ERR_ARG_OUTOFRANGE, "row range [%d,%d) outside [0,%d)", rstart, rend, M);
+  PetscCheck(cstart >= 0 && cend >= cstart && cend <= N, PETSC_ERR_ARG_OUTOFRANGE, "column range [%d,%d) outside [0,%d)", cstart, cend, N);
+  PetscCheck(rowptr && (rend == rstart || rowptr[0] == 0), PETSC_ERR_ARG_WRONG, "rowptr[0] must be 0");
+  const PetscInt m = rend - rstart, ncl = cend - cstart;
+  const PetscInt nnz = m ? rowptr[m] : 0;
+  Mat A;
+  Mat_B200CSR *a;
+  PetscCall(MatCreate_Private(&A));
+  PetscCall(MatSetUp_B200CSR(A, M, N, rstart, rend, cstart, cend, &a));
+  a->nnz = nnz;
+  /* ghosts = sorted unique off-range columns; local numbering = [owned | ghosts] like MatMPIAIJ's garray */
+  PetscInt noff = 0;
+  for (PetscInt k = 0; k < nnz; k++) {
+    PetscCheck(colidx[k] >= 0 && colidx[k] < N, PETSC_ERR_ARG_OUTOFRANGE, "column index %d outside [0,%d)", colidx[k], N);
+    if (colidx[k] < cstart || colidx[k] >= cend) noff++;
+  }
+  PetscInt *loc = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  PetscCheck(loc, PETSC_ERR_MEM, "out of memory");
+  if (noff) {
+    PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)noff), ng = 0;
+    PetscCheck(g, PETSC_ERR_MEM, "out of memory");
+    for (PetscInt k = 0; k < nnz; k++) if (colidx[k] < cstart || colidx[k] >= cend) g[ng++] = colidx[k];
+    qsort(g, (size_t)ng, sizeof(PetscInt), cmp_int);
+    PetscInt nu = 0;
+    for (PetscInt i = 0; i < ng; i++) if (i == 0 || g[i] != g[i - 1]) g[nu++] = g[i];
+    a->ghosts = g; a->nghost = nu;
+  }
+  for (PetscInt k = 0; k < nnz; k++) {
+    const PetscInt cg = colidx[k];
+    if (cg >= cstart && cg < cend) loc[k] = cg - cstart;
+    else {
+      PetscInt lo = 0, hi = a->nghost - 1;
+      while (lo < hi) { const PetscInt mid = (lo + hi) / 2; if (a->ghosts[mid] < cg) lo = mid + 1; else hi = mid; }
+      loc[k] = ncl + lo;
+    }
+  }
+  int rc = b2k_csr_create(ctx, m, ncl, a->nghost, rowptr, loc, val, &a->A);
+  free(loc);
+  if (rc) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_create failed (%d): %s", rc, b2k_last_error()); }
+  if (a->nghost) B2KCall(b2k_malloc(ctx, (void **)&a->xghost, sizeof(double) * (size_t)a->nghost));
+  *out = A;
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode MatB200CSRGetGhosts(Mat A, PetscInt *nghost, const PetscInt **ghosts)
+{
+  PetscCheck(!strcmp(A->type, "b200csr"), PETSC_ERR_ARG_WRONG, "not a b200csr matrix");
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  if (nghost) *nghost = a->nghost;
+  if (ghosts) *ghosts = a->ghosts;
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode dup_ints(const PetscInt *src, PetscInt n, PetscInt **dst)
+{
+  *dst = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(n > 0 ? n : 1));
+  PetscCheck(*dst, PETSC_ERR_MEM, "out of memory");
+  if (n > 0) memcpy(*dst, src, sizeof(PetscInt) * (size_t)n);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode MatB200CSRSetHalo(Mat A, PetscInt nrecv, const PetscInt *recvrank, const PetscInt *recvcount, PetscInt nsend,
+                                 const PetscInt *sendrank, const PetscInt *sendcount, const PetscInt *sendidx)
+{
+  PetscCheck(!strcmp(A->type, "b200csr"), PETSC_ERR_ARG_WRONG, "not a b200csr matrix");
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  b2k_ctx ctx = CTX();
+  PetscInt tot = 0, stot = 0;
+  for (PetscInt p = 0; p < nrecv; p++) tot += recvcount[p];
+  PetscCheck(tot == a->nghost, PETSC_ERR_ARG_SIZ, "halo plan receives %d values but the matrix has %d ghost columns", tot, a->nghost);
+  for (PetscInt q = 0; q < nsend; q++) stot += sendcount[q];
+  for (PetscInt i = 0; i < stot; i++) PetscCheck(sendidx[i] >= 0 && sendidx[i] < A->n, PETSC_ERR_ARG_OUTOFRANGE, "send index %d outside the local columns", sendidx[i]);
+  free(a->recvrank); free(a->recvcount); free(a->sendrank); free(a->sendcount);
+  PetscCall(dup_ints(recvrank, nrecv, &a->recvrank));
+  PetscCall(dup_ints(recvcount, nrecv, &a->recvcount));
+  PetscCall(dup_ints(sendrank, nsend, &a->sendrank));
+  PetscCall(dup_ints(sendcount, nsend, &a->sendcount));
+  a->nrecv = nrecv; a->nsend = nsend; a->nsendtot = stot;
+  if (a->d_sendidx) { B2KCall(b2k_free(ctx, a->d_sendidx)); a->d_sendidx = NULL; }
+  if (a->sendbuf) { B2KCall(b2k_free(ctx, a->sendbuf)); a->sendbuf = NULL; }
+  if (stot) {
+    B2KCall(b2k_malloc(ctx, (void **)&a->d_sendidx, sizeof(int) * (size_t)stot));
+    B2KCall(b2k_h2d(ctx, a->d_sendidx, sendidx, sizeof(int) * (size_t)stot));
+    B2KCall(b2k_malloc(ctx, (void **)&a->sendbuf, sizeof(double) * (size_t)stot));
+  }
+  a->halo_set = PETSC_TRUE;
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode MatB200CSRGetInfo(Mat A, int64_t *nnz, int64_t *nghost)
+{
+  PetscCheck(!strcmp(A->type, "b200csr"), PETSC_ERR_ARG_WRONG, "not a b200csr matrix");
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  if (nnz) *nnz = a->nnz;
+  if (nghost) *nghost = a->nghost;
+  return PETSC_SUCCESS;
+}
+
+/* d-dimensional Laplacian generated on the device, slab-partitioned along the slowest index
+   (ex1.c:37-48 tridiag(-1,2,-1); ex2.c:39-54 5-point; 7-point analogue for C3) */
+PetscErrorCode MatCreateB200Laplacian(PetscInt dim, PetscInt nx, PetscInt ny, PetscInt nz, Mat *out)
+{
+  b2k_ctx ctx = CTX();
+  PetscCheck(ctx, PETSC_ERR_ORDER, "Mat type b200csr needs a GPU context: call B2KInitialize() first (there is no CPU fallback)");
+  PetscCheck(dim >= 1 && dim <= 3, PETSC_ERR_ARG_OUTOFRANGE, "dim must be 1, 2 or 3");
+  if (dim < 3) nz = 1;
+  if (dim < 2) ny = 1;
+  PetscCheck(nx > 0 && ny > 0 && nz > 0, PETSC_ERR_ARG_OUTOFRANGE, "grid sizes must be positive");
+  const int64_t plane = (int64_t)ny * nz, Ntot = (int64_t)nx * plane;
+  PetscCheck(Ntot < 2147483647LL, PETSC_ERR_ARG_OUTOFRANGE, "global size %lld exceeds PetscInt", (long long)Ntot);
+  int rank = 0, size = 1;
+  PetscCall(B2KCommGetRank(B2KCommWorld(), &rank, &size));
+  PetscCheck(nx >= size, PETSC_ERR_ARG_SIZ, "cannot split %d planes over %d ranks", nx, size);
+  /* PetscLayout-style split of the nx planes */
+  const PetscInt base = nx / size, rem = nx % size;
+  const PetscInt p0 = rank * base + PetscMin(rank, rem), np = base + (rank < rem ? 1 : 0);
+  const int64_t row0 = (int64_t)p0 * plane, nrows = (int64_t)np * plane;
+  Mat A;
+  Mat_B200CSR *a;
+  PetscCall(MatCreate_Private(&A));
+  PetscCall(MatSetUp_B200CSR(A, (PetscInt)Ntot, (PetscInt)Ntot, (PetscInt)row0, (PetscInt)(row0 + nrows), (PetscInt)row0, (PetscInt)(row0 + nrows), &a));
+  int64_t glo = 0, ghi = 0;
+  int rc = b2k_csr_laplacian(ctx, dim, nx, ny, nz, row0, nrows, &a->A, &glo, &ghi);
+  if (rc) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_laplacian failed (%d): %s", rc, b2k_last_error()); }
+  B2KCall(b2k_csr_info(a->A, NULL, NULL, NULL, &a->nnz));
+  a->nghost = (PetscInt)(glo + ghi);
+  if (a->nghost) {
+    B2KCall(b2k_malloc(ctx, (void **)&a->xghost, sizeof(double) * (size_t)a->nghost));
+    /* ghost order [lower plane | upper plane]; the planes sent are contiguous pieces of x: no packing */
+    a->recvrank = (PetscInt *)malloc(2 * sizeof(PetscInt)); a->recvcount = (PetscInt *)malloc(2 * sizeof(PetscInt));
+    a->sendrank = (PetscInt *)malloc(2 * sizeof(PetscInt)); a->sendcount = (PetscInt *)malloc(2 * sizeof(PetscInt));
+    a->sendoff = (PetscInt *)malloc(2 * sizeof(PetscInt));
+    PetscCheck(a->recvrank && a->recvcount && a->sendrank && a->sendcount && a->sendoff, PETSC_ERR_MEM, "out of memory");
+    if (glo) {
+      a->recvrank[a->nrecv] = rank - 1; a->recvcount[a->nrecv++] = (PetscInt)plane;
+      a->sendrank[a->nsend] = rank - 1; a->sendcount[a->nsend] = (PetscInt)plane; a->sendoff[a->nsend++] = 0;
+    }
+    if (ghi) {
+      a->recvrank[a->nrecv] = rank + 1; a->recvcount[a->nrecv++] = (PetscInt)plane;
+      a->sendrank[a->nsend] = rank + 1; a->sendcount[a->nsend] = (PetscInt)plane; a->sendoff[a->nsend++] = (PetscInt)(nrows - plane);
+    }
+    a->halo_set = PETSC_TRUE;
+  }
+  *out = A;
+  return PETSC_SUCCESS;
+}
+
+/* explicit transpose (single rank): what SVDSetUp builds by default, svdsetup.c:300-306 */
+PetscErrorCode MatB200CSRTranspose(Mat A, Mat *At)
+{
+  PetscCheck(!strcmp(A->type, "b200csr"), PETSC_ERR_ARG_WRONG, "not a b200csr matrix");
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  b2k_ctx ctx = CTX();
+  PetscCheck(a->nghost == 0 && A->m == A->M && A->n == A->N, PETSC_ERR_SUP, "explicit transpose is implemented for a single rank; pass A^T with SVDSetTransposeMatrix() otherwise");
+  const PetscInt m = A->m, n = A->n;
+  const int64_t nnz = a->nnz;
+  int *drp, *dci;
+  double *dv;
+  B2KCall(b2k_csr_arrays(a->A, &drp, &dci, &dv));
+  PetscInt *rp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(m + 1)), *ci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  double *v = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+  PetscInt *trp = (PetscInt *)calloc((size_t)n + 2, sizeof(PetscInt)), *tci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  double *tv = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+  PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
+  B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
+  if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
+  for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
+  for (PetscInt c = 0; c < n; c++) trp[c + 2] += trp[c + 1];      /* trp[c+1] = start of column c (shifted by one) */
+  for (PetscInt r = 0; r < m; r++)
+    for (PetscInt k = rp[r]; k < rp[r + 1]; k++) { const PetscInt p = trp[ci[k] + 1]++; tci[p] = r; tv[p] = v[k]; }
+  PetscErrorCode ierr = MatCreateB200CSR(n, m, 0, n, trp, tci, tv, 0, m, At);
+  free(rp); free(ci); free(v); free(trp); free(tci); free(tv);
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}

@@ -279,7 +279,7 @@ static PetscErrorCode VecSumSq_Global(Vec v, PetscReal *ss)
 PetscErrorCode VecNorm(Vec v, NormType type, PetscReal *val)
 {
   PetscCheck(type == NORM_2 || type == NORM_FROBENIUS, PETSC_ERR_SUP, "only the 2-norm is implemented for Vec");
-  PetscReal s;
+  PetscReal s = 0.0;
   PetscCall(VecSumSq_Global(v, &s));
   *val = sqrt(s);
   return PETSC_SUCCESS;
@@ -410,8 +410,14 @@ PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y)
 
 PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left)
 {
-  if (right) { if (A->mem == B2K_MEM_DEVICE) PetscCall(VecCreateB200(A->n, A->N, right)); else PetscCall(VecCreateHost(A->n, A->N, right)); }
-  if (left) { if (A->mem == B2K_MEM_DEVICE) PetscCall(VecCreateB200(A->m, A->M, left)); else PetscCall(VecCreateHost(A->m, A->M, left)); }
+  if (right) {
+    if (A->mem == B2K_MEM_DEVICE) PetscCall(VecCreateB200(A->n, A->N, right)); else PetscCall(VecCreateHost(A->n, A->N, right));
+    (*right)->rstart = A->cstart;
+  }
+  if (left) {
+    if (A->mem == B2K_MEM_DEVICE) PetscCall(VecCreateB200(A->m, A->M, left)); else PetscCall(VecCreateHost(A->m, A->M, left));
+    (*left)->rstart = A->rstart;
+  }
   return PETSC_SUCCESS;
 }
 

@@ -1,0 +1,254 @@
+"""The reference's BV known-answer programs (src/sys/classes/bv/tests/test1.c, test2.c, test4.c,
+test13.c) restated against the C front-end (include/b2kslepc.h).  The reference validates a new BV type
+by adding its name to the `-bv_type {{…}}` loops of exactly these programs; here each
+scenario takes a `make_bv(n, m)` factory so the same code runs with the oracle's CPU type
+(tests/test_host_cpu.py) and with the product's "b200" type on the GPU (tests/test_slepc_gpu.py).
+Golden numbers: bv/tests/output/test1_1_bv_type-svec.out, test2_1.out, test4_1.out, test13_1.out.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import slepc_oracle as O
+from slepc_b200 import slepc as SL
+from slepc_b200.slepc import S, c_dbl, c_int
+
+EPS = np.finfo(float).eps
+
+
+def g6(x):
+    return float(f"{x:.6g}")
+
+
+def fill_test1(X, ncols, n):
+    for j in range(ncols):
+        c = np.zeros(n)
+        for i in range(4):
+            if i + j < n:
+                c[i + j] = 3 * i + j - 2
+        X.set_column(j, c)
+
+
+def qmat(k, l):
+    return SL.Mat.seqdense(np.array([[2.0 if i < j else -0.5 for j in range(l)] for i in range(k)]))
+
+
+def norm_column(X, j, t=SL.NORM_2):
+    v = c_dbl()
+    S.BVNormColumn(X.h, j, t, ctypes.byref(v))
+    return v.value
+
+
+def norm(X, t=SL.NORM_FROBENIUS):
+    v = c_dbl()
+    S.BVNorm(X.h, t, ctypes.byref(v))
+    return v.value
+
+
+def with_column(X, j, fn):
+    v = ctypes.c_void_p()
+    S.BVGetColumn(X.h, j, ctypes.byref(v))
+    try:
+        return fn(v)
+    finally:
+        S.BVRestoreColumn(X.h, j, ctypes.byref(v))
+
+
+def scenario_test1(make_bv):
+    n, k, l = 10, 5, 3
+    X, Y = make_bv(n, k), make_bv(n, l)
+    fill_test1(X, k, n)
+    for j in range(l):
+        Y.set_column(j, np.full(n, (j + 1) / 4.0))
+    Q = qmat(k, l)
+    S.BVMult(Y.h, 2.0, 1.0, X.h, Q.h)
+    assert np.allclose(Y.get_column(0), [2.25, 0.25, -5.75, -15.75, -19.75, -20.75, -17.75, -10.75, 0.25, 0.25], atol=1e-13)
+    assert np.allclose(Y.get_column(2), [-7.25, 0.75, 24.75, 44.75, 20.75, -20.25, -17.25, -10.25, 0.75, 0.75], atol=1e-13)
+    z = np.array([2.0 * (-0.5) ** i for i in range(k)])
+    with_column(Y, 0, lambda v: S.BVMultVec(X.h, -1.0, 1.0, v, z.ctypes.data_as(ctypes.c_void_p)))
+    assert np.allclose(Y.get_column(0), [6.25, -2.75, -11.75, -26.0, -14.0, -24.125, -16.25, -12.125, 0.25, 0.25], atol=1e-13)
+    M = SL.Mat.seqdense(np.zeros((l, k)))
+    S.BVDot(X.h, Y.h, M.h)
+    gold_M = np.array([[-244.25, -262.75, -379.125, -413.375, -412.0], [215.0, -35.0, -243.0, -377.0, -397.0],
+                       [427.5, 438.5, 76.5, -186.5, -310.5]])
+    assert np.allclose(M.dense_array(), gold_M, atol=1e-11)
+    zz = np.zeros(k)
+    with_column(Y, 0, lambda v: S.BVDotVec(X.h, v, zz.ctypes.data_as(ctypes.c_void_p)))
+    assert np.allclose(zz, [-244.25, -262.75, -379.125, -413.375, -412.0], atol=1e-11)
+    S.BVMultInPlace(X.h, Q.h, 1, l)
+    S.BVScale(X.h, 2.0)
+    assert np.allclose(X.get_column(1), [-8, 5, 14, 19, -20, -21, -18, -11, 0, 0], atol=1e-12)
+    assert np.allclose(X.get_column(2), [-8, 0, 24, 44, 20, -21, -18, -11, 0, 0], atol=1e-12)
+    assert g6(norm_column(X, 0)) == 16.7332
+    assert g6(norm(X)) == 87.1436
+    assert list(X.to_numpy()[0, :k]) == [-4.0, -8.0, -8.0, 0.0, 0.0]
+    for o in (X, Y, Q, M):
+        o.destroy()
+
+
+def scenario_test2(make_bv):
+    n, k = 20, 8
+    X = make_bv(n, k)
+    X0 = np.zeros((n, k), order="F")
+    for j in range(k):
+        for i in range(n // 2 + 1):
+            if i + j < n:
+                X0[i + j, j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
+    X.from_numpy(X0)
+    Y = SL.BV()
+    S.BVDuplicate(X.h, Y.ref)
+    S.BVCopy(X.h, Y.h)
+    Z = SL.BV()
+    S.BVDuplicate(X.h, Z.ref)
+    S.BVCopy(X.h, Z.h)
+    nrm = c_dbl()
+    for j in range(k):
+        S.BVOrthogonalizeColumn(X.h, j, None, ctypes.byref(nrm), None)
+        S.BVScaleColumn(X.h, j, 1.0 / nrm.value)
+    M = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVDot(X.h, X.h, M.h)
+    assert np.linalg.norm(M.dense_array() - np.eye(k), 1) < 100 * EPS
+    R = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVOrthogonalize(Y.h, R.h)
+    S.BVDot(Y.h, Y.h, M.h)
+    assert np.linalg.norm(M.dense_array() - np.eye(k), 1) < 100 * EPS
+    S.BVMult(Z.h, -1.0, 1.0, Y.h, R.h)
+    assert norm(Z) < 100 * EPS
+    Rm = R.dense_array()
+    assert np.allclose(np.tril(Rm, -1), 0.0)
+    e = SL.Vec()
+    S.BVCreateVec(X.h, e.ref)
+    S.VecSet(e.h, 1.0)
+    S.BVOrthogonalizeVec(X.h, e.h, None, ctypes.byref(nrm), None)
+    assert g6(nrm.value) == 2.50931
+    for o in (X, Y, Z, M, R, e):
+        o.destroy()
+
+
+def scenario_test4(make_bv, trans=False):
+    n, kx, lx, ky, ly = 18, 12, 3, 8, 2
+    X = make_bv(n, kx + 2)
+    X.set_active(lx, kx)
+    fill_test1(X, kx + 2, n)
+    Y = make_bv(n, ky + 1)
+    Y.set_active(ly, ky)
+    for j in range(ky + 1):
+        Y.set_column(j, np.full(n, (j + 1) / 4.0))
+    Qn = np.array([[2.0 if i < j else -0.5 for j in range(ky)] for i in range(kx)])
+    Q = SL.Mat.seqdense(Qn)
+    S.BVResize(X.h, kx + 4, 1)
+    S.BVMult(Y.h, 2.0, 0.5, X.h, Q.h)
+    z = np.array([2.0 * (-0.5) ** i for i in range(kx - lx)])
+    with_column(Y, 0, lambda v: S.BVMultVec(X.h, -1.0, 1.0, v, z.ctypes.data_as(ctypes.c_void_p)))
+    M = SL.Mat.seqdense(np.zeros((ky, kx)))
+    S.BVDot(X.h, Y.h, M.h)
+    zz = np.zeros(kx - lx)
+    with_column(Y, 0, lambda v: S.BVDotVec(X.h, v, zz.ctypes.data_as(ctypes.c_void_p)))
+    # cross-check the windowed products with the numpy oracle on the same data
+    Xo, Yo = O.BV(n, kx + 4), O.BV(n, ky + 1)
+    Xo.set_active(lx, kx)
+    Yo.set_active(ly, ky)
+    for j in range(kx + 2):
+        for i in range(4):
+            if i + j < n:
+                Xo.col(j)[i + j] = 3 * i + j - 2
+    for j in range(ky + 1):
+        Yo.col(j)[:] = (j + 1) / 4.0
+    Yo.mult(2.0, 0.5, Xo, Qn)
+    Xo.multvec(-1.0, 1.0, Yo.col(0), z)
+    assert np.allclose(Y.to_numpy(), Yo.V, atol=1e-12)
+    assert np.allclose(M.dense_array()[ly:ky, lx:kx], Xo.dot(Yo), atol=1e-10)
+    assert np.allclose(zz, Xo.dotvec(Yo.col(0)), atol=1e-10)
+    if trans:
+        Qt = SL.Mat.seqdense(Qn.T.copy())
+        S.BVMultInPlaceHermitianTranspose(X.h, Qt.h, lx + 1, ky)
+        Qt.destroy()
+    else:
+        S.BVMultInPlace(X.h, Q.h, lx + 1, ky)
+    S.BVScale(X.h, 2.0)
+    assert g6(norm_column(X, lx)) == 25.7682
+    assert g6(norm(X)) == 328.469
+    for o in (X, Y, Q, M):
+        o.destroy()
+
+
+def scenario_test13(make_bv):
+    n, k = 10, 5
+    X = make_bv(n, k)
+    fill_test1(X, k, n)
+    S.BVDotColumn(X.h, 2, None)          # q == NULL ⇒ the internal buffer (test13.c:60)
+    S.BVMultColumn(X.h, -1.0, 1.0, 2, None)
+    assert g6(norm(X)) == 711.996
+    X.destroy()
+
+
+def scenario_errors(make_bv):
+    """error behaviour of the front-end (same checks and messages as bvops.c / bvbasic.c)"""
+    X, Y = make_bv(10, 5), make_bv(10, 3)
+    v1, v2, v3 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    S.BVGetColumn(X.h, 0, ctypes.byref(v1))
+    with pytest.raises(SL.SlepcError, match="already fetched"):
+        S.BVGetColumn(X.h, 0, ctypes.byref(v2))
+    S.BVGetColumn(X.h, 1, ctypes.byref(v2))
+    with pytest.raises(SL.SlepcError, match="Too many requested columns"):
+        S.BVGetColumn(X.h, 2, ctypes.byref(v3))
+    with pytest.raises(SL.SlepcError, match="has not been fetched"):
+        S.BVRestoreColumn(X.h, 3, ctypes.byref(v1))
+    S.BVRestoreColumn(X.h, 0, ctypes.byref(v1))
+    S.BVRestoreColumn(X.h, 1, ctypes.byref(v2))
+    with pytest.raises(SL.SlepcError, match="only 5 are available"):
+        S.BVGetColumn(X.h, 5, ctypes.byref(v1))
+    Q = SL.Mat.seqdense(np.zeros((4, 3)))
+    with pytest.raises(SL.SlepcError, match="Mat argument has 4 rows, should have at least 5"):
+        S.BVMult(Y.h, 1.0, 0.0, X.h, Q.h)
+    with pytest.raises(SL.SlepcError, match="X and Y arguments must be different"):
+        S.BVMult(X.h, 1.0, 0.0, X.h, None)
+    Q5 = SL.Mat.seqdense(np.eye(5))
+    with pytest.raises(SL.SlepcError, match="Argument s has wrong value"):
+        S.BVMultInPlace(X.h, Q5.h, 7, 8)
+    with pytest.raises(SL.SlepcError, match="requested value of e is larger"):
+        S.BVSetActiveColumns(X.h, 0, 5) or S.BVMultInPlace(X.h, SL.Mat.seqdense(np.eye(5)[:, :3]).h, 0, 4)
+    with pytest.raises(SL.SlepcError, match="Requested norm not available"):
+        S.BVNorm(X.h, SL.NORM_2, ctypes.byref(c_dbl()))
+    with pytest.raises(SL.SlepcError, match="Illegal value of k"):
+        S.BVSetActiveColumns(X.h, 0, 9)
+    with pytest.raises(SL.SlepcError, match="Index j=7 but BV only has 5 columns"):
+        S.BVOrthogonalizeColumn(X.h, 7, None, None, None)
+    with pytest.raises(SL.SlepcError, match="Unable to find requested BV type"):
+        b = SL.BV()
+        S.BVCreate(b.ref)
+        S.BVSetType(b.h, b"nonexistent")
+    for o in (X, Y, Q, Q5):
+        o.destroy()
+
+
+def scenario_orthog_vs_oracle(make_bv, otype, refine, n, k, tol):
+    """column-by-column orthonormalisation of an ill-conditioned block: coefficients, norms and the basis must
+    match the numpy oracle (same algorithm, different reduction order ⇒ tolerance, not bit equality)."""
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((n, k))
+    if refine != SL.BV_ORTHOG_REFINE_NEVER:                 # without refinement such columns are rounding noise
+        A[:, 5] = A[:, 4] + 1e-6 * rng.standard_normal(n)   # forces DGKS refinement
+        A[:, 9] = A[:, :3] @ np.array([1.0, -2.0, 0.5]) + 1e-9 * rng.standard_normal(n)
+    X = make_bv(n, k)
+    X.from_numpy(A)
+    S.BVSetOrthogonalization(X.h, otype, refine, 0.7071, 0)
+    Xo = O.BV(n, k)
+    Xo.V[:] = A
+    Xo.orthog_type, Xo.orthog_ref = otype, refine
+    nrm, lin = c_dbl(), c_int()
+    H = np.zeros(k + 1)
+    for j in range(k):
+        S.BVOrthogonalizeColumn(X.h, j, H.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nrm), ctypes.byref(lin))
+        ho, no, lo = Xo.orthogonalize_column(j)
+        assert bool(lin.value) == bool(lo)
+        assert abs(nrm.value - no) <= 1e-7 * max(1.0, abs(no))
+        assert np.allclose(H[:j], ho, rtol=1e-6, atol=1e-8)
+        S.BVScaleColumn(X.h, j, 1.0 / nrm.value)
+        Xo.scale_column(j, 1.0 / no)
+    Q = X.to_numpy()
+    assert np.linalg.norm(Q.T @ Q - np.eye(k), 1) < (1e-6 if refine == SL.BV_ORTHOG_REFINE_NEVER else 100 * k * EPS)
+    # same subspace as the oracle's basis
+    assert np.linalg.norm(Q - Xo.V @ (Xo.V.T @ Q)) < 1e-6
+    X.destroy()

@@ -1,0 +1,228 @@
+"""Host logic of the product (libb2kslepc: BV front-end, DGKS driver, Arnoldi/Lanczos, DS, Krylov-Schur,
+TRLanczos) exercised on CPU through the oracle's host-memory BV/Mat plug-in, against
+  (a) the reference's golden outputs (same files as tests/test_oracle_golden.py), and
+  (b) the numpy oracle on the same seeded inputs.
+The product's own BV type needs a GPU and is covered by tests/test_slepc_gpu.py (-m gpu); here the C host
+driver is what is under test, the arithmetic comes from oracle/oracle_cpu.c.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import cpu_plugin as CP
+from oracle import slepc_oracle as O
+from slepc_b200 import slepc as SL
+from slepc_b200.slepc import S, c_dbl, c_int
+
+import bv_scenarios as SC
+
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _plugin():
+    CP.load()
+
+
+def make_bv(n, m):
+    return CP.bv_cpu(n, m)
+
+
+# ---- BV known-answer tests of the reference (bv/tests/test1,2,4,13) through the C front-end ------------
+def test_bv_test1():
+    SC.scenario_test1(make_bv)
+
+
+def test_bv_test2():
+    SC.scenario_test2(make_bv)
+
+
+def test_bv_test4():
+    SC.scenario_test4(make_bv)
+
+
+def test_bv_test4_trans():
+    SC.scenario_test4(make_bv, trans=True)
+
+
+def test_bv_test13():
+    SC.scenario_test13(make_bv)
+
+
+def test_bv_errors():
+    SC.scenario_errors(make_bv)
+
+
+@pytest.mark.parametrize("otype,refine", [(SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED), (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_ALWAYS),
+                                          (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_NEVER), (SL.BV_ORTHOG_MGS, SL.BV_ORTHOG_REFINE_IFNEEDED)])
+def test_bv_orthog_variants_match_oracle(otype, refine):
+    SC.scenario_orthog_vs_oracle(make_bv, otype, refine, n=300, k=12, tol=1e-12)
+
+
+# ---- solvers ------------------------------------------------------------------------------------------
+def fmt5(v):
+    return [f"{x:.5f}" for x in v]
+
+
+def solve_eps(A, nev, hermitian=True, ncv=None, tol=None, which=None, v0=None, lock=True, mpd=None):
+    M = CP.mat_csr(A)
+    eps = SL.EPS(M, hermitian=hermitian)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, nev, ncv if ncv else SL.PETSC_DETERMINE, mpd if mpd else SL.PETSC_DETERMINE)
+    if tol:
+        S.EPSSetTolerances(eps.h, tol, SL.PETSC_CURRENT)
+    if which:
+        S.EPSSetWhichEigenpairs(eps.h, which)
+    if not lock:
+        S.EPSKrylovSchurSetLocking(eps.h, 0)
+    keep = [M]
+    if v0 is not None:
+        r, _ = M.create_vecs()
+        r.set_values(v0)
+        arr = (ctypes.c_void_p * 1)(r.h)
+        S.EPSSetInitialSpace(eps.h, 1, arr)
+        keep.append(r)
+    eps.solve()
+    eps._keep = keep
+    return eps
+
+
+def test_eps_test4_golden():
+    A = O.laplacian_1d(30)
+    eps = solve_eps(A, 4, tol=1000 * EPS)
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = [eps.eigenvalue(i)[0] for i in range(4)]
+    assert fmt5(lam) == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    for i in range(4):
+        assert eps.error(i) < 5 * 1000 * EPS
+
+
+def test_eps_ex2_golden_and_oracle_parity():
+    nx = 72
+    A = O.laplacian_2d(nx)
+    eps = solve_eps(A, 4, ncv=20)
+    ref = O.eps_krylovschur(A, nx * nx, nev=4, ncv=20)
+    assert eps.reason > 0 and eps.nconv >= 4
+    # same deterministic start vector and same algorithm ⇒ same path as the numpy oracle
+    assert eps.nconv == ref.nconv and eps.its == ref.its
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(eps.nconv)])
+    assert np.allclose(lam, ref.eigr[ref.perm], rtol=1e-10, atol=0)
+    gold = ["7.99630", "7.99074", "7.98519", "7.98150"]
+    got = fmt5(lam[:4])
+    assert got[0] == gold[0] and set(got) <= set(gold)
+    for i in range(eps.nconv):
+        assert eps.error(i) < 5e-8
+
+
+@pytest.mark.parametrize("lock", [True, False])
+def test_eps_ex5_markov_golden(lock):
+    m = 15
+    A = O.markov_model(m)
+    N = m * (m + 1) // 2
+    v0 = np.zeros(N)
+    v0[:3] = 1.0
+    eps = solve_eps(A, 4, hermitian=False, which=SL.EPS_LARGEST_REAL, v0=v0, lock=lock)
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = [eps.eigenvalue(i) for i in range(4)]
+    assert fmt5([l[0] for l in lam]) == ["1.00000", "0.97137", "0.90423", "0.85714"]
+    assert all(l[1] == 0.0 for l in lam)
+    for i in range(4):
+        assert eps.error(i) < 5e-8
+    ref = O.eps_krylovschur(A, N, nev=4, which="largest_real", hermitian=False, v0=v0, lock=lock)
+    assert eps.its == ref.its and eps.nconv == ref.nconv
+
+
+def test_eps_nonsymmetric_complex_pairs():
+    """random nonsymmetric matrix: complex conjugate pairs must stay together (DSSort_NHEP_Total, final sort)"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 200
+    A = (sp.random(n, n, density=0.05, random_state=5, format="csr") + sp.diags(rng.standard_normal(n))).tocsr()
+    eps = solve_eps(A, 6, hermitian=False, tol=1e-9)
+    assert eps.reason > 0
+    ev = np.linalg.eigvals(A.toarray())
+    ev = ev[np.argsort(-np.abs(ev))]
+    got = np.array([complex(*eps.eigenvalue(i)) for i in range(eps.nconv)])
+    for g in got[:6]:
+        assert np.min(np.abs(ev - g)) < 1e-7 * max(1.0, abs(g))
+    r, _ = eps._keep[0].create_vecs()
+    i_ = eps._keep[0].create_vecs()[0]
+    for i in range(min(6, eps.nconv)):
+        assert eps.error(i) < 1e-7
+        re, im = eps.eigenpair(i, r, i_)
+        x = r.get_values() + 1j * i_.get_values()
+        assert np.linalg.norm(A @ x - complex(re, im) * x) < 1e-6 * abs(complex(re, im)) * np.linalg.norm(x)
+
+
+def test_eps_shift_and_which():
+    n = 100
+    A = O.laplacian_1d(n)
+    M = CP.mat_csr(A)
+    eps = SL.EPS(M, hermitian=True)
+    CP.use_cpu_bv(eps)
+    st = ctypes.c_void_p()
+    S.EPSGetST(eps.h, ctypes.byref(st))
+    S.STSetShift(st, 1.5)
+    S.EPSSetDimensions(eps.h, 3, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_SMALLEST_REAL)
+    S.EPSSetTolerances(eps.h, 1e-10, 2000)
+    eps.solve()
+    exact = np.sort(2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1)))
+    assert eps.nconv >= 3
+    lam = [eps.eigenvalue(i)[0] for i in range(3)]
+    assert np.allclose(lam, exact[:3], rtol=1e-8)
+
+
+def test_eps_argument_errors():
+    A = O.laplacian_1d(30)
+    M = CP.mat_csr(A)
+    eps = SL.EPS(M)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, 4, SL.PETSC_DETERMINE)
+    with pytest.raises(SL.SlepcError, match="ncv must be at least nev\\+1"):
+        eps.solve()
+    eps2 = SL.EPS(M)
+    with pytest.raises(SL.SlepcError, match="Must call EPSSolve"):
+        eps2.nconv
+    with pytest.raises(SL.SlepcError, match="Illegal value of nev"):
+        S.EPSSetDimensions(eps2.h, 0, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+
+
+@pytest.mark.parametrize("lock", [True, False])
+def test_svd_test3_golden(lock):
+    Mr, N = 35, 30
+    A = O.grcar_rect(Mr, N)
+    MA, MT = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(MA, MT)
+    CP.use_cpu_bv(svd)
+    S.SVDSetDimensions(svd.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    if not lock:
+        S.SVDTRLanczosSetLocking(svd.h, 0)
+    svd.solve()
+    assert svd.reason > 0 and svd.nconv >= 4
+    sig = [svd.triplet(i) for i in range(4)]
+    assert fmt5(sig) == ["3.22175", "3.21797", "3.16825", "3.15128"]
+    ref = O.svd_trlanczos(A, A.T.tocsr(), Mr, N, nsv=4, lock=lock)
+    assert svd.its == ref.its and svd.nconv == ref.nconv
+    for i in range(4):
+        assert svd.error(i) < 5e-8
+
+
+def test_svd_wide_matrix_swaps():
+    """M < N: SVDSetUp works with the transpose and swaps U/V (svdsetup.c:301-343)"""
+    A = O.grcar_rect(35, 30).T.tocsr()          # 30 x 35
+    MA, MT = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(MA, MT)
+    CP.use_cpu_bv(svd)
+    S.SVDSetDimensions(svd.h, 3, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    svd.solve()
+    assert svd.nconv >= 3
+    sv = np.linalg.svd(A.toarray(), compute_uv=False)
+    v, u = MA.create_vecs()
+    for i in range(3):
+        s = svd.triplet(i, u, v)
+        assert abs(s - sv[i]) < 1e-8 * sv[i]
+        uu, vv = u.get_values(), v.get_values()
+        assert np.linalg.norm(A @ vv - s * uu) < 1e-7 * s
+        assert svd.error(i) < 5e-8
