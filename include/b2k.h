@@ -62,6 +62,20 @@ int  b2k_mem_info(b2k_ctx ctx, size_t *free_bytes, size_t *total_bytes);
 int  b2k_timer_start(b2k_ctx ctx);
 int  b2k_timer_stop_ms(b2k_ctx ctx, double *ms);                                 /* blocking */
 
+/* bytes moved by b2k_h2d* / b2k_d2h* since the context was created (bench: e2e accounting) */
+int  b2k_ctx_copy_bytes(b2k_ctx ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* per-kernel-class timing: CUDA events around every launch of the class on the context's stream
+   (PetscLogGpuTimeBegin/End stand-in, bvcuda.cu:35-38).  b2k_prof_get synchronises. */
+#define B2K_PROF_DOTVEC   0   /* k_dotvec: V^T w (+ w^T w)              */
+#define B2K_PROF_MULTVEC  1   /* k_multvec: y = beta y + alpha V q      */
+#define B2K_PROF_GSFUSED  2   /* k_gs_fused: update + next dot, V once  */
+#define B2K_PROF_SPMV     3   /* k_spmv_csr_stream                      */
+#define B2K_PROF_GEMM     4   /* k_gemm_ts: V Q (restart), Y^T X        */
+#define B2K_PROF_ELEMWISE 5   /* scale / copy / axpby / fill            */
+#define B2K_PROF_NCLASS   6
+int  b2k_prof_enable(b2k_ctx ctx, int on);               /* on: start a fresh recording            */
+int  b2k_prof_get(b2k_ctx ctx, int cls, uint64_t *launches, double *ms, double *algorithmic_bytes);
+
 /* ---- BV level-1/2/3 (replace bvcuda.cu) ------------------------------------------------------ */
 /* q[0:k] = V(:,0:k)^T y                      — BVDotVec_BLAS_CUDA  bvcuda.cu:204-264 (gemv 'C')  */
 int  b2k_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *y, double *q);

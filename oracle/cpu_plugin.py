@@ -33,6 +33,8 @@ def load():
     lib.OracleCPUStreamTriad.argtypes = [ctypes.c_int64, c_int]
     lib.MatCreateOracleCSR.restype = c_int
     lib.MatCreateOracleCSR.argtypes = [c_int] * 6 + [c_vp] * 3 + [c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]
+    lib.MatCreateOracleLaplacian.restype = c_int
+    lib.MatCreateOracleLaplacian.argtypes = [c_int, c_int, c_int, c_int, c_vp]
     SL.chk(lib.OracleCPURegister())
     _lib = lib
     return lib
@@ -113,6 +115,14 @@ def mat_csr(A, rank=0, size=1, cranges=None, exchange=None):
     p = lambda a: a.ctypes.data_as(c_vp)
     SL.chk(_lib.MatCreateOracleCSR(M, N, rs, re, cs, ce, p(rp), p(cl), p(val), nghost, len(rr), p(rr), p(rc), len(sr), p(sr), p(sc), p(si),
                                    m.ref))
+    return m
+
+
+def mat_laplacian(dim, nx, ny=1, nz=1):
+    """host CSR Laplacian built in C (single rank) — the CPU baseline's operator"""
+    lib = load()
+    m = SL.Mat()
+    SL.chk(lib.MatCreateOracleLaplacian(dim, nx, ny, nz, m.ref))
     return m
 
 

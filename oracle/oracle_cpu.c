@@ -459,11 +459,53 @@ PetscErrorCode MatCreateOracleCSR(PetscInt M, PetscInt N, PetscInt rstart, Petsc
   return PETSC_SUCCESS;
 }
 
+/* d-dimensional Laplacian stencil, single rank, natural ordering (ex1.c:37-48, ex2.c:39-54; 7-point analogue) */
+PetscErrorCode MatCreateOracleLaplacian(PetscInt dim, PetscInt nx, PetscInt ny, PetscInt nz, Mat *out)
+{
+  if (dim < 3) nz = 1;
+  if (dim < 2) ny = 1;
+  const int64_t plane = (int64_t)ny * nz, N = (int64_t)nx * plane;
+  PetscCheck(N < 2147483647LL / 8, PETSC_ERR_ARG_OUTOFRANGE, "grid too large");
+  PetscInt *rp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(N + 1));
+  PetscCheck(rp, PETSC_ERR_MEM, "out of memory");
+  rp[0] = 0;
+  for (int64_t g = 0; g < N; g++) {
+    const int64_t i = g / plane, rem = g - i * plane, j = rem / nz, k = rem - j * nz;
+    int c = 1 + (i > 0) + (i < nx - 1);
+    if (dim >= 2) c += (j > 0) + (j < ny - 1);
+    if (dim >= 3) c += (k > 0) + (k < nz - 1);
+    rp[g + 1] = rp[g] + c;
+  }
+  const int64_t nnz = rp[N];
+  PetscInt *ci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)nnz);
+  double *v = (double *)malloc(sizeof(double) * (size_t)nnz);
+  PetscCheck(ci && v, PETSC_ERR_MEM, "out of memory");
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < N; g++) {
+    const int64_t i = g / plane, rem = g - i * plane, j = rem / nz, k = rem - j * nz;
+    int64_t p = rp[g];
+    if (i > 0) { ci[p] = (PetscInt)(g - plane); v[p++] = -1.0; }
+    if (dim >= 2 && j > 0) { ci[p] = (PetscInt)(g - nz); v[p++] = -1.0; }
+    if (dim >= 3 && k > 0) { ci[p] = (PetscInt)(g - 1); v[p++] = -1.0; }
+    ci[p] = (PetscInt)g; v[p++] = 2.0 * dim;
+    if (dim >= 3 && k < nz - 1) { ci[p] = (PetscInt)(g + 1); v[p++] = -1.0; }
+    if (dim >= 2 && j < ny - 1) { ci[p] = (PetscInt)(g + nz); v[p++] = -1.0; }
+    if (i < nx - 1) { ci[p] = (PetscInt)(g + plane); v[p++] = -1.0; }
+  }
+  PetscErrorCode ierr = MatCreateOracleCSR((PetscInt)N, (PetscInt)N, 0, (PetscInt)N, 0, (PetscInt)N, rp, ci, v, 0, 0, NULL, NULL, 0, NULL, NULL, NULL, out);
+  free(rp); free(ci); free(v);
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
 /* a rank that only SENDS halo values still has to take part in the exchange */
 PetscErrorCode MatOracleCSRHasHalo(Mat A, PetscBool *flg) { Mat_CPUCSR *a = (Mat_CPUCSR *)A->data; *flg = (a->nghost || a->nsend) ? PETSC_TRUE : PETSC_FALSE; return PETSC_SUCCESS; }
 
+void scipy_openblas_set_num_threads(int);
+
 PetscErrorCode OracleCPURegister(void)
 {
+  scipy_openblas_set_num_threads(1);   /* parallelism comes from the OpenMP row chunks above; BLAS runs serial inside them */
   static const B2KVecHostOps ops = {hv_set, hv_sumsq, hv_dot, hv_axpy, hv_scale};
   PetscCall(B2KVecRegisterHostOps(&ops));
   PetscCall(BVRegister("oraclecpu", BVCreate_OracleCPU));

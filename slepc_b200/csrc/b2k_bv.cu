@@ -417,8 +417,10 @@ static int launch_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, in
   if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
   const int pstride = ncols;
   dim3 grid(gx, ntiles);
+  PROF_BEGIN(ctx, B2K_PROF_DOTVEC, 8.0 * (double)n * (k + 1));
   if (vec2) k_dotvec<16, true><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
   else      k_dotvec<16, false><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, pstride, ncols, out);
   CKLAUNCH(ctx);
@@ -444,15 +446,18 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
   int gx = grid_rows(ctx, items > 0 ? items : 1, 6);
   if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
   const size_t shm = sizeof(double) * (size_t)(k > 0 ? k : 1);
+  PROF_BEGIN(ctx, B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
   if (nrm_out) {
     if (vec2) k_multvec<true, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
     else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
+    PROF_END(ctx);
     CKLAUNCH(ctx);
     k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, gx, 1, 1, nrm_out);
     CKLAUNCH(ctx);
   } else {
     if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
     else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
+    PROF_END(ctx);
     CKLAUNCH(ctx);
   }
   return B2K_OK;
@@ -538,21 +543,27 @@ extern "C" int b2k_scale(b2k_ctx ctx, double *X, int64_t ld, int64_t n, int k, d
     CK(cudaMemset2DAsync(X, ld * sizeof(double), 0, n * sizeof(double), k, ctx->stream));
     return B2K_OK;
   }
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n * k);
   k_scale<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(X, ld, n, alpha);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
 extern "C" int b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq)
 {
   if (n == 0) return B2K_OK;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n);
   k_scale_rsqrt<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, sumsq);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
 extern "C" int b2k_copy(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int k)
 {
   if (n == 0 || k == 0) return B2K_OK;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n * k);
   k_copy<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(Y, ldy, X, ldx, n);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
@@ -560,14 +571,18 @@ extern "C" int b2k_axpby(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, i
                          double beta)
 {
   if (n == 0 || k == 0) return B2K_OK;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, (beta == 0.0 ? 16.0 : 24.0) * (double)n * k);
   k_axpby<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(Y, ldy, X, ldx, n, alpha, beta);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
 extern "C" int b2k_fill(b2k_ctx ctx, double *x, int64_t n, double v)
 {
   if (n == 0) return B2K_OK;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 8.0 * (double)n);
   k_fill<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, v);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
@@ -593,7 +608,9 @@ static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *I
     CK(cudaFuncSetAttribute(k_gemm_ts<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));             \
     dim3 blk(RB / 4, 16);                                                                                       \
     const int64_t gx = (n + RB - 1) / RB;                                                                       \
+    PROF_BEGIN(ctx, B2K_PROF_GEMM, 8.0 * (double)n * (kin + nout));                                             \
     k_gemm_ts<RB><<<(unsigned)gx, blk, shm, ctx->stream>>>(Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta); \
+    PROF_END(ctx);                                                                                              \
     CKLAUNCH(ctx);                                                                                              \
   } while (0)
   if (sizeof(double) * (size_t)kin * 64 + qbytes <= 96 * 1024) LAUNCH_GEMM(64);

@@ -60,6 +60,7 @@ extern "C" int b2k_ctx_destroy(b2k_ctx c)
   cudaStreamSynchronize(c->stream);
   cudaFree(c->partials);
   cudaFree(c->dscratch);
+  if (c->prof_ev) { for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]); free(c->prof_ev); free(c->prof_id); free(c->prof_bytes); }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -71,6 +72,60 @@ extern "C" int b2k_ctx_sync(b2k_ctx c) { CK(cudaStreamSynchronize(c->stream)); r
 extern "C" void *b2k_ctx_stream(b2k_ctx c) { return (void *)c->stream; }
 extern "C" int b2k_ctx_sm_count(b2k_ctx c) { return c->sm_count; }
 extern "C" int b2k_ctx_launches(b2k_ctx c, uint64_t *n) { *n = c->launches; return B2K_OK; }
+extern "C" int b2k_ctx_copy_bytes(b2k_ctx c, uint64_t *h2d, uint64_t *d2h)
+{
+  if (h2d) *h2d = c->h2d_bytes;
+  if (d2h) *d2h = c->d2h_bytes;
+  return B2K_OK;
+}
+
+#define B2K_PROF_CAP 16384
+static int prof_flush(b2k_ctx c)
+{
+  if (c->prof_n == 0) return B2K_OK;
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->prof_n; i++) {
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    const int id = c->prof_id[i];
+    c->prof_ms[id] += (double)f;
+    c->prof_b[id] += c->prof_bytes[i];
+    c->prof_cnt[id]++;
+  }
+  c->prof_n = 0;
+  return B2K_OK;
+}
+extern "C" int b2k_prof_enable(b2k_ctx c, int on)
+{
+  if (on) {
+    if (!c->prof_ev) {
+      c->prof_cap = B2K_PROF_CAP;
+      c->prof_ev = (cudaEvent_t *)calloc(2 * (size_t)c->prof_cap, sizeof(cudaEvent_t));
+      c->prof_id = (int *)calloc((size_t)c->prof_cap, sizeof(int));
+      c->prof_bytes = (double *)calloc((size_t)c->prof_cap, sizeof(double));
+      if (!c->prof_ev || !c->prof_id || !c->prof_bytes) return B2K_ERR_MEM;
+      for (int i = 0; i < 2 * c->prof_cap; i++) CK(cudaEventCreate(&c->prof_ev[i]));
+    }
+    c->prof_n = 0;
+    for (int i = 0; i < B2K_PROF_NCLASS; i++) { c->prof_ms[i] = 0.0; c->prof_b[i] = 0.0; c->prof_cnt[i] = 0; }
+    c->prof_on = 1;
+  } else {
+    int rc = prof_flush(c);
+    c->prof_on = 0;
+    return rc;
+  }
+  return B2K_OK;
+}
+extern "C" int b2k_prof_get(b2k_ctx c, int cls, uint64_t *launches, double *ms, double *bytes)
+{
+  ARGCHK(cls >= 0 && cls < B2K_PROF_NCLASS, "kernel class out of range");
+  int rc = prof_flush(c);
+  if (rc) return rc;
+  if (launches) *launches = c->prof_cnt[cls];
+  if (ms) *ms = c->prof_ms[cls];
+  if (bytes) *bytes = c->prof_b[cls];
+  return B2K_OK;
+}
 
 extern "C" int b2k_malloc(b2k_ctx c, void **p, size_t bytes)
 {
@@ -89,23 +144,27 @@ extern "C" int b2k_free(b2k_ctx c, void *p)
 extern "C" int b2k_memset0(b2k_ctx c, void *p, size_t bytes) { CK(cudaMemsetAsync(p, 0, bytes, c->stream)); return B2K_OK; }
 extern "C" int b2k_h2d(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
+  c->h2d_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return B2K_OK;
 }
 extern "C" int b2k_d2h(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
+  c->d2h_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return B2K_OK;
 }
 extern "C" int b2k_h2d_async(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
+  c->h2d_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return B2K_OK;
 }
 extern "C" int b2k_d2h_async(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
+  c->d2h_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   return B2K_OK;
 }

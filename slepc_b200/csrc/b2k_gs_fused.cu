@@ -280,7 +280,9 @@ int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n,
   int grid = ctx->sm_count;
   if ((int64_t)grid > ntiles) grid = (int)(ntiles > 0 ? ntiles : 1);
   const int pstride = k + 1;
+  PROF_BEGIN(ctx, B2K_PROF_GSFUSED, 8.0 * (double)n * (k + 2));
   k_gs_fused<<<grid, F_THREADS, shm, ctx->stream>>>(V, ld, n, k, w, cin, ctx->partials, pstride, nstages);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return b2k_launch_reduce_partials(ctx, grid, pstride, k + 1, cout);
 }

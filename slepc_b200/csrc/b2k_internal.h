@@ -16,7 +16,26 @@ struct b2k_ctx_s {
   size_t       dscratch_elems;
   cudaEvent_t  ev0, ev1;
   uint64_t     launches;
+  uint64_t     h2d_bytes, d2h_bytes;
+  /* optional per-kernel-class timing with CUDA events on the launching stream (b2k_prof_*) */
+  int          prof_on, prof_n, prof_cap;
+  cudaEvent_t *prof_ev;         /* 2 events per recorded launch */
+  int         *prof_id;
+  double      *prof_bytes;
+  double       prof_ms[B2K_PROF_NCLASS], prof_b[B2K_PROF_NCLASS];
+  uint64_t     prof_cnt[B2K_PROF_NCLASS];
 };
+
+/* bracket the dominant kernel of an entry point; `bytes` = algorithmic bytes of this launch */
+#define PROF_BEGIN(ctx, cls, bytes)                                                          \
+  const int prof_slot_ = ((ctx)->prof_on && (ctx)->prof_n < (ctx)->prof_cap) ? (ctx)->prof_n++ : -1; \
+  if (prof_slot_ >= 0) {                                                                      \
+    (ctx)->prof_id[prof_slot_] = (cls);                                                       \
+    (ctx)->prof_bytes[prof_slot_] = (double)(bytes);                                          \
+    cudaEventRecord((ctx)->prof_ev[2 * prof_slot_], (ctx)->stream);                           \
+  }
+#define PROF_END(ctx)                                                                         \
+  if (prof_slot_ >= 0) cudaEventRecord((ctx)->prof_ev[2 * prof_slot_ + 1], (ctx)->stream);
 
 #define B2K_MAX_PART_BLOCKS 2048
 #define B2K_MAX_K           1024     /* max columns in one reduction (ncv+1 <= 1024)              */

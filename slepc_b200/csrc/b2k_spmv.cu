@@ -129,6 +129,7 @@ extern "C" int b2k_csr_create(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, i
     CK(cudaMemcpyAsync(A->val, val_host, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->h2d_bytes += sizeof(int) * (size_t)(nrows + 1) + (sizeof(int) + sizeof(double)) * (size_t)A->nnz;
   int rc = finish_create(ctx, A, rowptr_host);
   if (rc) return rc;
   *out = A;
@@ -184,8 +185,10 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
 {
   if (A->nrows == 0) return B2K_OK;
   ARGCHK(x != y, "SpMV cannot run in place");
+  PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 4.0 * (double)(A->nrows + 1) + 8.0 * (double)(A->ncols_local + A->nghost) + 8.0 * (double)A->nrows);
   k_spmv_csr_stream<<<A->nblk, SPMV_THREADS, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->blkrow, x,
                                                                  xghost ? xghost : x, (int)A->ncols_local, y, sigma);
+  PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
 }

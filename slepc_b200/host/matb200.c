@@ -118,7 +118,13 @@ PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscIn
     PetscCheck(colidx[k] >= 0 && colidx[k] < N, PETSC_ERR_ARG_OUTOFRANGE, "column index %d outside [0,%d)", colidx[k], N);
     if (colidx[k] < cstart || colidx[k] >= cend) noff++;
   }
-  PetscInt *loc = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  if (!noff && cstart == 0) {                     /* all columns owned and already locally numbered: upload as is */
+    int rc0 = b2k_csr_create(ctx, m, ncl, 0, rowptr, colidx, val, &a->A);
+    if (rc0) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_create failed (%d): %s", rc0, b2k_last_error()); }
+    *out = A;
+    return PETSC_SUCCESS;
+  }
+  PetscInt *loc = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nnz + 1));
   PetscCheck(loc, PETSC_ERR_MEM, "out of memory");
   if (noff) {
     PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)noff), ng = 0;

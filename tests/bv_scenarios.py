@@ -239,12 +239,19 @@ def scenario_orthog_vs_oracle(make_bv, otype, refine, n, k, tol):
     Xo.orthog_type, Xo.orthog_ref = otype, refine
     nrm, lin = c_dbl(), c_int()
     H = np.zeros(k + 1)
+    scale = float(np.linalg.norm(A, axis=0).max())
+    norms = []
     for j in range(k):
         S.BVOrthogonalizeColumn(X.h, j, H.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nrm), ctypes.byref(lin))
         ho, no, lo = Xo.orthogonalize_column(j)
         assert bool(lin.value) == bool(lo)
         assert abs(nrm.value - no) <= 1e-7 * max(1.0, abs(no))
-        assert np.allclose(H[:j], ho, rtol=1e-6, atol=1e-8)
+        # a coefficient against q_i carries the rounding of column i amplified by ||a||/||r_i|| (r_i = column i before
+        # normalisation): near-dependent columns (5 and 9) are amplified noise directions in BOTH implementations
+        # and every later basis vector inherits that perturbation
+        atol = 1e-13 * scale * scale / min(norms) if norms else 0.0
+        assert np.all(np.abs(H[:j] - ho) <= atol + 1e-12 * np.abs(ho)), (j, np.abs(H[:j] - ho), atol)
+        norms.append(no)
         S.BVScaleColumn(X.h, j, 1.0 / nrm.value)
         Xo.scale_column(j, 1.0 / no)
     Q = X.to_numpy()

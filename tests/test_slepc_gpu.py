@@ -1,0 +1,310 @@
+"""GPU parity tests of the product path: BV type "b200" + Mat type "b200csr" (sm_100a kernels through the
+C ABI) driven by the C host side, against the oracle (numpy restatement + CPU plug-in) and the reference's
+golden outputs.  Tolerances: eigen/singular values 1e-10 relative (north star), residuals below the requested
+tol (5*tol as the reference's -terse check, epsview.c:314-320), subspace angles 1e-6.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import slepc_oracle as O
+from slepc_b200 import slepc as SL
+from slepc_b200.slepc import S, c_dbl, c_int
+
+import bv_scenarios as SC
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    SL.initialize(0)
+    yield
+
+
+def make_bv(n, m):
+    return SL.BV.create(n, m, bvtype="b200")
+
+
+def fmt5(v):
+    return [f"{x:.5f}" for x in v]
+
+
+# ---- the reference's BV programs with -bv_type b200 -------------------------------------------------------
+def test_bv_test1():
+    SC.scenario_test1(make_bv)
+
+
+def test_bv_test2():
+    SC.scenario_test2(make_bv)
+
+
+@pytest.mark.parametrize("trans", [False, True])
+def test_bv_test4(trans):
+    SC.scenario_test4(make_bv, trans=trans)
+
+
+def test_bv_test13():
+    SC.scenario_test13(make_bv)
+
+
+def test_bv_errors():
+    SC.scenario_errors(make_bv)
+
+
+@pytest.mark.parametrize("fuse", ["0", "1", "2"])
+@pytest.mark.parametrize("otype,refine", [(SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED), (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_ALWAYS),
+                                          (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_NEVER), (SL.BV_ORTHOG_MGS, SL.BV_ORTHOG_REFINE_IFNEEDED)])
+def test_bv_orthog_variants_match_oracle(monkeypatch, otype, refine, fuse):
+    monkeypatch.setenv("B2K_BV_FUSE", fuse)
+    SC.scenario_orthog_vs_oracle(make_bv, otype, refine, n=3001, k=12, tol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 4096, 100003])
+def test_bv_orthonormalize_sizes(n):
+    """ragged / tiny / odd local sizes through the fused Gram-Schmidt hook"""
+    k = min(n, 9)
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, k))
+    X = make_bv(n, k)
+    X.from_numpy(A)
+    nrm, lin = c_dbl(), c_int()
+    for j in range(k):
+        S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
+        assert not lin.value
+    Q = X.to_numpy()
+    assert np.linalg.norm(Q.T @ Q - np.eye(k), 1) < 100 * k * EPS
+    Qr, _ = np.linalg.qr(A)
+    assert np.linalg.norm(Q - Qr @ (Qr.T @ Q)) < 1e-10
+    X.destroy()
+
+
+def test_bv_lindep_detected():
+    n, k = 5000, 4
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, k))
+    A[:, 3] = A[:, 0] - 2 * A[:, 2]
+    X = make_bv(n, k)
+    X.from_numpy(A)
+    nrm, lin = c_dbl(), c_int()
+    for j in range(k):
+        S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
+        assert bool(lin.value) == (j == 3)
+    X.destroy()
+
+
+# ---- solvers ----------------------------------------------------------------------------------------------
+def solve_eps(M, nev, hermitian=True, ncv=None, tol=None, which=None, v0=None, lock=True):
+    eps = SL.EPS(M, hermitian=hermitian)
+    S.EPSSetDimensions(eps.h, nev, ncv if ncv else SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    if tol:
+        S.EPSSetTolerances(eps.h, tol, SL.PETSC_CURRENT)
+    if which:
+        S.EPSSetWhichEigenpairs(eps.h, which)
+    if not lock:
+        S.EPSKrylovSchurSetLocking(eps.h, 0)
+    keep = [M]
+    if v0 is not None:
+        r, _ = M.create_vecs()
+        r.set_values(v0)
+        S.EPSSetInitialSpace(eps.h, 1, (ctypes.c_void_p * 1)(r.h))
+        keep.append(r)
+    eps.solve()
+    eps._keep = keep
+    return eps
+
+
+def eigvecs(eps, M):
+    r, _ = M.create_vecs()
+    out = []
+    for i in range(eps.nconv):
+        eps.eigenpair(i, r)
+        out.append(r.get_values())
+    return np.array(out).T
+
+
+def subspace_angle(X, Y):
+    """largest principal angle between span(X) and span(Y)"""
+    Qx, _ = np.linalg.qr(X)
+    Qy, _ = np.linalg.qr(Y)
+    s = np.linalg.svd(Qx.T @ Qy, compute_uv=False)
+    return float(np.arccos(np.clip(s.min(), -1, 1)))
+
+
+def test_spmv_matches_scipy_generic_csr():
+    import scipy.sparse as sp
+    A = sp.random(3000, 2500, density=0.004, random_state=1, format="csr")
+    M = SL.Mat.b200csr(A)
+    x, y = M.create_vecs()
+    xv = np.random.default_rng(2).standard_normal(2500)
+    x.set_values(xv)
+    M.mult(x, y)
+    assert np.allclose(y.get_values(), A @ xv, rtol=1e-13, atol=1e-13)
+    T = M.transpose()
+    tx, ty = T.create_vecs()
+    uv = np.random.default_rng(3).standard_normal(3000)
+    tx.set_values(uv)
+    T.mult(tx, ty)
+    assert np.allclose(ty.get_values(), A.T @ uv, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("dim,dims", [(1, (1000, 1, 1)), (2, (37, 41, 1)), (3, (11, 13, 17))])
+def test_laplacian_generator_matches_oracle(dim, dims):
+    nx, ny, nz = dims
+    M = SL.Mat.laplacian(dim, nx, ny, nz)
+    A = {1: lambda: O.laplacian_1d(nx), 2: lambda: O.laplacian_2d(nx, ny), 3: lambda: O.laplacian_3d(nx, ny, nz)}[dim]()
+    x, y = M.create_vecs()
+    xv = np.random.default_rng(5).standard_normal(A.shape[0])
+    x.set_values(xv)
+    M.mult(x, y)
+    assert np.allclose(y.get_values(), A @ xv, rtol=1e-14, atol=1e-13)
+
+
+def test_eps_test4_golden():
+    eps = solve_eps(SL.Mat.laplacian(1, 30), 4, tol=1000 * EPS)
+    assert eps.reason > 0 and eps.nconv >= 4
+    assert fmt5([eps.eigenvalue(i)[0] for i in range(4)]) == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    for i in range(4):
+        assert eps.error(i) < 5 * 1000 * EPS
+
+
+def test_eps_ex2_golden_and_oracle_parity():
+    nx = 72
+    M = SL.Mat.laplacian(2, nx, nx)
+    eps = solve_eps(M, 4, ncv=20)
+    A = O.laplacian_2d(nx)
+    ref = O.eps_krylovschur(A, nx * nx, nev=4, ncv=20)
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(eps.nconv)])
+    th = 2 - 2 * np.cos(np.arange(1, nx + 1) * np.pi / (nx + 1))
+    analytic = np.sort((th[:, None] + th[None, :]).ravel())[::-1]
+    for i in range(eps.nconv):
+        assert np.min(np.abs(analytic - lam[i])) < 1e-10 * lam[i]        # every value is an eigenvalue to 1e-10
+        assert eps.error(i) < 5e-8
+    gold = ["7.99630", "7.99074", "7.98519", "7.98150"]
+    got = fmt5(lam[:4])
+    assert got[0] == gold[0] and set(got) <= set(gold)
+    # same number of converged pairs and the same values as the oracle run from the same start vector
+    assert eps.nconv == ref.nconv
+    assert np.allclose(np.sort(lam), np.sort(ref.eigr[:ref.nconv]), rtol=1e-10, atol=0)
+    # eigenvectors: compare by subspace angle against the full analytic eigenspaces spanned by the oracle's vectors
+    X = eigvecs(eps, M)
+    assert subspace_angle(X[:, :1], ref.X[:, ref.perm[:1]]) < 1e-6
+
+
+@pytest.mark.parametrize("lock", [True, False])
+def test_eps_ex5_markov_golden(lock):
+    m = 15
+    A = O.markov_model(m)
+    N = m * (m + 1) // 2
+    v0 = np.zeros(N)
+    v0[:3] = 1.0
+    M = SL.Mat.b200csr(A)
+    eps = solve_eps(M, 4, hermitian=False, which=SL.EPS_LARGEST_REAL, v0=v0, lock=lock)
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = [eps.eigenvalue(i) for i in range(4)]
+    assert fmt5([l[0] for l in lam]) == ["1.00000", "0.97137", "0.90423", "0.85714"]
+    ref = O.eps_krylovschur(A, N, nev=4, which="largest_real", hermitian=False, v0=v0, lock=lock)
+    assert eps.nconv == ref.nconv
+    assert np.allclose([l[0] for l in lam], ref.eigr[ref.perm][:4], rtol=1e-10)
+    X = eigvecs(eps, M)
+    for i in range(4):
+        assert eps.error(i) < 5e-8
+        assert subspace_angle(X[:, i:i + 1], ref.X[:, ref.perm[i]:ref.perm[i] + 1]) < 1e-6
+
+
+def test_eps_markov_medium_vs_oracle():
+    """ex5-style Markov matrix, m=120 (N=7260): nev=8 largest real part as in BASELINE config 4"""
+    m = 120
+    A = O.markov_model(m)
+    N = A.shape[0]
+    v0 = np.zeros(N)
+    v0[:3] = 1.0
+    M = SL.Mat.b200csr(A)
+    eps = solve_eps(M, 8, hermitian=False, which=SL.EPS_LARGEST_REAL, v0=v0)
+    ref = O.eps_krylovschur(A, N, nev=8, which="largest_real", hermitian=False, v0=v0)
+    assert eps.reason > 0 and eps.nconv == ref.nconv
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(8)])
+    assert abs(lam[0] - 1.0) < 1e-10
+    assert np.allclose(lam, ref.eigr[ref.perm][:8], rtol=1e-10)
+    for i in range(8):
+        assert eps.error(i) < 5e-8
+
+
+def test_eps_3d_laplacian_multiplets():
+    """7-point Laplacian 24^3, nev=10: every returned value is an analytic eigenvalue to 1e-10 (multiset-aware,
+    SURVEY.md §7) and the invariant subspace is accurate."""
+    nx = 24
+    M = SL.Mat.laplacian(3, nx, nx, nx)
+    eps = solve_eps(M, 10)
+    assert eps.reason > 0 and eps.nconv >= 10
+    th = 2 - 2 * np.cos(np.arange(1, nx + 1) * np.pi / (nx + 1))
+    analytic = np.sort((th[:, None, None] + th[None, :, None] + th[None, None, :]).ravel())[::-1]
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(eps.nconv)])
+    assert np.all(np.diff(lam) <= 1e-12)
+    for i in range(eps.nconv):
+        assert np.min(np.abs(analytic - lam[i])) < 1e-10 * lam[i]
+        assert eps.error(i) < 5e-8
+    X = eigvecs(eps, M)
+    assert np.linalg.norm(X.T @ X - np.eye(eps.nconv), 1) < 1e-10
+
+
+@pytest.mark.parametrize("lock", [True, False])
+def test_svd_test3_golden(lock):
+    Mr, N = 35, 30
+    A = O.grcar_rect(Mr, N)
+    MA = SL.Mat.b200csr(A)
+    svd = SL.SVD(MA)
+    S.SVDSetDimensions(svd.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    if not lock:
+        S.SVDTRLanczosSetLocking(svd.h, 0)
+    svd.solve()
+    assert svd.reason > 0 and svd.nconv >= 4
+    assert fmt5([svd.triplet(i) for i in range(4)]) == ["3.22175", "3.21797", "3.16825", "3.15128"]
+    ref = O.svd_trlanczos(A, A.T.tocsr(), Mr, N, nsv=4, lock=lock)
+    assert svd.nconv == ref.nconv
+    assert np.allclose([svd.triplet(i) for i in range(4)], ref.sigma[:4], rtol=1e-10)
+    for i in range(4):
+        assert svd.error(i) < 5e-8
+
+
+def test_svd_random_sparse_vs_oracle():
+    """BASELINE config 5 shape (tall random sparse, ~20 nnz/row) at a size the oracle finishes in seconds"""
+    import scipy.sparse as sp
+    Mr, N = 20000, 4000
+    rng = np.random.default_rng(20261017)
+    rows = np.repeat(np.arange(Mr), 20)
+    cols = rng.integers(0, N, size=Mr * 20)
+    vals = rng.standard_normal(Mr * 20)
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(Mr, N))
+    A.sum_duplicates()
+    MA = SL.Mat.b200csr(A)
+    svd = SL.SVD(MA)
+    S.SVDSetDimensions(svd.h, 10, 20, SL.PETSC_DETERMINE)
+    svd.solve()
+    ref = O.svd_trlanczos(A, A.T.tocsr(), Mr, N, nsv=10, ncv=20)
+    assert svd.reason > 0 and svd.nconv == ref.nconv
+    sig = np.array([svd.triplet(i) for i in range(10)])
+    assert np.allclose(sig, ref.sigma[:10], rtol=1e-10)
+    v, u = MA.create_vecs()
+    for i in range(10):
+        assert svd.error(i) < 5e-8
+        svd.triplet(i, u, v)
+        assert subspace_angle(v.get_values()[:, None], ref.V[:, i:i + 1]) < 1e-6
+
+
+def test_eps_restart_cycles_api_matches_solve():
+    M = SL.Mat.laplacian(2, 40, 40)
+    a = solve_eps(M, 3, ncv=12)
+    b = SL.EPS(M, hermitian=True)
+    S.EPSSetDimensions(b.h, 3, 12, SL.PETSC_DETERMINE)
+    n = 0
+    while True:
+        done = b.cycles(2)
+        n += done
+        if done < 2:
+            break
+    assert b.its == a.its and b.nconv == a.nconv
+    assert np.allclose([a.eigenvalue(i)[0] for i in range(a.nconv)], [b.eigenvalue(i)[0] for i in range(b.nconv)], rtol=0, atol=0)
