@@ -463,22 +463,30 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
   return B2K_OK;
 }
 
+int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                            double *cout);   /* b2k_gs_fused.cu (TMA-staged) */
+int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
+                     const double *q, int dot, double *out);   /* b2k_gs_rt.cu (register tile) */
+int b2k_gs_fused_enabled(void);
+
 extern "C" int b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
                            const double *q)
 {
+  if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
+    int rc = b2k_gs_rt_launch(ctx, V, ld, n, k, alpha, beta, y, q, 0, nullptr);
+    if (rc != -1) return rc;
+  }
   return launch_multvec(ctx, V, ld, n, k, alpha, beta, y, q, nullptr);
 }
-
-int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
-                            double *cout);   /* b2k_gs_fused.cu */
-int b2k_gs_fused_enabled(void);
 
 extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
                                  double *cout)
 {
-  if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
-    int rc = b2k_gs_update_dot_fused(ctx, V, ld, n, k, w, cin, cout);
-    if (rc != -1) return rc;       /* -1: shape not supported by the fused kernel → two-sweep path */
+  const int mode = b2k_gs_fused_enabled();
+  if (mode && k > 0 && n > 0) {
+    int rc = (mode == 2) ? b2k_gs_update_dot_fused(ctx, V, ld, n, k, w, cin, cout)
+                         : b2k_gs_rt_launch(ctx, V, ld, n, k, -1.0, 1.0, w, cin, 1, cout);
+    if (rc != -1) return rc;       /* -1: shape not supported by the single-sweep kernels → two-sweep path */
   }
   /* two-sweep path: update sweep, then dot sweep (V read twice) */
   int rc = launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nullptr);
@@ -490,6 +498,10 @@ extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64
 extern "C" int b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
                                   double *nrm2_out)
 {
+  if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
+    int rc = b2k_gs_rt_launch(ctx, V, ld, n, k, -1.0, 1.0, w, cin, 0, nrm2_out);
+    if (rc != -1) return rc;
+  }
   return launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nrm2_out);
 }
 
@@ -594,12 +606,19 @@ extern "C" int b2k_set_random(b2k_ctx ctx, double *x, int64_t n, int64_t row0, u
   return B2K_OK;
 }
 
+int b2k_vq_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout, const double *Q,
+                  int ldq, int qtrans, double alpha, double beta);   /* b2k_vq.cu */
+
 static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout,
                           const double *Q, int ldq, int qtrans, double alpha, double beta)
 {
   if (n == 0 || nout == 0) return B2K_OK;
   ARGCHK(kin >= 0 && kin <= 2048, "kin out of range");
   if (kin == 0) return b2k_scale(ctx, Out, ldo, n, nout, beta);
+  {
+    int rc = b2k_vq_launch(ctx, Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta);   /* kin, nout <= 64: the restart shape */
+    if (rc != -1) return rc;
+  }
   const size_t qbytes = sizeof(double) * GEMM_KC * 64;
   const size_t lim = 200 * 1024;
 #define LAUNCH_GEMM(RB)                                                                                         \

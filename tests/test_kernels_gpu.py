@@ -98,10 +98,10 @@ def test_gs_update_dot_matches_cgs_pass(ctx, n, k):
 
 
 @pytest.mark.parametrize("k", [1, 5, 8, 9, 16, 17, 31, 33, 48, 64])
-@pytest.mark.parametrize("n", [128, 130, 128 * 7 + 1, 128 * 148 * 3 + 77, 1 << 20])
+@pytest.mark.parametrize("n", [1, 63, 128, 130, 128 * 7 + 1, 128 * 148 * 3 + 77, 1 << 20])
 def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
-    """The TMA-staged single-sweep kernel and the two-sweep path compute the same w and c
-    (different reduction order ⇒ compare to rounding, and each against the float64 reference)."""
+    """The single-sweep kernels (1: register tile, 2: TMA-staged) and the two-sweep path (0) compute the same w
+    and c (different reduction order ⇒ compare to rounding, and each against the float64 reference)."""
     from slepc_b200._b2k import check
     ld = n + (n % 2) + 2
     rng = np.random.default_rng(100 + k)
@@ -111,21 +111,21 @@ def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
     cin = rng.standard_normal(k + 1)
     dV, dc = ctx.to_device(H), ctx.to_device(cin)
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         check(ctx.lib.b2k_gs_set_fused(mode))
         dw = ctx.to_device(w)
         co = ctx.empty(k + 1)
         check(ctx.lib.b2k_gs_update_dot(ctx.h, dV.ptr, ld, n, k, dw.ptr, dc.ptr, co.ptr))
         out[mode] = (dw.to_host(), co.to_host())
-        if mode == 1:   # determinism of the fused kernel
+        if mode >= 1:   # determinism of the single-sweep kernels
             dw2 = ctx.to_device(w)
             co2 = ctx.empty(k + 1)
             check(ctx.lib.b2k_gs_update_dot(ctx.h, dV.ptr, ld, n, k, dw2.ptr, dc.ptr, co2.ptr))
-            assert np.array_equal(dw2.to_host(), out[1][0]) and np.array_equal(co2.to_host(), out[1][1])
+            assert np.array_equal(dw2.to_host(), out[mode][0]) and np.array_equal(co2.to_host(), out[mode][1])
     check(ctx.lib.b2k_gs_set_fused(1))
     wref = w - H[:n] @ cin[:k]
     cref = np.concatenate([H[:n].T @ wref, [wref @ wref]])
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         assert np.allclose(out[mode][0], wref, rtol=1e-13, atol=1e-13 * np.sqrt(k)), mode
         assert np.allclose(out[mode][1], cref, rtol=1e-12, atol=1e-12 * np.sqrt(n)), mode
 
@@ -165,7 +165,8 @@ def test_level1(ctx):
     assert np.all(x.to_host() == 1.5)
 
 
-@pytest.mark.parametrize("n,kin,nout", [(1000, 5, 3), (4097, 64, 32), (100003, 33, 70), (50, 200, 7), (333, 700, 5)])
+@pytest.mark.parametrize("n,kin,nout", [(1000, 5, 3), (4097, 64, 32), (100003, 33, 70), (50, 200, 7), (333, 700, 5),
+                                        (4096, 64, 32), (100002, 48, 20), (130, 64, 64), (2, 3, 2), (33000, 17, 47)])
 def test_mult(ctx, n, kin, nout):
     from slepc_b200._b2k import check
     ldx, ldy, ldq = n + 2, n + 4, kin + 3
@@ -183,7 +184,8 @@ def test_mult(ctx, n, kin, nout):
 
 
 @pytest.mark.parametrize("trans", [0, 1])
-@pytest.mark.parametrize("n,k,s,e", [(10, 5, 1, 3), (4099, 64, 0, 40), (100003, 48, 5, 48), (1000, 65, 0, 65)])
+@pytest.mark.parametrize("n,k,s,e", [(10, 5, 1, 3), (4099, 64, 0, 40), (100003, 48, 5, 48), (1000, 65, 0, 65),
+                                     (4098, 64, 0, 40), (100002, 48, 5, 48), (126, 17, 3, 17), (70000, 64, 0, 64), (1000, 64, 20, 21)])
 def test_mult_inplace(ctx, n, k, s, e, trans):
     """BVMultInPlace semantics (bvblas.c:74-106): V(:,s:e) = V(:,0:k) Q(0:k,s:e), other columns untouched."""
     from slepc_b200._b2k import check

@@ -85,13 +85,23 @@ def test_bv_lindep_detected():
     n, k = 5000, 4
     rng = np.random.default_rng(0)
     A = rng.standard_normal((n, k))
-    A[:, 3] = A[:, 0] - 2 * A[:, 2]
+    A[:, 2] = A[:, 0] - 2 * A[:, 1]        # exactly dependent: what is left is rounding noise that DGKS happily
+    A[:, 3] = 0.0                          # re-orthogonalises (oracle: 3 passes, lindep False); a zero column IS flagged
     X = make_bv(n, k)
     X.from_numpy(A)
+    Xo = O.BV(n, k)
+    Xo.V[:] = A
     nrm, lin = c_dbl(), c_int()
     for j in range(k):
+        p0, q0 = X.counters()[0], Xo.npasses
         S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
-        assert bool(lin.value) == (j == 3)
+        no, lo = Xo.orthonormalize_column(j)
+        assert bool(lin.value) == bool(lo) == (j == 3)
+        assert X.counters()[0] - p0 == Xo.npasses - q0
+        if j == 2:
+            assert nrm.value < 1e-12 and no < 1e-12
+        if j == 3:
+            assert nrm.value == 0.0
     X.destroy()
 
 
@@ -223,14 +233,16 @@ def test_eps_markov_medium_vs_oracle():
     v0 = np.zeros(N)
     v0[:3] = 1.0
     M = SL.Mat.b200csr(A)
-    eps = solve_eps(M, 8, hermitian=False, which=SL.EPS_LARGEST_REAL, v0=v0)
-    ref = O.eps_krylovschur(A, N, nev=8, which="largest_real", hermitian=False, v0=v0)
-    assert eps.reason > 0 and eps.nconv == ref.nconv
+    # non-normal matrix: an eigenvalue is only as accurate as its residual (times a condition number), so the
+    # 1e-10 eigenvalue parity of the north star is tested with residuals driven below it
+    eps = solve_eps(M, 8, hermitian=False, which=SL.EPS_LARGEST_REAL, v0=v0, tol=1e-12)
+    ref = O.eps_krylovschur(A, N, nev=8, which="largest_real", hermitian=False, v0=v0, tol=1e-12)
+    assert eps.reason > 0 and eps.nconv >= 8 and ref.nconv >= 8
     lam = np.array([eps.eigenvalue(i)[0] for i in range(8)])
     assert abs(lam[0] - 1.0) < 1e-10
     assert np.allclose(lam, ref.eigr[ref.perm][:8], rtol=1e-10)
     for i in range(8):
-        assert eps.error(i) < 5e-8
+        assert eps.error(i) < 5e-12
 
 
 def test_eps_3d_laplacian_multiplets():
