@@ -97,7 +97,10 @@ def test_bv_lindep_detected():
         S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
         no, lo = Xo.orthonormalize_column(j)
         assert bool(lin.value) == bool(lo) == (j == 3)
-        assert X.counters()[0] - p0 == Xo.npasses - q0
+        if j == 2:                         # what DGKS sees after pass 1 is pure rounding noise: 2 or 3 passes depending on
+            assert X.counters()[0] - p0 in (2, 3) and Xo.npasses - q0 in (2, 3)       # the reduction order (bvorthog.c:180)
+        else:
+            assert X.counters()[0] - p0 == Xo.npasses - q0
         if j == 2:
             assert nrm.value < 1e-12 and no < 1e-12
         if j == 3:
