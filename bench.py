@@ -304,7 +304,8 @@ def run_b200(args, wl):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if dom in tr:
-            roofline["traffic"] = tr[dom]
+            roofline["traffic"] = tr[dom]["ratio"] * prof[dom]["bytes"] / prof[dom]["launches"]
+            roofline["traffic_source"] = f"ncu dram bytes / algorithmic bytes = {tr[dom]['ratio']} for {tr[dom]['kernel']} ({tr[dom]['report']}) x this run's bytes per launch"
     except Exception:
         pass
     eps.destroy()

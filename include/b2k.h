@@ -123,8 +123,10 @@ int  b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int
 /* x *= 1/sqrt(sumsq[0]) guarded (no-op if sumsq is 0 or 1): normalisation with the norm still on
    the device                                  — BVOrthonormalizeColumn bvorthog.c:417-422        */
 int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
-/* select the single-sweep (1) or the two-sweep (0) implementation of b2k_gs_update_dot (default 1; env B2K_GS_FUSED) */
-int  b2k_gs_set_fused(int on);
+/* implementation of the update sweeps (b2k_multvec, b2k_gs_update_norm, b2k_gs_update_dot); env B2K_GS_FUSED:
+   0 generic kernels, two sweeps for update+dot; 1 register-tile single sweep; 2 1-D bulk-copy staged single sweep;
+   3 (default) 2-D tensor-map (TMA) pipelined single sweep, register tile for k <= 4 or fewer than 4096 rows       */
+int  b2k_gs_set_fused(int mode);
 
 /* ---- sparse matrix-vector product (replaces PETSc MatMult behind bvops.c:879 / stsolve.c:22) -- */
 /* CSR with int32 indices.  Column indices < ncols_local address x, the rest address

@@ -374,7 +374,7 @@ static PetscErrorCode MatMult_CPUCSR(Mat A, Vec x, Vec y)
 {
   Mat_CPUCSR *a = (Mat_CPUCSR *)A->data;
   const double *xx = x->array;
-  if (a->nghost) {
+  if (a->nghost || a->nsend) {                      /* a rank that only SENDS still takes part in the exchange */
     memcpy(a->xfull, x->array, sizeof(double) * (size_t)A->n);
     for (PetscInt i = 0; i < a->nsendtot; i++) a->sendbuf[i] = x->array[a->sendidx[i]];
     /* pairwise exchange in rank order (the callback is a blocking sendrecv) */

@@ -467,13 +467,26 @@ int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n,
                             double *cout);   /* b2k_gs_fused.cu (TMA-staged) */
 int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
                      const double *q, int dot, double *out);   /* b2k_gs_rt.cu (register tile) */
+int b2k_gs_tma_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
+                      const double *q, int dot, double *out);  /* b2k_gs_tma.cu (2-D tensor-map pipeline) */
 int b2k_gs_fused_enabled(void);
+
+/* single-sweep update kernels in order of preference for the selected mode; -1 = shape not supported */
+static int gs_single_sweep(b2k_ctx ctx, int mode, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
+                           const double *q, int dot, double *out)
+{
+  if (mode == 3) {
+    int rc = b2k_gs_tma_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out);
+    if (rc != -1) return rc;
+  }
+  return b2k_gs_rt_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out);
+}
 
 extern "C" int b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
                            const double *q)
 {
   if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
-    int rc = b2k_gs_rt_launch(ctx, V, ld, n, k, alpha, beta, y, q, 0, nullptr);
+    int rc = gs_single_sweep(ctx, b2k_gs_fused_enabled(), V, ld, n, k, alpha, beta, y, q, 0, nullptr);
     if (rc != -1) return rc;
   }
   return launch_multvec(ctx, V, ld, n, k, alpha, beta, y, q, nullptr);
@@ -485,7 +498,7 @@ extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64
   const int mode = b2k_gs_fused_enabled();
   if (mode && k > 0 && n > 0) {
     int rc = (mode == 2) ? b2k_gs_update_dot_fused(ctx, V, ld, n, k, w, cin, cout)
-                         : b2k_gs_rt_launch(ctx, V, ld, n, k, -1.0, 1.0, w, cin, 1, cout);
+                         : gs_single_sweep(ctx, mode, V, ld, n, k, -1.0, 1.0, w, cin, 1, cout);
     if (rc != -1) return rc;       /* -1: shape not supported by the single-sweep kernels → two-sweep path */
   }
   /* two-sweep path: update sweep, then dot sweep (V read twice) */
@@ -499,7 +512,7 @@ extern "C" int b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int6
                                   double *nrm2_out)
 {
   if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
-    int rc = b2k_gs_rt_launch(ctx, V, ld, n, k, -1.0, 1.0, w, cin, 0, nrm2_out);
+    int rc = gs_single_sweep(ctx, b2k_gs_fused_enabled(), V, ld, n, k, -1.0, 1.0, w, cin, 0, nrm2_out);
     if (rc != -1) return rc;
   }
   return launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nrm2_out);

@@ -33,12 +33,13 @@ int b2k_gs_fused_enabled(void)
 {
   if (g_fused_enabled < 0) {
     const char *e = getenv("B2K_GS_FUSED");
-    g_fused_enabled = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    g_fused_enabled = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
   }
   return g_fused_enabled;
 }
-/* 0: generic two-sweep kernels, 1: register-tile single sweep (default), 2: TMA-staged single sweep */
-extern "C" int b2k_gs_set_fused(int mode) { g_fused_enabled = (mode >= 0 && mode <= 2) ? mode : 1; return B2K_OK; }
+/* 0: generic two-sweep kernels, 1: register-tile single sweep, 2: 1-D bulk-copy staged single sweep,
+   3: 2-D tensor-map (TMA) pipelined single sweep */
+extern "C" int b2k_gs_set_fused(int mode) { g_fused_enabled = (mode >= 0 && mode <= 3) ? mode : 3; return B2K_OK; }
 
 /* ---- PTX helpers ------------------------------------------------------------------------------ */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

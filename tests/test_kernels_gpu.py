@@ -98,9 +98,10 @@ def test_gs_update_dot_matches_cgs_pass(ctx, n, k):
 
 
 @pytest.mark.parametrize("k", [1, 5, 8, 9, 16, 17, 31, 33, 48, 64])
-@pytest.mark.parametrize("n", [1, 63, 128, 130, 128 * 7 + 1, 128 * 148 * 3 + 77, 1 << 20])
+@pytest.mark.parametrize("n", [1, 63, 128, 130, 128 * 7 + 1, 4096, 4097, 12345, 128 * 148 * 3 + 77, 1 << 20])
 def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
-    """The single-sweep kernels (1: register tile, 2: TMA-staged) and the two-sweep path (0) compute the same w
+    """The single-sweep kernels (1: register tile, 2: 1-D bulk-copy staged, 3: 2-D tensor-map TMA pipeline; 3 falls back to 1
+    below 4096 rows) and the two-sweep path (0) compute the same w
     and c (different reduction order ⇒ compare to rounding, and each against the float64 reference)."""
     from slepc_b200._b2k import check
     ld = n + (n % 2) + 2
@@ -111,7 +112,7 @@ def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
     cin = rng.standard_normal(k + 1)
     dV, dc = ctx.to_device(H), ctx.to_device(cin)
     out = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         check(ctx.lib.b2k_gs_set_fused(mode))
         dw = ctx.to_device(w)
         co = ctx.empty(k + 1)
@@ -122,12 +123,43 @@ def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
             co2 = ctx.empty(k + 1)
             check(ctx.lib.b2k_gs_update_dot(ctx.h, dV.ptr, ld, n, k, dw2.ptr, dc.ptr, co2.ptr))
             assert np.array_equal(dw2.to_host(), out[mode][0]) and np.array_equal(co2.to_host(), out[mode][1])
-    check(ctx.lib.b2k_gs_set_fused(1))
+    check(ctx.lib.b2k_gs_set_fused(3))
     wref = w - H[:n] @ cin[:k]
     cref = np.concatenate([H[:n].T @ wref, [wref @ wref]])
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         assert np.allclose(out[mode][0], wref, rtol=1e-13, atol=1e-13 * np.sqrt(k)), mode
         assert np.allclose(out[mode][1], cref, rtol=1e-12, atol=1e-12 * np.sqrt(n)), mode
+
+
+@pytest.mark.parametrize("alpha,beta", [(-1.0, 1.0), (2.0, 0.0), (0.5, -0.25)])
+@pytest.mark.parametrize("n,k", [(4096, 1), (4097, 7), (50001, 16), (50001, 17), (1 << 18, 40), (300007, 64)])
+def test_multvec_and_update_norm_tensor_map_pipeline(ctx, n, k, alpha, beta):
+    """b2k_multvec / b2k_gs_update_norm through the 2-D tensor-map kernel (mode 3): general alpha/beta, beta==0 must not
+    read y (BLAS semantics), odd n (zero-filled tail rows), k below the box width (zero-filled columns)."""
+    from slepc_b200._b2k import check
+    ld = n + (n % 2)
+    rng = np.random.default_rng(n + k)
+    H = np.zeros((ld, k), order="F")
+    H[:n] = rng.standard_normal((n, k))
+    y = rng.standard_normal(n)
+    q = rng.standard_normal(k)
+    dV, dq = ctx.to_device(H), ctx.to_device(q)
+    check(ctx.lib.b2k_gs_set_fused(3))
+    try:
+        yy = y.copy()
+        if beta == 0.0:
+            yy[::3] = np.nan
+        dy = ctx.to_device(yy)
+        check(ctx.lib.b2k_multvec(ctx.h, dV.ptr, ld, n, k, alpha, beta, dy.ptr, dq.ptr))
+        ref = alpha * (H[:n] @ q) + (0.0 if beta == 0.0 else beta * y)
+        assert np.allclose(dy.to_host(), ref, rtol=1e-13, atol=1e-12 * k)
+        dw, nr = ctx.to_device(y), ctx.empty(1)
+        check(ctx.lib.b2k_gs_update_norm(ctx.h, dV.ptr, ld, n, k, dw.ptr, dq.ptr, nr.ptr))
+        wref = y - H[:n] @ q
+        assert np.allclose(dw.to_host(), wref, rtol=1e-13, atol=1e-12 * k)
+        assert np.isclose(nr.to_host()[0], wref @ wref, rtol=1e-12)
+    finally:
+        check(ctx.lib.b2k_gs_set_fused(3))
 
 
 def test_level1(ctx):

@@ -50,15 +50,20 @@ def main():
     for k in (1, 8, 16, 24, 32, 48, 64):
         rec("gs_dot", timeit(ctx, lambda: check(lib.b2k_gs_dot(h, V.ptr, ld, n, k, w.ptr, c.ptr)), reps), 8 * n * (k + 1), k=k)
     check(lib.b2k_memset0(h, c.ptr, 8 * (m + 1)))
-    for k in (1, 8, 16, 32, 48, 64):
-        rec("multvec", timeit(ctx, lambda: check(lib.b2k_multvec(h, V.ptr, ld, n, k, -1.0, 1.0, w.ptr, c.ptr)), reps),
-            8 * n * (k + 2), k=k)
-    for mode in (0, 1):
+    for mode in (1, 3):
+        check(lib.b2k_gs_set_fused(mode))
+        for k in (1, 8, 16, 32, 48, 64):
+            rec("multvec", timeit(ctx, lambda: check(lib.b2k_multvec(h, V.ptr, ld, n, k, -1.0, 1.0, w.ptr, c.ptr)), reps),
+                8 * n * (k + 2), k=k, single_sweep=mode)
+        for k in (16, 32, 48, 64):
+            rec("gs_update_norm", timeit(ctx, lambda: check(lib.b2k_gs_update_norm(h, V.ptr, ld, n, k, w.ptr, c.ptr, c2.ptr)), reps),
+                8 * n * (k + 2), k=k, single_sweep=mode)
+    for mode in (0, 1, 3):
         check(lib.b2k_gs_set_fused(mode))
         for k in (1, 4, 8, 16, 24, 32, 48, 64):
             rec("gs_update_dot", timeit(ctx, lambda: check(lib.b2k_gs_update_dot(h, V.ptr, ld, n, k, w.ptr, c.ptr, c2.ptr)), reps),
                 8 * n * (k + 2), k=k, single_sweep=mode, note="bytes of ONE read of V + w read/write")
-    check(lib.b2k_gs_set_fused(1))
+    check(lib.b2k_gs_set_fused(3))
     rec("scale_rsqrt", timeit(ctx, lambda: check(lib.b2k_scale_rsqrt(h, w.ptr, n, c.ptr)), reps), 16 * n)
     rec("sumsq", timeit(ctx, lambda: check(lib.b2k_sumsq(h, w.ptr, n, n, 1, c2.ptr)), reps), 8 * n)
     # mult_inplace: k=64 -> 32 columns
