@@ -144,6 +144,9 @@ int  b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val);
 int  b2k_csr_spmv(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y);
 /* y = A x - sigma*xdiag   (shifted operator of STSHIFT, shift.c:79; xdiag = x rows owned here)    */
 int  b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y, double sigma);
+/* storage used by b2k_csr_spmv: 0 CSR-stream only, 1 (default) SELL-32 copy when its padding is <= 25 %, 2 SELL-32 always;
+   read when a matrix is created (env B2K_SPMV_SELL) and at every product (0 forces CSR-stream)                      */
+int  b2k_spmv_set_sell(int mode);
 /* device generator: rows [row0,row0+nrows) of the d-dimensional Laplacian stencil (d=1,2,3) on an
    nx*ny*nz grid, natural ordering, slab partition along the slowest index: ex1.c:37-48, ex2.c:39-54.
    Ghost layout: [lower neighbour plane | upper neighbour plane].                                   */
@@ -151,6 +154,9 @@ int  b2k_csr_laplacian(b2k_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz,
                        b2k_csr *A, int64_t *nghost_lo, int64_t *nghost_hi);
 /* gather: out[i] = x[idx[i]] (packs halo send buffers)                                             */
 int  b2k_gather(b2k_ctx ctx, double *out, const double *x, const int *idx, int64_t count);
+
+/* scatter-add: out[idx[i]] += in[i] (idx unique within a call): accumulates the reverse halo of y = A^T x            */
+int  b2k_scatter_add(b2k_ctx ctx, double *out, const int *idx, const double *in, int64_t count);
 
 /* ---- row-partition communicator (replaces MPIU_Allreduce bvcuda.cu:228-248, VecScatter) -------- */
 #define B2K_COMM_ID_BYTES 128

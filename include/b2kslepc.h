@@ -123,6 +123,7 @@ PetscErrorCode MatDestroy(Mat *A);
 PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y);
 PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left);
+PetscErrorCode MatCreateHermitianTranspose(Mat A, Mat *At);          /* virtual: MatMult(At) = MatMultTranspose(A) */
 PetscErrorCode MatGetType(Mat A, const char **type);
 /* operator plug-in, the MatShell route (cf. src/eps/tutorials/ex3.c:46-49,140-168) */
 typedef PetscErrorCode (*MatMultFn)(Mat A, Vec x, Vec y);

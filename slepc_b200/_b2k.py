@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2k_gs_update_norm": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
     "b2k_scale_rsqrt": [c_vp, c_vp, c_i64, c_vp],
     "b2k_gs_set_fused": [c_int],
+    "b2k_spmv_set_sell": [c_int],
     "b2k_csr_create": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_adopt": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_destroy": [c_vp, c_vp],
@@ -69,6 +70,7 @@ SIGNATURES = {
     "b2k_csr_laplacian": [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),
                           ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
     "b2k_gather": [c_vp, c_vp, c_vp, c_vp, c_i64],
+    "b2k_scatter_add": [c_vp, c_vp, c_vp, c_vp, c_i64],
     "b2k_comm_unique_id": [c_vp],
     "b2k_comm_create": [c_vp, c_int, c_int, c_vp, ctypes.POINTER(c_vp)],
     "b2k_comm_destroy": [c_vp],

@@ -25,7 +25,151 @@ struct b2k_csr_s {
   double *val;
   int    *blkrow;     /* [nblk+1] first row of each row block */
   int     nblk;
+  /* SELL-32 copy (sliced ELLPACK, slice height 32 = one warp, no row sorting): built when padding is small */
+  int64_t  nslices, sell_elems;
+  int64_t *sl_off;    /* [nslices+1] element offset of each slice; width = (off[s+1]-off[s])/32 */
+  int     *sl_col;
+  double  *sl_val;
 };
+
+/* ------------------------------------------------------------------------------------------------
+ * SELL-32 SpMV: one warp per slice of 32 consecutive rows, lane = row.  Entry w of the slice's rows is
+ * stored at off + 32*w + lane, so every (col,val) load of a warp is one fully coalesced 128 B / 256 B
+ * request, there is no row pointer, no shared memory and no barrier, and a thread has `width`
+ * independent matrix loads + gathers in flight.  Padding entries carry val = 0 and the row's own first
+ * column.  Same algorithmic bytes as CSR minus the row pointers.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int ld_stream_i32(const int *p)
+{
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p)
+{
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_spmv_sell(const int64_t *__restrict__ sl_off, const int *__restrict__ col,
+                                                    const double *__restrict__ val, const double *__restrict__ x,
+                                                    const double *__restrict__ xg, int ncl, double *__restrict__ y, int64_t nrows,
+                                                    int64_t nslices, double sigma)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slice >= nslices) return;
+  const int64_t off = sl_off[slice];
+  const int width = (int)((sl_off[slice + 1] - off) >> 5);
+  const int *cp = col + off + lane;
+  const double *vp = val + off + lane;
+  double acc = 0.0;
+  int w = 0;
+  for (; w + 4 <= width; w += 4) {
+    const int c0 = ld_stream_i32(cp + 32 * w), c1 = ld_stream_i32(cp + 32 * (w + 1)), c2 = ld_stream_i32(cp + 32 * (w + 2)),
+              c3 = ld_stream_i32(cp + 32 * (w + 3));
+    const double v0 = ld_stream_f64(vp + 32 * w), v1 = ld_stream_f64(vp + 32 * (w + 1)), v2 = ld_stream_f64(vp + 32 * (w + 2)),
+                 v3 = ld_stream_f64(vp + 32 * (w + 3));
+    const double x0 = (c0 < ncl) ? __ldg(x + c0) : __ldg(xg + (c0 - ncl));
+    const double x1 = (c1 < ncl) ? __ldg(x + c1) : __ldg(xg + (c1 - ncl));
+    const double x2 = (c2 < ncl) ? __ldg(x + c2) : __ldg(xg + (c2 - ncl));
+    const double x3 = (c3 < ncl) ? __ldg(x + c3) : __ldg(xg + (c3 - ncl));
+    acc = fma(v0, x0, acc);
+    acc = fma(v1, x1, acc);
+    acc = fma(v2, x2, acc);
+    acc = fma(v3, x3, acc);
+  }
+  for (; w < width; w++) {
+    const int c = ld_stream_i32(cp + 32 * w);
+    const double v = ld_stream_f64(vp + 32 * w);
+    acc = fma(v, (c < ncl) ? __ldg(x + c) : __ldg(xg + (c - ncl)), acc);
+  }
+  const int64_t row = slice * 32 + lane;
+  if (row < nrows) {
+    if (sigma != 0.0) acc -= sigma * x[row];
+    y[row] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sell_width(const int *__restrict__ rowptr, int64_t nrows, int64_t nslices, int *__restrict__ width)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slice >= nslices) return;
+  const int64_t row = slice * 32 + lane;
+  int len = (row < nrows) ? rowptr[row + 1] - rowptr[row] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) width[slice] = len;
+}
+
+__global__ void __launch_bounds__(256) k_sell_fill(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val,
+                                                    int64_t nrows, int64_t nslices, const int64_t *__restrict__ sl_off, int *__restrict__ scol,
+                                                    double *__restrict__ sval)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slice >= nslices) return;
+  const int64_t off = sl_off[slice];
+  const int width = (int)((sl_off[slice + 1] - off) >> 5);
+  const int64_t row = slice * 32 + lane;
+  int a = 0, len = 0;
+  if (row < nrows) { a = rowptr[row]; len = rowptr[row + 1] - a; }
+  const int padcol = len > 0 ? colidx[a] : 0;
+  for (int w = 0; w < width; w++) {
+    const bool in = w < len;
+    scol[off + 32 * w + lane] = in ? colidx[a + w] : padcol;
+    sval[off + 32 * w + lane] = in ? val[a + w] : 0.0;
+  }
+}
+
+static int g_sell_mode = -1;      /* env B2K_SPMV_SELL: 0 never, 1 (default) when padding <= 25 %, 2 always */
+static int sell_mode(void)
+{
+  if (g_sell_mode < 0) {
+    const char *e = getenv("B2K_SPMV_SELL");
+    g_sell_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return g_sell_mode;
+}
+extern "C" int b2k_spmv_set_sell(int mode) { g_sell_mode = (mode >= 0 && mode <= 2) ? mode : 1; return B2K_OK; }
+
+static int build_sell(b2k_ctx ctx, b2k_csr A)
+{
+  A->nslices = 0; A->sl_off = NULL; A->sl_col = NULL; A->sl_val = NULL; A->sell_elems = 0;
+  if (!sell_mode() || A->nrows == 0 || A->nnz == 0) return B2K_OK;
+  const int64_t ns = (A->nrows + 31) / 32;
+  int *dwidth = NULL;
+  CK(cudaMalloc(&dwidth, sizeof(int) * (size_t)ns));
+  const unsigned grid = (unsigned)((ns + 7) / 8);
+  k_sell_width<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->nrows, ns, dwidth);
+  CKLAUNCH(ctx);
+  int *hw = (int *)malloc(sizeof(int) * (size_t)ns);
+  int64_t *hoff = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ns + 1));
+  if (!hw || !hoff) { free(hw); free(hoff); cudaFree(dwidth); return B2K_ERR_MEM; }
+  CK(cudaMemcpyAsync(hw, dwidth, sizeof(int) * (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dwidth);
+  int64_t tot = 0;
+  for (int64_t s = 0; s < ns; s++) { hoff[s] = tot; tot += 32 * (int64_t)hw[s]; }
+  hoff[ns] = tot;
+  free(hw);
+  if (sell_mode() == 1 && (double)tot > 1.25 * (double)A->nnz) { free(hoff); return B2K_OK; }   /* too much padding: stay on CSR-stream */
+  size_t fr = 0, to = 0;
+  cudaMemGetInfo(&fr, &to);
+  if ((double)tot * 12.0 + 8.0 * (double)(ns + 1) > 0.5 * (double)fr) { free(hoff); return B2K_OK; }   /* keep room for the basis */
+  CK(cudaMalloc(&A->sl_off, sizeof(int64_t) * (size_t)(ns + 1)));
+  CK(cudaMalloc(&A->sl_col, sizeof(int) * (size_t)tot));
+  CK(cudaMalloc(&A->sl_val, sizeof(double) * (size_t)tot));
+  CK(cudaMemcpyAsync(A->sl_off, hoff, sizeof(int64_t) * (size_t)(ns + 1), cudaMemcpyHostToDevice, ctx->stream));
+  k_sell_fill<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->nrows, ns, A->sl_off, A->sl_col, A->sl_val);
+  CKLAUNCH(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  free(hoff);
+  A->nslices = ns; A->sell_elems = tot;
+  return B2K_OK;
+}
 
 __global__ void __launch_bounds__(SPMV_THREADS) k_spmv_csr_stream(const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                                                    const double *__restrict__ val, const int *__restrict__ blkrow,
@@ -107,7 +251,7 @@ static int finish_create(b2k_ctx ctx, b2k_csr A, const int *rowptr_host)
   CK(cudaMemcpyAsync(A->blkrow, blk, sizeof(int) * (size_t)(nb + 1), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   free(blk);
-  return B2K_OK;
+  return build_sell(ctx, A);
 }
 
 extern "C" int b2k_csr_create(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t nghost, const int *rowptr_host,
@@ -160,6 +304,7 @@ extern "C" int b2k_csr_destroy(b2k_ctx ctx, b2k_csr A)
   if (!A) return B2K_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(A->rowptr); cudaFree(A->colidx); cudaFree(A->val); cudaFree(A->blkrow);
+  cudaFree(A->sl_off); cudaFree(A->sl_col); cudaFree(A->sl_val);
   free(A);
   return B2K_OK;
 }
@@ -185,9 +330,15 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
 {
   if (A->nrows == 0) return B2K_OK;
   ARGCHK(x != y, "SpMV cannot run in place");
+  /* algorithmic bytes of the CSR product whichever storage runs: the SELL copy moves 12 B per stored
+     entry (padding included) and no row pointers */
   PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 4.0 * (double)(A->nrows + 1) + 8.0 * (double)(A->ncols_local + A->nghost) + 8.0 * (double)A->nrows);
-  k_spmv_csr_stream<<<A->nblk, SPMV_THREADS, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->blkrow, x,
-                                                                 xghost ? xghost : x, (int)A->ncols_local, y, sigma);
+  if (A->nslices > 0 && sell_mode())
+    k_spmv_sell<<<(unsigned)((A->nslices + 7) / 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x,
+                                                                            (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
+  else
+    k_spmv_csr_stream<<<A->nblk, SPMV_THREADS, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->blkrow, x,
+                                                                   xghost ? xghost : x, (int)A->ncols_local, y, sigma);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
@@ -209,6 +360,23 @@ extern "C" int b2k_gather(b2k_ctx ctx, double *out, const double *x, const int *
   int64_t g = (count + 255) / 256;
   if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
   k_gather<<<(unsigned)g, 256, 0, ctx->stream>>>(out, x, idx, count);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
+/* out[idx[i]] += in[i]: accumulation of the reverse halo (A^T products); idx entries are unique within one call */
+__global__ void __launch_bounds__(256) k_scatter_add(double *__restrict__ out, const int *__restrict__ idx, const double *__restrict__ in,
+                                                      int64_t n)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[idx[i]] += in[i];
+}
+extern "C" int b2k_scatter_add(b2k_ctx ctx, double *out, const int *idx, const double *in, int64_t count)
+{
+  if (count == 0) return B2K_OK;
+  int64_t g = (count + 255) / 256;
+  if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+  k_scatter_add<<<(unsigned)g, 256, 0, ctx->stream>>>(out, idx, in, count);
   CKLAUNCH(ctx);
   return B2K_OK;
 }

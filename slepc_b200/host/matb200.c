@@ -24,6 +24,10 @@ typedef struct {
   double   *sendbuf;         /* device pack buffer                                             */
   PetscInt  nsendtot;
   int64_t   nnz;
+  /* implicit transpose (MatMultTranspose): local A_loc^T split into the owned-column rows and the ghost-column rows,
+     built on first use; zghost/rbuf are the reverse-halo buffers */
+  b2k_csr   ATown, ATgh;
+  double   *zghost, *rbuf;
 } Mat_B200CSR;
 
 #define CTX() B2KGetContext()
@@ -65,12 +69,93 @@ static PetscErrorCode MatMult_B200CSR(Mat A, Vec x, Vec y)
   return PETSC_SUCCESS;
 }
 
+/* A_loc^T from the CSR arrays in HBM: rows = local columns [owned | ghosts], columns = local rows.  Host counting sort
+   (set-up cost, once); the owned and the ghost block become two CSR matrices so that the owned part of y = A^T x is
+   written in place and only the ghost part travels. */
+static PetscErrorCode MatBuildLocalTranspose_B200CSR(Mat A)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt m = A->m, ncl = A->n, ng = a->nghost, nt = ncl + ng;
+  const int64_t nnz = a->nnz;
+  int *drp, *dci;
+  double *dv;
+  B2KCall(b2k_csr_arrays(a->A, &drp, &dci, &dv));
+  PetscInt *rp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(m + 1)), *ci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  double *v = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+  PetscInt *trp = (PetscInt *)calloc((size_t)nt + 2, sizeof(PetscInt)), *tci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
+  double *tv = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+  PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
+  B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
+  if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
+  for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
+  for (PetscInt c = 0; c < nt; c++) trp[c + 2] += trp[c + 1];
+  for (PetscInt r = 0; r < m; r++)
+    for (PetscInt k = rp[r]; k < rp[r + 1]; k++) { const PetscInt p = trp[ci[k] + 1]++; tci[p] = r; tv[p] = v[k]; }
+  /* trp[0..nt] is now the row pointer of the (ncl+ng) x m transpose */
+  int rc = b2k_csr_create(ctx, ncl, m, 0, trp, tci, tv, &a->ATown);
+  if (!rc && ng) {
+    const PetscInt base = trp[ncl];
+    PetscInt *grp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(ng + 1));
+    PetscCheck(grp, PETSC_ERR_MEM, "out of memory");
+    for (PetscInt c = 0; c <= ng; c++) grp[c] = trp[ncl + c] - base;
+    rc = b2k_csr_create(ctx, ng, m, 0, grp, tci + base, tv + base, &a->ATgh);
+    free(grp);
+    if (!rc) rc = b2k_malloc(ctx, (void **)&a->zghost, sizeof(double) * (size_t)ng);
+  }
+  if (!rc && a->nsendtot) rc = b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot);
+  free(rp); free(ci); free(v); free(trp); free(tci); free(tv);
+  PetscCheck(!rc, PETSC_ERR_GPU, "building the local transpose failed (%d): %s", rc, b2k_last_error());
+  return PETSC_SUCCESS;
+}
+
+/* y = A^T x with A row-partitioned: local y_own = A_own^T x, ghost-column contributions z = A_gh^T x are sent to the owners
+   of those columns (the halo plan run backwards) and accumulated in peer order — deterministic.  This is PETSc's
+   MatMultTranspose_MPIAIJ (local transpose products + VecScatter SCATTER_REVERSE/ADD_VALUES), reached from
+   SVDTwoSideLanczos (gklanczos.c:80,103) when the transpose is implicit (svdsetup.c:273-279,309-315). */
+static PetscErrorCode MatMultTranspose_B200CSR(Mat A, Vec x, Vec y)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  b2k_ctx ctx = CTX();
+  B2KComm comm = B2KCommWorld();
+  int size = 1;
+  PetscCheck(x->mem == B2K_MEM_DEVICE && y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "b200csr needs device vectors");
+  PetscCall(B2KCommGetRank(comm, NULL, &size));
+  if (!a->ATown) PetscCall(MatBuildLocalTranspose_B200CSR(A));
+  B2KCall(b2k_csr_spmv(ctx, a->ATown, x->array, NULL, y->array));
+  if (size == 1 || (a->nghost == 0 && a->nsend == 0)) return PETSC_SUCCESS;
+  PetscCheck(a->halo_set, PETSC_ERR_ORDER, "MatB200CSRSetHalo() must be called before MatMultTranspose() on more than one rank");
+  PetscCheck(comm->kind == 1, PETSC_ERR_SUP, "b200csr needs the NCCL communicator (B2KCommInitNCCL)");
+  if (a->nghost) B2KCall(b2k_csr_spmv(ctx, a->ATgh, x->array, NULL, a->zghost));
+  if (a->nsendtot && !a->rbuf) B2KCall(b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot));
+  B2KCall(b2k_comm_group_start(comm->nccl));
+  PetscInt roff = 0, soff = 0;
+  for (PetscInt p = 0; p < a->nrecv; p++) {        /* what I receive in MatMult I now send back */
+    B2KCall(b2k_comm_sendrecv(comm->nccl, a->zghost + roff, a->recvcount[p], a->recvrank[p], NULL, 0, 0));
+    roff += a->recvcount[p];
+  }
+  for (PetscInt q = 0; q < a->nsend; q++) {
+    B2KCall(b2k_comm_sendrecv(comm->nccl, NULL, 0, 0, a->rbuf + soff, a->sendcount[q], a->sendrank[q]));
+    soff += a->sendcount[q];
+  }
+  B2KCall(b2k_comm_group_end(comm->nccl));
+  soff = 0;
+  for (PetscInt q = 0; q < a->nsend; q++) {
+    if (a->d_sendidx) B2KCall(b2k_scatter_add(ctx, y->array, a->d_sendidx + soff, a->rbuf + soff, a->sendcount[q]));
+    else B2KCall(b2k_axpby(ctx, y->array + a->sendoff[q], A->n, a->rbuf + soff, a->sendcount[q], a->sendcount[q], 1, 1.0, 1.0));
+    soff += a->sendcount[q];
+  }
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode MatDestroy_B200CSR(Mat A)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
   if (!a) return PETSC_SUCCESS;
   b2k_ctx ctx = CTX();
   if (ctx) {
+    b2k_csr_destroy(ctx, a->ATown); b2k_csr_destroy(ctx, a->ATgh);
+    b2k_free(ctx, a->zghost); b2k_free(ctx, a->rbuf);
     b2k_csr_destroy(ctx, a->A);
     b2k_free(ctx, a->xghost); b2k_free(ctx, a->d_sendidx); b2k_free(ctx, a->sendbuf);
   }
@@ -90,6 +175,7 @@ static PetscErrorCode MatSetUp_B200CSR(Mat A, PetscInt M, PetscInt N, PetscInt r
   A->mem = B2K_MEM_DEVICE;
   A->data = a;
   A->ops.mult = MatMult_B200CSR;
+  A->ops.multtranspose = MatMultTranspose_B200CSR;
   A->ops.destroy = MatDestroy_B200CSR;
   *out = a;
   return PETSC_SUCCESS;
@@ -188,6 +274,7 @@ PetscErrorCode MatB200CSRSetHalo(Mat A, PetscInt nrecv, const PetscInt *recvrank
   a->nrecv = nrecv; a->nsend = nsend; a->nsendtot = stot;
   if (a->d_sendidx) { B2KCall(b2k_free(ctx, a->d_sendidx)); a->d_sendidx = NULL; }
   if (a->sendbuf) { B2KCall(b2k_free(ctx, a->sendbuf)); a->sendbuf = NULL; }
+  if (a->rbuf) { B2KCall(b2k_free(ctx, a->rbuf)); a->rbuf = NULL; }
   if (stot) {
     B2KCall(b2k_malloc(ctx, (void **)&a->d_sendidx, sizeof(int) * (size_t)stot));
     B2KCall(b2k_h2d(ctx, a->d_sendidx, sendidx, sizeof(int) * (size_t)stot));
@@ -249,6 +336,7 @@ PetscErrorCode MatCreateB200Laplacian(PetscInt dim, PetscInt nx, PetscInt ny, Pe
       a->recvrank[a->nrecv] = rank + 1; a->recvcount[a->nrecv++] = (PetscInt)plane;
       a->sendrank[a->nsend] = rank + 1; a->sendcount[a->nsend] = (PetscInt)plane; a->sendoff[a->nsend++] = (PetscInt)(nrows - plane);
     }
+    for (PetscInt q = 0; q < a->nsend; q++) a->nsendtot += a->sendcount[q];
     a->halo_set = PETSC_TRUE;
   }
   *out = A;

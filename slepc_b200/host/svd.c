@@ -135,8 +135,13 @@ PetscErrorCode SVDSetUp(SVD svd)
   if (svd->owns_AT) { if (svd->swapped) PetscCall(MatDestroy(&svd->A)); else PetscCall(MatDestroy(&svd->AT)); svd->owns_AT = PETSC_FALSE; }
   Mat T = svd->userAT;
   if (!T) {
-    PetscCheck(!svd->impltrans, PETSC_ERR_SUP, "the implicit transpose needs a MatMultTranspose kernel; pass A^T with SVDSetTransposeMatrix() or let SVDSetUp build it");
-    PetscCall(MatB200CSRTranspose(svd->OP, &T));
+    /* svdsetup.c:271-315: explicit transpose unless asked otherwise or the Mat type cannot build one (b200csr on more than
+       one rank has no MATOP_TRANSPOSE): then a virtual transpose over MatMultTranspose */
+    int csize = 1;
+    PetscCall(B2KCommGetRank(B2KCommWorld(), NULL, &csize));
+    const PetscBool is_csr = !strcmp(svd->OP->type, "b200csr") ? PETSC_TRUE : PETSC_FALSE;
+    if (svd->impltrans || !is_csr || csize > 1) PetscCall(MatCreateHermitianTranspose(svd->OP, &T));
+    else PetscCall(MatB200CSRTranspose(svd->OP, &T));
     svd->owns_AT = PETSC_TRUE;
   } else PetscCheck(T->M == N && T->N == M, PETSC_ERR_ARG_SIZ, "the transpose matrix is %d x %d, expected %d x %d", T->M, T->N, N, M);
   const PetscBool swap = (M < N) ? PETSC_TRUE : PETSC_FALSE;

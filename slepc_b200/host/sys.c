@@ -408,6 +408,25 @@ PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y)
   return PETSC_SUCCESS;
 }
 
+/* virtual transpose (PETSc MatCreateHermitianTranspose, used by svdsetup.c:309-315 for the implicit transpose): MatMult of
+   the result is MatMultTranspose of A and vice versa; A must outlive it */
+static PetscErrorCode MatMult_Transpose(Mat T, Vec x, Vec y) { return MatMultTranspose((Mat)T->data, x, y); }
+static PetscErrorCode MatMultTranspose_Transpose(Mat T, Vec x, Vec y) { return MatMult((Mat)T->data, x, y); }
+PetscErrorCode MatCreateHermitianTranspose(Mat A, Mat *At)
+{
+  Mat t;
+  PetscCheck(A->ops.multtranspose, PETSC_ERR_SUP, "Mat type %s has no MatMultTranspose", A->type);
+  PetscCall(MatCreate_Private(&t));
+  strcpy(t->type, "transpose");
+  t->m = A->n; t->n = A->m; t->M = A->N; t->N = A->M;
+  t->rstart = A->cstart; t->rend = A->cend; t->cstart = A->rstart; t->cend = A->rend;
+  t->mem = A->mem; t->data = A;
+  t->ops.mult = MatMult_Transpose;
+  t->ops.multtranspose = MatMultTranspose_Transpose;
+  *At = t;
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left)
 {
   if (right) {

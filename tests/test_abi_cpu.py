@@ -42,6 +42,7 @@ def test_kernels_are_sm100a_sass():
     assert "sm_100a" in out
     sass = subprocess.run([cuobjdump, "-sass", _b2k.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass
+    assert "UTMALDG" in sass          # cp.async.bulk.tensor.2d of the tensor-map pipeline (k_gs_tma)
 
 
 def _gpu_present():

@@ -248,8 +248,9 @@ def test_dot(ctx):
     assert np.allclose(got[:ky], Y[:n].T @ X[:n], rtol=1e-12, atol=1e-10)
 
 
-def _spmv(ctx, A, x, xg=None):
+def _spmv(ctx, A, x, xg=None, sell=1, sigma=None):
     from slepc_b200._b2k import check
+    check(ctx.lib.b2k_spmv_set_sell(sell))
     A = A.tocsr()
     A.sort_indices()
     nloc = A.shape[1] if xg is None else len(x)
@@ -262,14 +263,19 @@ def _spmv(ctx, A, x, xg=None):
     dx = ctx.to_device(x)
     dg = ctx.to_device(xg) if xg is not None else None
     dy = ctx.empty(A.shape[0])
-    check(ctx.lib.b2k_csr_spmv(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr))
+    if sigma is None:
+        check(ctx.lib.b2k_csr_spmv(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr))
+    else:
+        check(ctx.lib.b2k_csr_spmv_shift(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr, sigma))
     y = dy.to_host()
     check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    check(ctx.lib.b2k_spmv_set_sell(1))
     return y
 
 
+@pytest.mark.parametrize("sell", [0, 1, 2])          # CSR-stream kernel / SELL-32 when padding is small / SELL-32 always
 @pytest.mark.parametrize("gen", ["lap1", "lap2", "lap3", "markov", "random", "longrow", "empty_rows"])
-def test_spmv_csr(ctx, gen):
+def test_spmv_csr(ctx, gen, sell):
     import scipy.sparse as sp
     rng = np.random.default_rng(41)
     if gen == "lap1":
@@ -289,9 +295,12 @@ def test_spmv_csr(ctx, gen):
     else:
         A = sp.random(5000, 5000, density=0.0005, random_state=9, format="csr")   # many empty rows
     x = rng.standard_normal(A.shape[1])
-    y = _spmv(ctx, A, x)
+    y = _spmv(ctx, A, x, sell=sell)
     ref = A @ x
     assert np.allclose(y, ref, rtol=1e-13, atol=1e-12)
+    if A.shape[0] == A.shape[1]:                            # shifted operator of STSHIFT (shift.c:79)
+        y = _spmv(ctx, A, x, sell=sell, sigma=0.75)
+        assert np.allclose(y, ref - 0.75 * x, rtol=1e-13, atol=1e-12)
 
 
 def test_spmv_ghost_columns(ctx):
@@ -301,8 +310,9 @@ def test_spmv_ghost_columns(ctx):
     rng = np.random.default_rng(43)
     x = rng.standard_normal(A.shape[1])
     used = B[:, :nloc + 50]
-    y = _spmv(ctx, used, x[:nloc], x[nloc:nloc + 50])
-    assert np.allclose(y, (A @ x)[:nloc], rtol=1e-13, atol=1e-13)
+    for sell in (0, 2):
+        y = _spmv(ctx, used, x[:nloc], x[nloc:nloc + 50], sell=sell)
+        assert np.allclose(y, (A @ x)[:nloc], rtol=1e-13, atol=1e-13)
 
 
 @pytest.mark.parametrize("dim,dims", [(1, (1000, 1, 1)), (2, (40, 33, 1)), (3, (12, 9, 7))])

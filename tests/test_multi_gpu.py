@@ -1,0 +1,77 @@
+"""Row-partitioned solves on 2 (or more) B200s over NCCL: needs >= 2 visible GPUs, skipped otherwise
+(`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`).  The same host logic is covered on CPU by
+tests/test_dist_cpu.py (gloo)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_case(case, world, tmp_path):
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = tmp_path / f"{case}_{world}.json"
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mgpu_worker.py"), case, str(out)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(l[-3000:] for l in logs)
+    return json.load(open(out))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_bv_orthonormalize(world, tmp_path):
+    r = run_case("bv", world, tmp_path)
+    assert r["orth"] < 1e-13 and r["span"] < 1e-10 and r["dn"] < 1e-12
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_eps_laplacian_device_generator(world, tmp_path):
+    r = run_case("lap", world, tmp_path)
+    assert r["nconv"] >= 6
+    an = np.array(r["analytic"])
+    for x in r["lam"][:6]:
+        assert np.min(np.abs(an - x)) < 1e-10 * abs(x)
+    assert max(r["errs"][:6]) < 5e-8
+
+
+def test_eps_markov_general_halo(tmp_path):
+    r = run_case("markov", 2, tmp_path)
+    assert r["nconv"] >= 4
+    assert np.allclose(r["lam"][:4], r["ref"][:4], rtol=1e-9, atol=0)
+    assert max(r["errs"][:4]) < 5e-8
+
+
+def test_svd_two_row_layouts(tmp_path):
+    r = run_case("svd", 2, tmp_path)
+    assert r["nconv"] >= 5
+    assert np.allclose(r["sigma"][:5], r["ref"][:5], rtol=1e-10, atol=0)
+    assert max(r["errs"][:5]) < 5e-8
+    assert r["nconv_impl"] >= 5 and np.allclose(r["sigma_impl"][:5], r["ref"][:5], rtol=1e-10, atol=0)
+    assert max(r["errs_impl"][:5]) < 5e-8

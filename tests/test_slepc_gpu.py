@@ -310,6 +310,42 @@ def test_svd_random_sparse_vs_oracle():
         assert subspace_angle(v.get_values()[:, None], ref.V[:, i:i + 1]) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(3000, 700), (700, 3000)])
+def test_mat_mult_transpose_and_implicit_svd(shape):
+    """MatMultTranspose of Mat b200csr (local A^T kernels) == scipy, and SVDSolve over the implicit transpose
+    (SVDSetImplicitTranspose, svdsetup.c:273-279,309-315) returns the triplets of the explicit-transpose run."""
+    import scipy.sparse as sp
+    Mr, N = shape
+    A = sp.random(Mr, N, density=8.0 / N, random_state=5, format="csr")
+    MA = SL.Mat.b200csr(A)
+    x, y = MA.create_vecs()                                  # x: column space (N), y: row space (Mr)
+    rng = np.random.default_rng(6)
+    u = rng.standard_normal(Mr)
+    y.set_values(u)
+    S.MatMultTranspose(MA.h, y.h, x.h)
+    assert np.allclose(x.get_values(), A.T @ u, rtol=1e-13, atol=1e-12)
+    T = SL.Mat()
+    S.MatCreateHermitianTranspose(MA.h, T.ref)
+    xv = rng.standard_normal(N)
+    x.set_values(xv)
+    S.MatMultTranspose(T.h, x.h, y.h)                        # (A^T)^T x = A x
+    assert np.allclose(y.get_values(), A @ xv, rtol=1e-13, atol=1e-12)
+    res = []
+    for impl in (0, 1):
+        svd = SL.SVD(MA)
+        S.SVDSetImplicitTranspose(svd.h, impl)
+        S.SVDSetDimensions(svd.h, 5, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+        svd.solve()
+        assert svd.reason > 0 and svd.nconv >= 5
+        assert max(svd.error(i) for i in range(5)) < 5e-8
+        res.append([svd.triplet(i) for i in range(5)])
+        svd.destroy()
+    assert np.allclose(res[0], res[1], rtol=1e-10)
+    sref = np.linalg.svd(A.toarray(), compute_uv=False)
+    assert np.allclose(res[1], sref[:5], rtol=1e-10)
+    T.destroy()
+
+
 def test_eps_restart_cycles_api_matches_solve():
     M = SL.Mat.laplacian(2, 40, 40)
     a = solve_eps(M, 3, ncv=12)
