@@ -212,19 +212,10 @@ def run_b200(args, wl):
     from slepc_b200.slepc import S
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
+    from slepc_b200 import dist as D
     lib = _b2k.load()
-    SL.initialize(local)
+    D.init()                                       # B2KInitialize(local GPU) + NCCL communicator over the ranks
     ctx = S.B2KGetContext()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idbuf = (ctypes.c_char * 128)()
-        if rank == 0:
-            _b2k.check(lib.b2k_comm_unique_id(idbuf))
-        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        raw = bytes(t.cpu().numpy().tobytes())
-        S.B2KCommInitNCCL(rank, world, ctypes.c_char_p(raw))
 
     def barrier():
         if world > 1:
@@ -293,12 +284,13 @@ def run_b200(args, wl):
         if p["launches"]:
             kernels[name] = dict(launches=p["launches"], ms_total=round(p["ms"], 3), avg_ms=p["ms"] / p["launches"],
                                  share_of_step=p["ms"] / ms.value, achieved_gbs=p["bytes"] / p["ms"] / 1e6,
-                                 frac_of_peak=p["bytes"] / p["ms"] / 1e6 / peak)
+                                 frac_of_peak=p["bytes"] / p["ms"] / 1e6 / peak, frac_of_nominal_8tbs=p["bytes"] / p["ms"] / 1e6 / 8000.0)
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
     gs_bytes = sum(prof[k]["bytes"] for k in ("dotvec", "multvec", "gs_fused"))
     gs_ms = sum(prof[k]["ms"] for k in ("dotvec", "multvec", "gs_fused"))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["achieved_gbs"] / peak, "frac_of_nominal_8tbs": kernels[dom]["achieved_gbs"] / 8000.0,
+                "traffic": None, "peak_source": peak_src,
                 "launches": kernels[dom]["launches"], "avg_launch_ms": kernels[dom]["avg_ms"],
                 "note": "achieved = algorithmic bytes (SURVEY.md §8d, DESIGN.md) / CUDA-event time of every launch of the class in the timed region"}
     try:
@@ -358,6 +350,27 @@ def run_b200(args, wl):
         e2.destroy()
         A.destroy()
 
+    # ---------------- time-to-solution of a complete solve (BASELINE.json's other metric), reduced grid ----------------
+    tts = None
+    if not args.no_tts:
+        g = 1024
+        Mt = SL.Mat.laplacian(wl["dim"], g * (world if wl["scaling"] == "weak" else 1), g, g if wl["dim"] == 3 else 1) if wl["dim"] == 2 else \
+            SL.Mat.laplacian(3, 128, 128, 128)
+        et = SL.EPS(Mt, hermitian=True)
+        S.EPSSetDimensions(et.h, wl["nev"], wl["ncv"], SL.PETSC_DETERMINE)
+        S.EPSSetTolerances(et.h, 1e-8, SL.PETSC_CURRENT)
+        barrier()
+        t0 = time.perf_counter()
+        et.solve()
+        barrier()
+        dt = allmax(time.perf_counter() - t0)
+        tts = {"workload": ("2-D Laplacian %dx1024" % (g * (world if wl["scaling"] == "weak" else 1))) if wl["dim"] == 2 else "3-D Laplacian 128^3",
+               "nev": wl["nev"], "ncv": wl["ncv"], "seconds": dt, "restarts": et.its, "nconv": et.nconv,
+               "max_rel_residual": max(et.error(i) for i in range(et.nconv)) if et.nconv else None,
+               "full_size": "profiles/r01_tts_1gpu.jsonl: C2 4096x4096 converges 20 pairs in 455.8 s (4171 restarts, 116955 MatMults) on one B200"}
+        et.destroy()
+        Mt.destroy()
+
     # ---------------- CPU baseline on the same box (rank 0, N=1 only) --------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -382,13 +395,10 @@ def run_b200(args, wl):
             "lanczos_steps": steps, "lanczos_steps_per_s": steps / (t_ms / 1e3), "gs_passes_per_step": gs_passes / max(steps, 1),
             "seconds_per_restart_cycle": t_ms / 1e3 / args.steps,
             "kernels": kernels, "gs_sweeps_gbs": (gs_bytes / gs_ms / 1e6) if gs_ms else None,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": nl, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": nl, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        S.B2KCommReset()
-        dist.destroy_process_group()
+    D.finalize()
 
 
 def main():
@@ -400,6 +410,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tts", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -100,6 +100,9 @@ int  b2k_mult(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, int64_t ldx,
                                                — BVMultInPlace_BLAS_CUDA bvcuda.cu:65-112          */
 int  b2k_mult_inplace(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, int s, int e,
                       const double *Q, int ldq, int trans);
+/* 1 (default; env B2K_VQ_TMA): b2k_mult / b2k_mult_inplace with <= 64 columns on >= 4096 rows run the TMA-fed FP64
+   tensor-core kernel (k_vq_tma); 0: the DFMA kernel k_vq                                                        */
+int  b2k_vq_set_tma(int on);
 /* M(ky x kx) = Y^T X (local)                  — BVDot_BLAS_CUDA     bvcuda.cu:140-199 (gemm 'C')  */
 int  b2k_dot(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx,
              double *M, int ldm);

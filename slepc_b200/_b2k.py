@@ -60,6 +60,7 @@ SIGNATURES = {
     "b2k_scale_rsqrt": [c_vp, c_vp, c_i64, c_vp],
     "b2k_gs_set_fused": [c_int],
     "b2k_spmv_set_sell": [c_int],
+    "b2k_vq_set_tma": [c_int],
     "b2k_csr_create": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_adopt": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_destroy": [c_vp, c_vp],

@@ -621,6 +621,8 @@ extern "C" int b2k_set_random(b2k_ctx ctx, double *x, int64_t n, int64_t row0, u
 
 int b2k_vq_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout, const double *Q,
                   int ldq, int qtrans, double alpha, double beta);   /* b2k_vq.cu */
+int b2k_vq_tma_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout, const double *Q,
+                      int ldq, int qtrans, double alpha, double beta);   /* b2k_vq_tma.cu (TMA ring + FP64 tensor cores) */
 
 static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64_t ldi, int64_t n, int kin, int nout,
                           const double *Q, int ldq, int qtrans, double alpha, double beta)
@@ -629,7 +631,9 @@ static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *I
   ARGCHK(kin >= 0 && kin <= 2048, "kin out of range");
   if (kin == 0) return b2k_scale(ctx, Out, ldo, n, nout, beta);
   {
-    int rc = b2k_vq_launch(ctx, Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta);   /* kin, nout <= 64: the restart shape */
+    int rc = b2k_vq_tma_launch(ctx, Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta);   /* kin, nout <= 64, large n */
+    if (rc != -1) return rc;
+    rc = b2k_vq_launch(ctx, Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta);           /* kin, nout <= 64: the restart shape */
     if (rc != -1) return rc;
   }
   const size_t qbytes = sizeof(double) * GEMM_KC * 64;

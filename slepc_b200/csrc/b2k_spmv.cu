@@ -12,6 +12,7 @@
  * per row.
  */
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 #include "b2k_internal.h"
 
@@ -27,9 +28,12 @@ struct b2k_csr_s {
   int     nblk;
   /* SELL-32 copy (sliced ELLPACK, slice height 32 = one warp, no row sorting): built when padding is small */
   int64_t  nslices, sell_elems;
-  int64_t *sl_off;    /* [nslices+1] element offset of each slice; width = (off[s+1]-off[s])/32 */
+  int64_t *sl_off;    /* [nslices+1 (+3 padding)] element offset of each slice; width = (off[s+1]-off[s])/32 */
   int     *sl_col;
   double  *sl_val;
+  /* chunks of whole slices (even first slice, <= SP_CAP entries, <= SP_MAXS slices) for the bulk-copy pipeline kernel */
+  int     *sp_chunk;  /* [nchunks+1] first slice of each chunk */
+  int      nchunks;
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -52,43 +56,189 @@ __device__ __forceinline__ double ld_stream_f64(const double *p)
   return r;
 }
 
+#define SELL_CHUNK 8
+/* persistent warps: each warp walks the slices with a grid stride, TWO slices per iteration so that a lane keeps up to
+   16 matrix loads (192 B) in flight before it touches x */
 __global__ void __launch_bounds__(256) k_spmv_sell(const int64_t *__restrict__ sl_off, const int *__restrict__ col,
                                                     const double *__restrict__ val, const double *__restrict__ x,
                                                     const double *__restrict__ xg, int ncl, double *__restrict__ y, int64_t nrows,
                                                     int64_t nslices, double sigma)
 {
   const int lane = threadIdx.x & 31;
-  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slice >= nslices) return;
-  const int64_t off = sl_off[slice];
-  const int width = (int)((sl_off[slice + 1] - off) >> 5);
-  const int *cp = col + off + lane;
-  const double *vp = val + off + lane;
-  double acc = 0.0;
-  int w = 0;
-  for (; w + 4 <= width; w += 4) {
-    const int c0 = ld_stream_i32(cp + 32 * w), c1 = ld_stream_i32(cp + 32 * (w + 1)), c2 = ld_stream_i32(cp + 32 * (w + 2)),
-              c3 = ld_stream_i32(cp + 32 * (w + 3));
-    const double v0 = ld_stream_f64(vp + 32 * w), v1 = ld_stream_f64(vp + 32 * (w + 1)), v2 = ld_stream_f64(vp + 32 * (w + 2)),
-                 v3 = ld_stream_f64(vp + 32 * (w + 3));
-    const double x0 = (c0 < ncl) ? __ldg(x + c0) : __ldg(xg + (c0 - ncl));
-    const double x1 = (c1 < ncl) ? __ldg(x + c1) : __ldg(xg + (c1 - ncl));
-    const double x2 = (c2 < ncl) ? __ldg(x + c2) : __ldg(xg + (c2 - ncl));
-    const double x3 = (c3 < ncl) ? __ldg(x + c3) : __ldg(xg + (c3 - ncl));
-    acc = fma(v0, x0, acc);
-    acc = fma(v1, x1, acc);
-    acc = fma(v2, x2, acc);
-    acc = fma(v3, x3, acc);
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s0 < nslices; s0 += 2 * nwarps) {
+    const int64_t s1 = s0 + nwarps;
+    const bool two = s1 < nslices;
+    const int64_t off0 = sl_off[s0], end0 = sl_off[s0 + 1];
+    const int64_t off1 = two ? sl_off[s1] : 0, end1 = two ? sl_off[s1 + 1] : 0;
+    const int width0 = (int)((end0 - off0) >> 5), width1 = (int)((end1 - off1) >> 5);
+    const int *cp0 = col + off0 + lane, *cp1 = col + off1 + lane;
+    const double *vp0 = val + off0 + lane, *vp1 = val + off1 + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    const int wmax = max(width0, width1);
+    for (int w = 0; w < wmax; w += SELL_CHUNK) {
+      /* issue both slices' matrix loads back to back, then the gathers */
+      int c0[SELL_CHUNK], c1[SELL_CHUNK];
+      double v0[SELL_CHUNK], v1[SELL_CHUNK];
+#pragma unroll
+      for (int u = 0; u < SELL_CHUNK; u++) {
+        const bool on0 = w + u < width0, on1 = w + u < width1;
+        c0[u] = on0 ? ld_stream_i32(cp0 + 32 * (w + u)) : 0;
+        v0[u] = on0 ? ld_stream_f64(vp0 + 32 * (w + u)) : 0.0;
+        c1[u] = on1 ? ld_stream_i32(cp1 + 32 * (w + u)) : 0;
+        v1[u] = on1 ? ld_stream_f64(vp1 + 32 * (w + u)) : 0.0;
+      }
+      /* branch-free gathers (entries past the slice width read a valid dummy address with v = 0) so that all of them are
+         in flight together */
+      double x0[SELL_CHUNK], x1[SELL_CHUNK];
+#pragma unroll
+      for (int u = 0; u < SELL_CHUNK; u++) {
+        const double *p0 = (c0[u] < ncl) ? x + c0[u] : xg + (c0[u] - ncl);
+        const double *p1 = (c1[u] < ncl) ? x + c1[u] : xg + (c1[u] - ncl);
+        x0[u] = __ldg(p0);
+        x1[u] = __ldg(p1);
+      }
+#pragma unroll
+      for (int u = 0; u < SELL_CHUNK; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
+    }
+    const int64_t r0 = s0 * 32 + lane, r1 = s1 * 32 + lane;
+    if (r0 < nrows) { if (sigma != 0.0) acc0 -= sigma * x[r0]; y[r0] = acc0; }
+    if (two && r1 < nrows) { if (sigma != 0.0) acc1 -= sigma * x[r1]; y[r1] = acc1; }
   }
-  for (; w < width; w++) {
-    const int c = ld_stream_i32(cp + 32 * w);
-    const double v = ld_stream_f64(vp + 32 * w);
-    acc = fma(v, (c < ncl) ? __ldg(x + c) : __ldg(xg + (c - ncl)), acc);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SELL-32 SpMV, bulk-copy pipeline: the matrix stream (the 12 B per entry that dominate the traffic) is moved by the
+ * TMA unit, not by the warps.  Chunks of whole slices are contiguous in sl_col / sl_val, so ONE producer thread per SM
+ * keeps a 4-stage shared-memory ring full with three `cp.async.bulk` copies per chunk (slice offsets, columns, values;
+ * completion through an mbarrier with complete_tx::bytes) while 16 consumer warps read (col,val) from shared memory, gather
+ * x through L1/L2, and write y.  HBM latency of the stream is covered by ~150 KB in flight per SM instead of by
+ * per-thread loads that sit two dependent round trips (offset -> entry -> x) away from the arithmetic.
+ * ---------------------------------------------------------------------------------------------- */
+#define SP_CAP     4096                 /* entries per stage: 16 KB of columns + 32 KB of values */
+#define SP_MAXS    64                   /* slices per chunk                                       */
+#define SP_STAGES  4
+#define SP_CWARPS  16
+#define SP_THREADS (32 * SP_CWARPS + 32)
+#define SP_OFFS    (SP_MAXS + 2)
+#define SP_STAGE_BYTES (SP_OFFS * 8 + SP_CAP * 12)
+
+__device__ __forceinline__ uint32_t sp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t sp_try_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void sp_wait(uint32_t bar, uint32_t parity) { while (!sp_try_wait(bar, parity)) { } }
+__device__ __forceinline__ void sp_bulk(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__restrict__ sl_off, const int *__restrict__ col,
+                 const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int ncl,
+                 double *__restrict__ y, int64_t nrows, double sigma)
+{
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sp_raw);
+  unsigned long long *empty = full + SP_STAGES;
+  volatile int *meta = reinterpret_cast<volatile int *>(empty + SP_STAGES);      /* [stage][2]: first slice, slice count */
+  unsigned char *stages = sp_raw + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < SP_STAGES; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&full[s])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&empty[s])), "r"(SP_CWARPS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int64_t row = slice * 32 + lane;
-  if (row < nrows) {
-    if (sigma != 0.0) acc -= sigma * x[row];
-    y[row] = acc;
+  __syncthreads();
+
+  if (warp == SP_CWARPS) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int c = blockIdx.x;
+      int s0 = 0, s1 = 0;
+      int64_t e0 = 0, e1 = 0;
+      if (c < nchunks) { s0 = chunk[c]; s1 = chunk[c + 1]; e0 = sl_off[s0]; e1 = sl_off[s1]; }
+      while (c < nchunks) {
+        /* look one chunk ahead so that the dependent loads (chunk -> offsets) are off the critical path */
+        const int cn = c + gridDim.x;
+        int n0 = 0, n1 = 0;
+        int64_t f0 = 0, f1 = 0;
+        if (cn < nchunks) { n0 = chunk[cn]; n1 = chunk[cn + 1]; f0 = sl_off[n0]; f1 = sl_off[n1]; }
+        sp_wait(sp_smem_u32(&empty[s]), ph ^ 1);
+        unsigned char *st = stages + (size_t)s * SP_STAGE_BYTES;
+        const uint32_t bar = sp_smem_u32(&full[s]);
+        const uint32_t nent = (uint32_t)(e1 - e0);
+        const uint32_t noff = (uint32_t)(((s1 - s0 + 1) + 1) & ~1);               /* even count: 16-byte multiples */
+        meta[2 * s] = s0; meta[2 * s + 1] = s1 - s0;                              /* released by the arrive below */
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(noff * 8u + nent * 12u) : "memory");
+        sp_bulk(sp_smem_u32(st), sl_off + s0, noff * 8u, bar);
+        sp_bulk(sp_smem_u32(st + SP_OFFS * 8), col + e0, nent * 4u, bar);
+        sp_bulk(sp_smem_u32(st + SP_OFFS * 8 + SP_CAP * 4), val + e0, nent * 8u, bar);
+        if (++s == SP_STAGES) { s = 0; ph ^= 1; }
+        c = cn; s0 = n0; s1 = n1; e0 = f0; e1 = f1;
+      }
+    }
+    return;
+  }
+
+  int s = 0;
+  uint32_t ph = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    sp_wait(sp_smem_u32(&full[s]), ph);
+    const int s0 = meta[2 * s], ns = meta[2 * s + 1];
+    const unsigned char *st = stages + (size_t)s * SP_STAGE_BYTES;
+    const int64_t *offs = reinterpret_cast<const int64_t *>(st);
+    const int *scol = reinterpret_cast<const int *>(st + SP_OFFS * 8);
+    const double *sval = reinterpret_cast<const double *>(st + SP_OFFS * 8 + SP_CAP * 4);
+    const int64_t base = offs[0];
+    for (int j = warp; j < ns; j += SP_CWARPS) {
+      const int o = (int)(offs[j] - base);
+      const int width = (int)((offs[j + 1] - offs[j]) >> 5);
+      const int *cp = scol + o + lane;
+      const double *vp = sval + o + lane;
+      double acc = 0.0;
+      for (int w = 0; w < width; w += SELL_CHUNK) {
+        int cc[SELL_CHUNK];
+        double vv[SELL_CHUNK], xx[SELL_CHUNK];
+#pragma unroll
+        for (int u = 0; u < SELL_CHUNK; u++) {
+          const bool on = w + u < width;
+          cc[u] = on ? cp[32 * (w + u)] : 0;
+          vv[u] = on ? vp[32 * (w + u)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SELL_CHUNK; u++) {
+          const double *p = (cc[u] < ncl) ? x + cc[u] : xg + (cc[u] - ncl);
+          xx[u] = __ldg(p);
+        }
+#pragma unroll
+        for (int u = 0; u < SELL_CHUNK; u++) acc = fma(vv[u], xx[u], acc);
+      }
+      const int64_t row = (int64_t)(s0 + j) * 32 + lane;
+      if (row < nrows) {
+        if (sigma != 0.0) acc -= sigma * x[row];
+        y[row] = acc;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sp_smem_u32(&empty[s])) : "memory");
+    if (++s == SP_STAGES) { s = 0; ph ^= 1; }
   }
 }
 
@@ -137,7 +287,7 @@ extern "C" int b2k_spmv_set_sell(int mode) { g_sell_mode = (mode >= 0 && mode <=
 
 static int build_sell(b2k_ctx ctx, b2k_csr A)
 {
-  A->nslices = 0; A->sl_off = NULL; A->sl_col = NULL; A->sl_val = NULL; A->sell_elems = 0;
+  A->nslices = 0; A->sl_off = NULL; A->sl_col = NULL; A->sl_val = NULL; A->sell_elems = 0; A->sp_chunk = NULL; A->nchunks = 0;
   if (!sell_mode() || A->nrows == 0 || A->nnz == 0) return B2K_OK;
   const int64_t ns = (A->nrows + 31) / 32;
   int *dwidth = NULL;
@@ -146,27 +296,46 @@ static int build_sell(b2k_ctx ctx, b2k_csr A)
   k_sell_width<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->nrows, ns, dwidth);
   CKLAUNCH(ctx);
   int *hw = (int *)malloc(sizeof(int) * (size_t)ns);
-  int64_t *hoff = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ns + 1));
+  int64_t *hoff = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ns + 4));
   if (!hw || !hoff) { free(hw); free(hoff); cudaFree(dwidth); return B2K_ERR_MEM; }
   CK(cudaMemcpyAsync(hw, dwidth, sizeof(int) * (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dwidth);
   int64_t tot = 0;
   for (int64_t s = 0; s < ns; s++) { hoff[s] = tot; tot += 32 * (int64_t)hw[s]; }
-  hoff[ns] = tot;
+  hoff[ns] = hoff[ns + 1] = hoff[ns + 2] = hoff[ns + 3] = tot;   /* padding: the pipeline kernel copies an even count */
+  /* chunks of whole slices for k_spmv_sell_pipe: even first slice, <= SP_CAP entries, <= SP_MAXS slices */
+  int *hchunk = (int *)malloc(sizeof(int) * (size_t)(ns / 2 + 3));
+  int nchunks = 0;
+  bool pipe_ok = hchunk != NULL && ns < 2147483000LL;
+  for (int64_t s = 0; pipe_ok && s < ns;) {
+    hchunk[nchunks++] = (int)s;
+    int64_t e = s;
+    while (e < ns && e - s < SP_MAXS && hoff[e + 1] - hoff[s] <= SP_CAP) e++;
+    if (e < ns) e = s + ((e - s) & ~(int64_t)1);                    /* keep the next chunk on an even slice */
+    if (e == s) pipe_ok = false;                                    /* a slice (pair) wider than a stage: no pipeline */
+    s = e;
+  }
+  if (pipe_ok) hchunk[nchunks] = (int)ns;
   free(hw);
-  if (sell_mode() == 1 && (double)tot > 1.25 * (double)A->nnz) { free(hoff); return B2K_OK; }   /* too much padding: stay on CSR-stream */
+  if (sell_mode() == 1 && (double)tot > 1.25 * (double)A->nnz) { free(hoff); free(hchunk); return B2K_OK; }   /* too much padding: stay on CSR-stream */
   size_t fr = 0, to = 0;
   cudaMemGetInfo(&fr, &to);
-  if ((double)tot * 12.0 + 8.0 * (double)(ns + 1) > 0.5 * (double)fr) { free(hoff); return B2K_OK; }   /* keep room for the basis */
-  CK(cudaMalloc(&A->sl_off, sizeof(int64_t) * (size_t)(ns + 1)));
+  if ((double)tot * 12.0 + 8.0 * (double)(ns + 1) > 0.5 * (double)fr) { free(hoff); free(hchunk); return B2K_OK; }   /* keep room for the basis */
+  CK(cudaMalloc(&A->sl_off, sizeof(int64_t) * (size_t)(ns + 4)));
   CK(cudaMalloc(&A->sl_col, sizeof(int) * (size_t)tot));
   CK(cudaMalloc(&A->sl_val, sizeof(double) * (size_t)tot));
-  CK(cudaMemcpyAsync(A->sl_off, hoff, sizeof(int64_t) * (size_t)(ns + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(A->sl_off, hoff, sizeof(int64_t) * (size_t)(ns + 4), cudaMemcpyHostToDevice, ctx->stream));
+  if (pipe_ok && nchunks > 0) {
+    CK(cudaMalloc(&A->sp_chunk, sizeof(int) * (size_t)(nchunks + 1)));
+    CK(cudaMemcpyAsync(A->sp_chunk, hchunk, sizeof(int) * (size_t)(nchunks + 1), cudaMemcpyHostToDevice, ctx->stream));
+    A->nchunks = nchunks;
+  }
   k_sell_fill<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->nrows, ns, A->sl_off, A->sl_col, A->sl_val);
   CKLAUNCH(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   free(hoff);
+  free(hchunk);
   A->nslices = ns; A->sell_elems = tot;
   return B2K_OK;
 }
@@ -304,7 +473,7 @@ extern "C" int b2k_csr_destroy(b2k_ctx ctx, b2k_csr A)
   if (!A) return B2K_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(A->rowptr); cudaFree(A->colidx); cudaFree(A->val); cudaFree(A->blkrow);
-  cudaFree(A->sl_off); cudaFree(A->sl_col); cudaFree(A->sl_val);
+  cudaFree(A->sl_off); cudaFree(A->sl_col); cudaFree(A->sl_val); cudaFree(A->sp_chunk);
   free(A);
   return B2K_OK;
 }
@@ -333,8 +502,20 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
   /* algorithmic bytes of the CSR product whichever storage runs: the SELL copy moves 12 B per stored
      entry (padding included) and no row pointers */
   PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 4.0 * (double)(A->nrows + 1) + 8.0 * (double)(A->ncols_local + A->nghost) + 8.0 * (double)A->nrows);
-  if (A->nslices > 0 && sell_mode())
-    k_spmv_sell<<<(unsigned)((A->nslices + 7) / 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x,
+  static int pipe_mode = -1;          /* env B2K_SPMV_PIPE: 1 (default) bulk-copy pipeline over the SELL copy, 0 plain SELL kernel */
+  if (pipe_mode < 0) {
+    const char *e = getenv("B2K_SPMV_PIPE");
+    pipe_mode = (e && e[0] == '0') ? 0 : 1;
+    if (pipe_mode) {
+      cudaError_t ce = cudaFuncSetAttribute(k_spmv_sell_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_STAGES * SP_STAGE_BYTES);
+      if (ce != cudaSuccess) { cudaGetLastError(); pipe_mode = 0; }
+    }
+  }
+  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= 4 * ctx->sm_count)
+    k_spmv_sell_pipe<<<ctx->sm_count, SP_THREADS, 128 + SP_STAGES * SP_STAGE_BYTES, ctx->stream>>>(
+        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma);
+  else if (A->nslices > 0 && sell_mode())
+    k_spmv_sell<<<(unsigned)std::min<int64_t>((A->nslices + 15) / 16, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x,
                                                                             (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
   else
     k_spmv_csr_stream<<<A->nblk, SPMV_THREADS, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->blkrow, x,

@@ -215,12 +215,14 @@ def test_mult(ctx, n, kin, nout):
     assert np.array_equal(got[n:], Y[n:])
 
 
+@pytest.mark.parametrize("tma", [1, 0])                # TMA ring + FP64 tensor cores (k_vq_tma) / DFMA kernel (k_vq)
 @pytest.mark.parametrize("trans", [0, 1])
 @pytest.mark.parametrize("n,k,s,e", [(10, 5, 1, 3), (4099, 64, 0, 40), (100003, 48, 5, 48), (1000, 65, 0, 65),
                                      (4098, 64, 0, 40), (100002, 48, 5, 48), (126, 17, 3, 17), (70000, 64, 0, 64), (1000, 64, 20, 21)])
-def test_mult_inplace(ctx, n, k, s, e, trans):
+def test_mult_inplace(ctx, n, k, s, e, trans, tma):
     """BVMultInPlace semantics (bvblas.c:74-106): V(:,s:e) = V(:,0:k) Q(0:k,s:e), other columns untouched."""
     from slepc_b200._b2k import check
+    check(ctx.lib.b2k_vq_set_tma(tma))
     ld, ldq = n + 2, k + 1
     V, dV, pV = _mk(ctx, n, k + 2, ld, 21)
     rng = np.random.default_rng(22)
@@ -234,6 +236,7 @@ def test_mult_inplace(ctx, n, k, s, e, trans):
     ref[:n, s:e] = V[:n, :k] @ Qe[:k, s:e]
     assert np.allclose(got[:n], ref[:n], rtol=1e-12, atol=1e-11 * np.sqrt(k))
     assert np.array_equal(got[:, e:], V[:, e:]) and np.array_equal(got[:, :s], V[:, :s])
+    check(ctx.lib.b2k_vq_set_tma(1))
 
 
 def test_dot(ctx):

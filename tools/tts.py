@@ -30,22 +30,12 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    import torch
     from slepc_b200 import _b2k, matgen
+    from slepc_b200 import dist as D
     from slepc_b200 import slepc as SL
     from slepc_b200.slepc import S
-    torch.cuda.set_device(local)
     lib = _b2k.load()
-    SL.initialize(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idbuf = (ctypes.c_char * 128)()
-        if rank == 0:
-            _b2k.check(lib.b2k_comm_unique_id(idbuf))
-        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        S.B2KCommInitNCCL(rank, world, ctypes.c_char_p(bytes(t.cpu().numpy().tobytes())))
+    D.init()
 
     def split(N):
         base, rem = divmod(N, world)
@@ -80,6 +70,7 @@ def main():
         M = SL.Mat()
         pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         S.MatCreateB200CSR(N, N, r0, r1, pp(rp), pp(ci), pp(v), r0, r1, M.ref)
+        D.setup_halo(M, N)
         solver = SL.EPS(M, hermitian=False)
         S.EPSSetWhichEigenpairs(solver.h, SL.EPS_LARGEST_REAL)
         S.EPSSetDimensions(solver.h, 8, args.ncv or SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
@@ -99,7 +90,9 @@ def main():
         M = SL.Mat()
         pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         S.MatCreateB200CSR(Mr, Nc, r0, r1, pp(rp), pp(ci), pp(v), c0, c1, M.ref)
-        solver = SL.SVD(M)
+        D.setup_halo(M, Nc)
+        del rp, ci, v
+        solver = SL.SVD(M)                                         # A^T through MatMultTranspose (implicit) on > 1 rank
         S.SVDSetDimensions(solver.h, 10, args.ncv or 20, SL.PETSC_DETERMINE)
         info = dict(matrix=f"random sparse {Mr}x{Nc}, 20 draws/row", rows=Mr, cols=Nc, nsv=10, ncv=args.ncv or 20)
     is_svd = args.case == "c5"
@@ -131,11 +124,7 @@ def main():
         out["max_rel_dist_to_analytic"] = float(max(np.min(np.abs(analytic - x)) / abs(x) for x in vals))
     if rank == 0:
         print(json.dumps(out), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        S.B2KCommReset()
-        dist.destroy_process_group()
+    D.finalize()
 
 
 if __name__ == "__main__":
