@@ -209,13 +209,13 @@ static tm_encode_fn tm_get_encode(void)
   return g_encode;
 }
 
-int b2k_tm_make_map(CUtensorMap *map, const double *base, int64_t n, int64_t ncols, int64_t ld, int box_cols)
+int b2k_tm_make_map(CUtensorMap *map, const double *base, int64_t n, int64_t ncols, int64_t ld, int box_cols, int box_rows)
 {
   tm_encode_fn enc = tm_get_encode();
   if (!enc) return -1;
   const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)ncols};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  const cuuint32_t box[2] = {TM_ROWS, (cuuint32_t)box_cols};
+  const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -259,8 +259,8 @@ int b2k_gs_tma_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k
   if (!b2k_is_aligned16(V) || !b2k_is_aligned16(w) || (ld & 1)) return -1;
   CUtensorMap mV, mW;
   const int cpt = (k <= 16) ? 4 : (k <= 32 ? 8 : (k <= 48 ? 12 : 16));
-  if (b2k_tm_make_map(&mV, V, n, k, ld, 4 * cpt)) return -1;
-  if (b2k_tm_make_map(&mW, w, n, 1, ld, 1)) return -1;
+  if (b2k_tm_make_map(&mV, V, n, k, ld, 4 * cpt, TM_ROWS)) return -1;
+  if (b2k_tm_make_map(&mW, w, n, 1, ld, 1, TM_ROWS)) return -1;
   const int nrm = out != nullptr;
   const int64_t ntiles = (n + TM_ROWS - 1) / TM_ROWS;
   int grid = ctx->sm_count;

@@ -34,6 +34,7 @@ struct b2k_csr_s {
   /* chunks of whole slices (even first slice, <= SP_CAP entries, <= SP_MAXS slices) for the bulk-copy pipeline kernel */
   int     *sp_chunk;  /* [nchunks+1] first slice of each chunk */
   int      nchunks;
+  int      sp_cap;    /* entries of the largest chunk, rounded up to 32 */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -115,13 +116,15 @@ __global__ void __launch_bounds__(256) k_spmv_sell(const int64_t *__restrict__ s
  * x through L1/L2, and write y.  HBM latency of the stream is covered by ~150 KB in flight per SM instead of by
  * per-thread loads that sit two dependent round trips (offset -> entry -> x) away from the arithmetic.
  * ---------------------------------------------------------------------------------------------- */
-#define SP_CAP     4096                 /* entries per stage: 16 KB of columns + 32 KB of values */
-#define SP_MAXS    64                   /* slices per chunk                                       */
-#define SP_STAGES  4
+#define SP_CAP     8192                 /* upper bound of entries per chunk (32 slices of width 8); the stage size of a matrix is
+                                           its largest chunk (cap), the ring depth what fits 200 KB: 2..4 stages              */
+#define SP_MAXS    32                   /* slices per chunk: 2 per consumer warp, processed together */
+#define SP_STAGES  4                    /* maximum ring depth */
 #define SP_CWARPS  16
 #define SP_THREADS (32 * SP_CWARPS + 32)
 #define SP_OFFS    (SP_MAXS + 2)
-#define SP_STAGE_BYTES (SP_OFFS * 8 + SP_CAP * 12)
+#define SP_STAGE_BYTES(cap) (SP_OFFS * 8 + (cap) * 12)
+#define SP_SMEM_BUDGET (200 * 1024)
 
 __device__ __forceinline__ uint32_t sp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sp_try_wait(uint32_t bar, uint32_t parity)
@@ -146,19 +149,46 @@ __device__ __forceinline__ void sp_bulk(uint32_t dst, const void *src, uint32_t 
                : "memory");
 }
 
+/* two slices of the same compile-time width W from shared memory: no predicates, no width loop; GHOST = the matrix has
+   halo columns (otherwise every column index addresses x directly) */
+template <int W, bool GHOST>
+__device__ __forceinline__ void sp_pair(const int *__restrict__ cp0, const double *__restrict__ vp0, const int *__restrict__ cp1,
+                                        const double *__restrict__ vp1, const double *__restrict__ x, const double *__restrict__ xg,
+                                        int ncl, double &acc0, double &acc1)
+{
+  int c0[W], c1[W];
+  double v0[W], v1[W], x0[W], x1[W];
+#pragma unroll
+  for (int u = 0; u < W; u++) { c0[u] = cp0[32 * u]; c1[u] = cp1[32 * u]; v0[u] = vp0[32 * u]; v1[u] = vp1[32 * u]; }
+#pragma unroll
+  for (int u = 0; u < W; u++) {
+    if (GHOST) {
+      x0[u] = __ldg((c0[u] < ncl) ? x + c0[u] : xg + (c0[u] - ncl));
+      x1[u] = __ldg((c1[u] < ncl) ? x + c1[u] : xg + (c1[u] - ncl));
+    } else {
+      x0[u] = __ldg(x + c0[u]);
+      x1[u] = __ldg(x + c1[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < W; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
+}
+
+template <bool GHOST>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__restrict__ sl_off, const int *__restrict__ col,
                  const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int ncl,
-                 double *__restrict__ y, int64_t nrows, double sigma)
+                 double *__restrict__ y, int64_t nrows, double sigma, int cap, int nstages)
 {
   extern __shared__ __align__(128) unsigned char sp_raw[];
+  const size_t stage_bytes = SP_STAGE_BYTES((size_t)cap);
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sp_raw);
   unsigned long long *empty = full + SP_STAGES;
   volatile int *meta = reinterpret_cast<volatile int *>(empty + SP_STAGES);      /* [stage][2]: first slice, slice count */
   unsigned char *stages = sp_raw + 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < SP_STAGES; s++) {
+    for (int s = 0; s < nstages; s++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&full[s])), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&empty[s])), "r"(SP_CWARPS));
     }
@@ -181,7 +211,7 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
         int64_t f0 = 0, f1 = 0;
         if (cn < nchunks) { n0 = chunk[cn]; n1 = chunk[cn + 1]; f0 = sl_off[n0]; f1 = sl_off[n1]; }
         sp_wait(sp_smem_u32(&empty[s]), ph ^ 1);
-        unsigned char *st = stages + (size_t)s * SP_STAGE_BYTES;
+        unsigned char *st = stages + (size_t)s * stage_bytes;
         const uint32_t bar = sp_smem_u32(&full[s]);
         const uint32_t nent = (uint32_t)(e1 - e0);
         const uint32_t noff = (uint32_t)(((s1 - s0 + 1) + 1) & ~1);               /* even count: 16-byte multiples */
@@ -189,8 +219,8 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(noff * 8u + nent * 12u) : "memory");
         sp_bulk(sp_smem_u32(st), sl_off + s0, noff * 8u, bar);
         sp_bulk(sp_smem_u32(st + SP_OFFS * 8), col + e0, nent * 4u, bar);
-        sp_bulk(sp_smem_u32(st + SP_OFFS * 8 + SP_CAP * 4), val + e0, nent * 8u, bar);
-        if (++s == SP_STAGES) { s = 0; ph ^= 1; }
+        sp_bulk(sp_smem_u32(st + SP_OFFS * 8 + (size_t)cap * 4), val + e0, nent * 8u, bar);
+        if (++s == nstages) { s = 0; ph ^= 1; }
         c = cn; s0 = n0; s1 = n1; e0 = f0; e1 = f1;
       }
     }
@@ -202,43 +232,64 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     sp_wait(sp_smem_u32(&full[s]), ph);
     const int s0 = meta[2 * s], ns = meta[2 * s + 1];
-    const unsigned char *st = stages + (size_t)s * SP_STAGE_BYTES;
+    const unsigned char *st = stages + (size_t)s * stage_bytes;
     const int64_t *offs = reinterpret_cast<const int64_t *>(st);
     const int *scol = reinterpret_cast<const int *>(st + SP_OFFS * 8);
-    const double *sval = reinterpret_cast<const double *>(st + SP_OFFS * 8 + SP_CAP * 4);
+    const double *sval = reinterpret_cast<const double *>(st + SP_OFFS * 8 + (size_t)cap * 4);
     const int64_t base = offs[0];
-    for (int j = warp; j < ns; j += SP_CWARPS) {
-      const int o = (int)(offs[j] - base);
-      const int width = (int)((offs[j + 1] - offs[j]) >> 5);
-      const int *cp = scol + o + lane;
-      const double *vp = sval + o + lane;
-      double acc = 0.0;
-      for (int w = 0; w < width; w += SELL_CHUNK) {
-        int cc[SELL_CHUNK];
-        double vv[SELL_CHUNK], xx[SELL_CHUNK];
+    for (int j = warp; j < ns; j += 2 * SP_CWARPS) {
+      /* two slices per warp at a time (j and j + 16): twice the gathers in flight, and a chunk of 16 or 32 slices keeps
+         all 16 warps equally busy */
+      const int j1 = j + SP_CWARPS;
+      const bool two = j1 < ns;
+      const int o0 = (int)(offs[j] - base), width0 = (int)((offs[j + 1] - offs[j]) >> 5);
+      const int o1 = two ? (int)(offs[j1] - base) : 0, width1 = two ? (int)((offs[j1 + 1] - offs[j1]) >> 5) : 0;
+      const int *cp0 = scol + o0 + lane, *cp1 = scol + o1 + lane;
+      const double *vp0 = sval + o0 + lane, *vp1 = sval + o1 + lane;
+      double acc0 = 0.0, acc1 = 0.0;
+      int wmax = max(width0, width1);
+      if (two && width0 == width1 && width0 <= 8) {       /* the common case: specialised on the width */
+        switch (width0) {
+          case 1: sp_pair<1, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 2: sp_pair<2, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 3: sp_pair<3, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 4: sp_pair<4, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 5: sp_pair<5, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 6: sp_pair<6, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 7: sp_pair<7, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          case 8: sp_pair<8, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+          default: break;
+        }
+        wmax = 0;
+      }
+      for (int w = 0; w < wmax; w += SELL_CHUNK) {
+        int c0[SELL_CHUNK], c1[SELL_CHUNK];
+        double v0[SELL_CHUNK], v1[SELL_CHUNK], x0[SELL_CHUNK], x1[SELL_CHUNK];
 #pragma unroll
         for (int u = 0; u < SELL_CHUNK; u++) {
-          const bool on = w + u < width;
-          cc[u] = on ? cp[32 * (w + u)] : 0;
-          vv[u] = on ? vp[32 * (w + u)] : 0.0;
+          const bool on0 = w + u < width0, on1 = w + u < width1;
+          c0[u] = on0 ? cp0[32 * (w + u)] : 0;
+          v0[u] = on0 ? vp0[32 * (w + u)] : 0.0;
+          c1[u] = on1 ? cp1[32 * (w + u)] : 0;
+          v1[u] = on1 ? vp1[32 * (w + u)] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < SELL_CHUNK; u++) {
-          const double *p = (cc[u] < ncl) ? x + cc[u] : xg + (cc[u] - ncl);
-          xx[u] = __ldg(p);
+          const double *p0 = (c0[u] < ncl) ? x + c0[u] : xg + (c0[u] - ncl);
+          const double *p1 = (c1[u] < ncl) ? x + c1[u] : xg + (c1[u] - ncl);
+          x0[u] = __ldg(p0);
+          x1[u] = __ldg(p1);
         }
 #pragma unroll
-        for (int u = 0; u < SELL_CHUNK; u++) acc = fma(vv[u], xx[u], acc);
+        for (int u = 0; u < SELL_CHUNK; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
       }
-      const int64_t row = (int64_t)(s0 + j) * 32 + lane;
-      if (row < nrows) {
-        if (sigma != 0.0) acc -= sigma * x[row];
-        y[row] = acc;
-      }
+      const int64_t r0 = (int64_t)(s0 + j) * 32 + lane, r1 = (int64_t)(s0 + j1) * 32 + lane;
+      if (r0 < nrows) { if (sigma != 0.0) acc0 -= sigma * x[r0]; y[r0] = acc0; }
+      if (two && r1 < nrows) { if (sigma != 0.0) acc1 -= sigma * x[r1]; y[r1] = acc1; }
     }
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sp_smem_u32(&empty[s])) : "memory");
-    if (++s == SP_STAGES) { s = 0; ph ^= 1; }
+    if (++s == nstages) { s = 0; ph ^= 1; }
   }
 }
 
@@ -307,13 +358,16 @@ static int build_sell(b2k_ctx ctx, b2k_csr A)
   /* chunks of whole slices for k_spmv_sell_pipe: even first slice, <= SP_CAP entries, <= SP_MAXS slices */
   int *hchunk = (int *)malloc(sizeof(int) * (size_t)(ns / 2 + 3));
   int nchunks = 0;
+  int64_t maxent = 0;
   bool pipe_ok = hchunk != NULL && ns < 2147483000LL;
   for (int64_t s = 0; pipe_ok && s < ns;) {
     hchunk[nchunks++] = (int)s;
     int64_t e = s;
     while (e < ns && e - s < SP_MAXS && hoff[e + 1] - hoff[s] <= SP_CAP) e++;
-    if (e < ns) e = s + ((e - s) & ~(int64_t)1);                    /* keep the next chunk on an even slice */
+    if (e < ns) e = s + ((e - s) >= 16 ? ((e - s) & ~(int64_t)15) : ((e - s) & ~(int64_t)1));   /* 16 or 32 slices = equal work for
+                                                                       the 16 consumer warps; always an even boundary */
     if (e == s) pipe_ok = false;                                    /* a slice (pair) wider than a stage: no pipeline */
+    if (hoff[e] - hoff[s] > maxent) maxent = hoff[e] - hoff[s];
     s = e;
   }
   if (pipe_ok) hchunk[nchunks] = (int)ns;
@@ -330,6 +384,7 @@ static int build_sell(b2k_ctx ctx, b2k_csr A)
     CK(cudaMalloc(&A->sp_chunk, sizeof(int) * (size_t)(nchunks + 1)));
     CK(cudaMemcpyAsync(A->sp_chunk, hchunk, sizeof(int) * (size_t)(nchunks + 1), cudaMemcpyHostToDevice, ctx->stream));
     A->nchunks = nchunks;
+    A->sp_cap = (int)((maxent + 31) & ~(int64_t)31);
   }
   k_sell_fill<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->nrows, ns, A->sl_off, A->sl_col, A->sl_val);
   CKLAUNCH(ctx);
@@ -507,13 +562,25 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
     const char *e = getenv("B2K_SPMV_PIPE");
     pipe_mode = (e && e[0] == '0') ? 0 : 1;
     if (pipe_mode) {
-      cudaError_t ce = cudaFuncSetAttribute(k_spmv_sell_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_STAGES * SP_STAGE_BYTES);
+      cudaError_t ce = cudaFuncSetAttribute(k_spmv_sell_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_spmv_sell_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
       if (ce != cudaSuccess) { cudaGetLastError(); pipe_mode = 0; }
     }
   }
-  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= 4 * ctx->sm_count)
-    k_spmv_sell_pipe<<<ctx->sm_count, SP_THREADS, 128 + SP_STAGES * SP_STAGE_BYTES, ctx->stream>>>(
-        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma);
+  int sp_stages = 0;
+  size_t sp_shm = 0;
+  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= 4 * ctx->sm_count) {
+    sp_stages = (int)(SP_SMEM_BUDGET / SP_STAGE_BYTES((size_t)A->sp_cap));
+    if (sp_stages > SP_STAGES) sp_stages = SP_STAGES;
+    sp_shm = 128 + (size_t)sp_stages * SP_STAGE_BYTES((size_t)A->sp_cap);
+  }
+  if (sp_stages >= 2 && A->nghost > 0)
+    k_spmv_sell_pipe<true><<<ctx->sm_count, SP_THREADS, sp_shm, ctx->stream>>>(
+        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma,
+        A->sp_cap, sp_stages);
+  else if (sp_stages >= 2)
+    k_spmv_sell_pipe<false><<<ctx->sm_count, SP_THREADS, sp_shm, ctx->stream>>>(
+        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, x, (int)A->ncols_local, y, A->nrows, sigma, A->sp_cap, sp_stages);
   else if (A->nslices > 0 && sell_mode())
     k_spmv_sell<<<(unsigned)std::min<int64_t>((A->nslices + 15) / 16, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x,
                                                                             (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
