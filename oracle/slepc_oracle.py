@@ -986,9 +986,110 @@ class SVDResult:
     pass
 
 
+def _svd_orthogonalize_cgs(V, i, h, a, norm_fn):
+    """SVDOrthogonalizeCGS, trlanczos.c:319-355: the post-processing after the first (merged) CGS pass of the
+    one-sided recurrence.  h[0:i] are the already scaled coefficients, h[i] = v_i^T v_i before the update."""
+    refine, eta = V.orthog_ref, V.orthog_eta
+    if refine == BV.REFINE_NEVER:
+        return norm_fn(i)
+    if refine == BV.REFINE_ALWAYS:
+        V.set_active(0, i)
+        c = V.dotvec(V.col(i))                                # BVDotColumn
+        h[0:i] = c
+        V.multvec(-1.0, 1.0, V.col(i), c)                     # BVMultColumn
+        return norm_fn(i)
+    dot = h[i]
+    onorm = math.sqrt(dot) / a
+    s = float(np.sum(h[0:i] ** 2))
+    nrm = dot / (a * a) - s
+    nrm = math.sqrt(nrm) if nrm > 0.0 else norm_fn(i)
+    if nrm < eta * onorm:
+        V.set_active(0, i)
+        c = V.dotvec(V.col(i))
+        h[0:i] = c
+        V.multvec(-1.0, 1.0, V.col(i), c)
+        nrm = norm_fn(i)
+    return nrm
+
+
+def _svd_oneside_cgs(A, AT, alpha, beta, V, U, nconv, l, n, work):
+    """SVDOneSideTRLanczosCGS, trlanczos.c:357-448.  Returns the number of mat-vecs."""
+    k = nconv + l
+    nmv = 1
+    U.col(k)[:] = A @ V.col(k)
+    if l > 0:
+        U.set_active(nconv, k)                                # BVMultColumn(U,-1,1,k,work) uses columns nconv..k-1
+        work[0:l] = beta[nconv:nconv + l]
+        U.multvec(-1.0, 1.0, U.col(k), work[0:l])
+        U.set_active(nconv, n)
+    refine = V.orthog_ref
+
+    def step(i):
+        """norm of u_{i-1} and the merged first CGS pass of v_i (the Begin/End split reductions of :385-400)"""
+        a = U.norm_column(i - 1)
+        if refine == BV.REFINE_IFNEEDED:
+            V.set_active(0, i + 1)
+            work[0:i + 1] = V.dotvec(V.col(i))                # includes v_i^T v_i at work[i]
+            V.set_active(0, i)
+        else:
+            V.set_active(0, i)
+            work[0:i] = V.dotvec(V.col(i))
+        U.scale_column(i - 1, 1.0 / a)
+        work[0:i] /= a
+        V.multvec(-1.0, 1.0 / a, V.col(i), work[0:i])
+        b = _svd_orthogonalize_cgs(V, i, work, a, V.norm_column)
+        return a, b
+
+    for i in range(k + 1, n):
+        V.col(i)[:] = AT @ U.col(i - 1)
+        a, b = step(i)
+        V.scale_column(i, 1.0 / b)
+        if not abs(b) > 10 * EPS_MACH:
+            raise FloatingPointError("Recurrence generated a zero vector; use a two-sided variant")
+        U.col(i)[:] = A @ V.col(i) - b * U.col(i - 1)
+        nmv += 2
+        alpha[i - 1] = a
+        beta[i - 1] = b
+    V.col(n)[:] = AT @ U.col(n - 1)
+    nmv += 1
+    a, b = step(n)
+    V.set_active(nconv, n)
+    alpha[n - 1] = a
+    beta[n - 1] = b
+    return nmv
+
+
+def _svd_oneside_mgs(A, AT, alpha, beta, V, U, nconv, l, n, work):
+    """SVDOneSideTRLanczosMGS, trlanczos.c:264-314."""
+    k = nconv + l
+    nmv = 1
+    U.col(k)[:] = A @ V.col(k)
+    if l > 0:
+        U.set_active(nconv, k)
+        U.multvec(-1.0, 1.0, U.col(k), beta[nconv:nconv + l].copy())
+        U.set_active(nconv, n)
+    a = U.norm_column(k)
+    U.scale_column(k, 1.0 / a)
+    alpha[k] = a
+    for i in range(k + 1, n):
+        V.col(i)[:] = AT @ U.col(i - 1)
+        b, _ = V.orthonormalize_column(i, False)
+        beta[i - 1] = b
+        U.col(i)[:] = A @ V.col(i) - b * U.col(i - 1)
+        nmv += 2
+        a = U.norm_column(i)
+        U.scale_column(i, 1.0 / a)
+        alpha[i] = a
+    V.col(n)[:] = AT @ U.col(n - 1)
+    nmv += 1
+    _, b, _ = V.orthogonalize_column(n)
+    beta[n - 1] = b
+    return nmv
+
+
 def svd_trlanczos(A, AT, M, N, nsv, ncv=None, mpd=None, tol=1e-8, max_it=None, keep=0.5, lock=True,
-                  v0=None, seed=0x5EED, orthog=None):
-    """SVDSolve with -svd_type trlanczos (two-sided), largest singular values.
+                  v0=None, seed=0x5EED, orthog=None, oneside=False):
+    """SVDSolve with -svd_type trlanczos (two-sided, or one-sided with `oneside`), largest singular values.
     Requires M>=N (svdsetup.c:301-306 swaps A/AT otherwise; callers do the swap)."""
     assert M >= N
     ncv, mpd = svd_default_dims(N, nsv, ncv, mpd)
@@ -1006,6 +1107,7 @@ def svd_trlanczos(A, AT, M, N, nsv, ncv=None, mpd=None, tol=1e-8, max_it=None, k
     sigma = np.zeros(ncv + 1)
     errest = np.zeros(ncv + 1)
     w = np.zeros(ld)
+    swork = np.zeros(ncv + 1)
     nconv = 0
     its = 0
     reason = 0
@@ -1022,35 +1124,41 @@ def svd_trlanczos(A, AT, M, N, nsv, ncv=None, mpd=None, tol=1e-8, max_it=None, k
         nv = min(nconv + mpd, ncv)
         alpha = ds.T[:, 0]
         beta = ds.T[:, 1]
-        # SVDTwoSideLanczos gklanczos.c:58-113
-        k0 = nconv + l
-        n_ = nv
-        breakdown = False
-        U.col(k0)[:] = A @ V.col(k0)
-        nmatvec += 1
-        alpha[k0], lindep = U.orthonormalize_column(k0, False)
-        if lindep:
-            n_ = k0
-            breakdown = True
+        if oneside:                                          # trlanczos.c:480-483
+            n_ = nv
+            breakdown = False
+            fn = _svd_oneside_mgs if V.orthog_type == BV.MGS else _svd_oneside_cgs
+            nmatvec += fn(A, AT, alpha, beta, V, U, nconv, l, nv, swork)
         else:
-            for i in range(k0 + 1, nv):
-                V.col(i)[:] = AT @ U.col(i - 1)
-                nmatvec += 1
-                beta[i - 1], lindep = V.orthonormalize_column(i, False)
-                if lindep:
-                    n_ = i
-                    break
-                U.col(i)[:] = A @ V.col(i)
-                nmatvec += 1
-                alpha[i], lindep = U.orthonormalize_column(i, False)
-                if lindep:
-                    n_ = i
-                    break
-            if not lindep:
-                V.col(n_)[:] = AT @ U.col(n_ - 1)
-                nmatvec += 1
-                _, beta[n_ - 1], lindep = V.orthogonalize_column(n_)
-            breakdown = lindep
+            # SVDTwoSideLanczos gklanczos.c:58-113
+            k0 = nconv + l
+            n_ = nv
+            breakdown = False
+            U.col(k0)[:] = A @ V.col(k0)
+            nmatvec += 1
+            alpha[k0], lindep = U.orthonormalize_column(k0, False)
+            if lindep:
+                n_ = k0
+                breakdown = True
+            else:
+                for i in range(k0 + 1, nv):
+                    V.col(i)[:] = AT @ U.col(i - 1)
+                    nmatvec += 1
+                    beta[i - 1], lindep = V.orthonormalize_column(i, False)
+                    if lindep:
+                        n_ = i
+                        break
+                    U.col(i)[:] = A @ V.col(i)
+                    nmatvec += 1
+                    alpha[i], lindep = U.orthonormalize_column(i, False)
+                    if lindep:
+                        n_ = i
+                        break
+                if not lindep:
+                    V.col(n_)[:] = AT @ U.col(n_ - 1)
+                    nmatvec += 1
+                    _, beta[n_ - 1], lindep = V.orthogonalize_column(n_)
+                breakdown = lindep
         nv = n_
         V.scale_column(nv, 1.0 / beta[nv - 1])               # trlanczos.c:487
         V.set_active(nconv, nv)
@@ -1102,6 +1210,9 @@ def svd_trlanczos(A, AT, M, N, nsv, ncv=None, mpd=None, tol=1e-8, max_it=None, k
         if reason == 0 and not breakdown:
             V.copy_column(nv, k + l)
         nconv = k
+    if oneside:                                              # trlanczos.c:540-542
+        for i in range(nconv):
+            U.orthonormalize_column(i, False)
     ds.truncate(nconv, True)
     res = SVDResult()
     res.nconv, res.its, res.reason, res.nmatvec = nconv, its, reason, nmatvec

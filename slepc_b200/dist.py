@@ -70,19 +70,20 @@ def setup_halo(A, ncols_global):
     ghosts = np.ctypeslib.as_array(ctypes.cast(gp, ctypes.POINTER(ctypes.c_int)), shape=(ng.value,)).copy() if ng.value else np.empty(0, np.int32)
     starts = np.array([split(ncols_global, world, r)[0] for r in range(world)] + [ncols_global])
     owner = np.searchsorted(starts, ghosts, side="right") - 1
-    needed = {int(p): ghosts[owner == p] for p in np.unique(owner)}
+    needed = {int(p): np.ascontiguousarray(ghosts[owner == p], dtype=np.int32) for p in np.unique(owner)}
     allneeded = [None] * world
     dist.all_gather_object(allneeded, needed)
     c0 = int(starts[rank])
     rr = sorted(needed)
     rc = [len(needed[p]) for p in rr]
-    sr, sc, si = [], [], []
+    sr, sc, si = [], [], [np.empty(0, np.int32)]
     for p in range(world):
         g = allneeded[p].get(rank)
         if p != rank and g is not None and len(g):
             sr.append(p)
             sc.append(len(g))
-            si.extend((np.asarray(g) - c0).tolist())
+            si.append(np.asarray(g, dtype=np.int64) - c0)
+    si = np.concatenate(si)
     i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
     rr, rc, sr, sc, si = i32(rr), i32(rc), i32(sr), i32(sc), i32(si)
     pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)

@@ -212,7 +212,21 @@ PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscIn
   }
   PetscInt *loc = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nnz + 1));
   PetscCheck(loc, PETSC_ERR_MEM, "out of memory");
-  if (noff) {
+  PetscInt *map = NULL;                           /* global column -> ghost slot, when an N-long table is affordable */
+  if (noff && (int64_t)N <= 536870912LL && (int64_t)N <= 8 * (int64_t)noff + 1048576) {
+    /* O(nnz + N): mark the off-range columns, enumerate them in order (= sorted unique), keep the inverse table */
+    map = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)N);
+    PetscCheck(map, PETSC_ERR_MEM, "out of memory");
+    memset(map, 0xff, sizeof(PetscInt) * (size_t)N);
+    for (PetscInt k = 0; k < nnz; k++) if (colidx[k] < cstart || colidx[k] >= cend) map[colidx[k]] = 0;
+    PetscInt nu = 0;
+    for (PetscInt cg = 0; cg < N; cg++) if (map[cg] == 0) nu++;
+    PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nu ? nu : 1));
+    PetscCheck(g, PETSC_ERR_MEM, "out of memory");
+    nu = 0;
+    for (PetscInt cg = 0; cg < N; cg++) if (map[cg] == 0) { map[cg] = nu; g[nu++] = cg; }
+    a->ghosts = g; a->nghost = nu;
+  } else if (noff) {
     PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)noff), ng = 0;
     PetscCheck(g, PETSC_ERR_MEM, "out of memory");
     for (PetscInt k = 0; k < nnz; k++) if (colidx[k] < cstart || colidx[k] >= cend) g[ng++] = colidx[k];
@@ -224,12 +238,14 @@ PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscIn
   for (PetscInt k = 0; k < nnz; k++) {
     const PetscInt cg = colidx[k];
     if (cg >= cstart && cg < cend) loc[k] = cg - cstart;
+    else if (map) loc[k] = ncl + map[cg];
     else {
       PetscInt lo = 0, hi = a->nghost - 1;
       while (lo < hi) { const PetscInt mid = (lo + hi) / 2; if (a->ghosts[mid] < cg) lo = mid + 1; else hi = mid; }
       loc[k] = ncl + lo;
     }
   }
+  free(map);
   int rc = b2k_csr_create(ctx, m, ncl, a->nghost, rowptr, loc, val, &a->A);
   free(loc);
   if (rc) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_create failed (%d): %s", rc, b2k_last_error()); }

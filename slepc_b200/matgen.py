@@ -26,6 +26,34 @@ def _csr_from_coo(nrows, r, c, v, sum_duplicates=False):
     return rowptr.astype(np.int32), c.astype(np.int32), np.ascontiguousarray(v, dtype=np.float64)
 
 
+def _csr_from_rowslots(cols, vals, valid=None, sum_duplicates=False):
+    """CSR from a fixed number of candidate entries per row (cols/vals/valid are nrows x w): every row is sorted by
+    column on its own (argsort along axis 1 — no global sort), invalid slots dropped, duplicates optionally merged."""
+    nrows, w = cols.shape
+    big = np.iinfo(np.int64).max
+    key = cols.astype(np.int64, copy=True)
+    if valid is not None:
+        key[~valid] = big
+    order = np.argsort(key, axis=1, kind="stable")
+    key = np.take_along_axis(key, order, axis=1)
+    vals = np.take_along_axis(vals, order, axis=1)
+    keep = key != big
+    if sum_duplicates and w > 1:
+        dup = np.zeros_like(keep)
+        dup[:, 1:] = (key[:, 1:] == key[:, :-1]) & keep[:, 1:]
+        if dup.any():
+            # add every run of equal columns into its first slot (runs are short: walk right to left)
+            for s in range(w - 1, 0, -1):
+                d = dup[:, s]
+                if d.any():
+                    vals[d, s - 1] += vals[d, s]
+            keep &= ~dup
+    rowptr = np.zeros(nrows + 1, dtype=np.int64)
+    np.cumsum(keep.sum(axis=1), out=rowptr[1:])
+    assert rowptr[-1] < 2 ** 31, "local nnz exceeds PetscInt (int32)"
+    return rowptr.astype(np.int32), key[keep].astype(np.int32), np.ascontiguousarray(vals[keep], dtype=np.float64)
+
+
 def markov_size(m):
     return m * (m + 1) // 2
 
@@ -41,18 +69,13 @@ def markov_rows(m, r0=0, r1=None):
     i = np.searchsorted(start, ix0, side="right")                # 1-based outer index
     jmax = m - i + 1
     j = ix0 - start[i - 1] + 1                                   # 1-based inner index
-    rloc = ix0 - r0
-    rows, cols, vals = [], [], []
     inner = j != jmax
     pd = cst * (i + j - 1)
-    rows.append(rloc[inner]); cols.append(ix0[inner] + 1); vals.append(np.where(i == 1, 2 * pd, pd)[inner])            # north
-    rows.append(rloc[inner]); cols.append((ix0 + jmax)[inner]); vals.append(np.where(j == 1, 2 * pd, pd)[inner])       # east
     pu = 0.5 - cst * (i + j - 3)
-    s = j > 1
-    rows.append(rloc[s]); cols.append(ix0[s] - 1); vals.append(pu[s])                                                  # south
-    w = i > 1
-    rows.append(rloc[w]); cols.append((ix0 - jmax - 1)[w]); vals.append(pu[w])                                         # west
-    return _csr_from_coo(r1 - r0, np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))
+    cols = np.stack([ix0 + 1, ix0 + jmax, ix0 - 1, ix0 - jmax - 1], axis=1)              # north, east, south, west
+    vals = np.stack([np.where(i == 1, 2 * pd, pd), np.where(j == 1, 2 * pd, pd), pu, pu], axis=1)
+    valid = np.stack([inner, inner, j > 1, i > 1], axis=1)
+    return _csr_from_rowslots(cols, vals, valid)
 
 
 def _splitmix64(x):
@@ -67,16 +90,36 @@ def random_sparse_rows(M, N, nnz_row=20, seed=20261017, r0=0, r1=None):
     """rows [r0,r1) of the M x N synthetic matrix of config C5; reproducible per (seed,row,slot) whatever the partition"""
     r1 = M if r1 is None else r1
     nloc = r1 - r0
-    with np.errstate(over="ignore"):
-        row = np.repeat(np.arange(r0, r1, dtype=np.uint64), nnz_row)
-        slot = np.tile(np.arange(nnz_row, dtype=np.uint64), nloc)
-        key = _splitmix64(row * np.uint64(0x100000001B3) + slot + (np.uint64(seed) << np.uint64(20)))
-        col = (_splitmix64(key) % np.uint64(N)).astype(np.int64)
-        u1 = ((_splitmix64(key ^ np.uint64(0xA5A5A5A5A5A5A5A5)) >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
-        u2 = ((_splitmix64(key ^ np.uint64(0x5A5A5A5A5A5A5A5A)) >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
-    val = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)       # Box-Muller
-    rloc = (row - np.uint64(r0)).astype(np.int64)
-    return _csr_from_coo(nloc, rloc, col, val, sum_duplicates=True)
+    step = 1 << 20                                   # rows per chunk: bounds the temporaries; chunks run on a thread pool
+
+    def chunk(a):
+        b = min(a + step, r1)
+        with np.errstate(over="ignore"):
+            row = np.arange(a, b, dtype=np.uint64)[:, None]
+            slot = np.arange(nnz_row, dtype=np.uint64)[None, :]
+            key = _splitmix64(row * np.uint64(0x100000001B3) + slot + (np.uint64(seed) << np.uint64(20)))
+            col = (_splitmix64(key) % np.uint64(N)).astype(np.int64)
+            u1 = ((_splitmix64(key ^ np.uint64(0xA5A5A5A5A5A5A5A5)) >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
+            u2 = ((_splitmix64(key ^ np.uint64(0x5A5A5A5A5A5A5A5A)) >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
+        val = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)       # Box-Muller
+        return _csr_from_rowslots(col, val, None, sum_duplicates=True)
+
+    starts = list(range(r0, r1, step))
+    if len(starts) > 1:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1, len(starts)))) as pool:
+            chunks = list(pool.map(chunk, starts))   # numpy releases the GIL inside its loops
+    else:
+        chunks = [chunk(a) for a in starts]
+    if not chunks:
+        return np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0)
+    if len(chunks) == 1:
+        return chunks[0]
+    nnz = np.cumsum([0] + [int(c[0][-1]) for c in chunks])
+    assert nnz[-1] < 2 ** 31, "local nnz exceeds PetscInt (int32)"
+    rowptr = np.concatenate([chunks[0][0]] + [c[0][1:] + np.int32(o) for c, o in zip(chunks[1:], nnz[1:-1])])
+    return rowptr, np.concatenate([c[1] for c in chunks]), np.concatenate([c[2] for c in chunks])
 
 
 def laplacian_rows(dim, nx, ny=1, nz=1, r0=0, r1=None):

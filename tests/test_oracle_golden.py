@@ -186,6 +186,22 @@ def test_svd_test3_grcar_golden(lock):
     assert np.linalg.norm(r.V.T @ r.V - np.eye(r.nconv), 1) < 1e-12
 
 
+@pytest.mark.parametrize("orthog", [None, (O.BV.MGS, O.BV.REFINE_IFNEEDED, 0.7071), (O.BV.CGS, O.BV.REFINE_ALWAYS, 0.7071),
+                                    (O.BV.CGS, O.BV.REFINE_NEVER, 0.7071)])
+def test_svd_test3_oneside_golden(orthog):
+    """test3.c suffixes 1_trlanczos_one, _one_mgs, _one_always share output/test3_1.out"""
+    M, N = 35, 30
+    A = O.grcar_rect(M, N)
+    AT = A.T.tocsr()
+    r = O.svd_trlanczos(A, AT, M, N, nsv=4, tol=1e-8, oneside=True, orthog=orthog)
+    assert r.reason > 0 and r.nconv >= 4
+    assert fmt5(r.sigma[:4]) == ["3.22175", "3.21797", "3.16825", "3.15128"]
+    for i in range(4):
+        assert O.svd_relative_error(A, AT, r.sigma[i], r.U[:, i], r.V[:, i]) < 5e-8
+    # test3.c:84-103: level of orthogonality of both bases below 20*tol... the .out says "below the tolerance"
+    assert np.linalg.norm(r.U.T @ r.U - np.eye(r.nconv), 1) + np.linalg.norm(r.V.T @ r.V - np.eye(r.nconv), 1) < 20 * 1e-8
+
+
 def test_eps_matches_analytic_and_arpack_1d():
     n = 400
     A = O.laplacian_1d(n)
