@@ -396,6 +396,9 @@ def run_b200(args, wl):
             "seconds_per_restart_cycle": t_ms / 1e3 / args.steps,
             "kernels": kernels, "gs_sweeps_gbs": (gs_bytes / gs_ms / 1e6) if gs_ms else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": nl, "clocks": clocks,
+            "collectives": ("none (1 GPU)" if world == 1 else
+                            ("k-vector reductions fused into the reduction kernel over NVLink peer memory (k_reduce_partials_xg); halo: ncclSend/Recv"
+                             if D.P2P else "k-vector reductions: ncclAllReduce; halo: ncclSend/Recv")),
         }
         print(json.dumps(line), flush=True)
     D.finalize()

@@ -178,6 +178,18 @@ int  b2k_comm_group_end(b2k_comm comm);
 int  b2k_comm_allgather(b2k_comm comm, const double *sendbuf, double *recvbuf, int64_t count_per_rank);
 int  b2k_comm_reduce_scatter_sum(b2k_comm comm, const double *sendbuf, double *recvbuf, int64_t count_per_rank);
 int  b2k_comm_barrier(b2k_comm comm);
+/* One-shot reductions over NVLink peer memory (replace the device ncclAllReduce of <= 1025 doubles that follows every
+   Gram-Schmidt sweep, i.e. the MPIU_Allreduce of bvcuda.cu:228-248): each rank exports a mailbox (CUDA IPC handle,
+   B2K_COMM_P2P_HANDLE_BYTES), the launcher all-gathers the handles, each rank maps its peers (<= 8 ranks, one box).
+   While the reduce scope is global the BV reductions (b2k_dotvec, b2k_gs_*, b2k_sumsq, b2k_colabssum) return sums over
+   all ranks directly, bit-identical on every rank; collective: all ranks issue the same reductions in the same order. */
+#define B2K_COMM_P2P_HANDLE_BYTES 64
+int  b2k_comm_p2p_handle(b2k_comm comm, void *handle_out_host);
+int  b2k_comm_p2p_open(b2k_comm comm, const void *all_handles_host /* size x 64 bytes, rank order */);
+int  b2k_comm_p2p_close(b2k_comm comm);           /* back to NCCL for the reductions (mappings are released by destroy) */
+int  b2k_comm_p2p_enabled(b2k_comm comm);
+int  b2k_comm_reduce_scope(b2k_comm comm, int global_on, int *fused_out);
+int  b2k_comm_p2p_error(b2k_comm comm, int *flag_out);
 
 #ifdef __cplusplus
 }

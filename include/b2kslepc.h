@@ -85,6 +85,13 @@ typedef int (*B2KSendrecvFn)(const double *sbuf, int nsend, int dest, double *rb
 /* host-buffer communicator driven by callbacks (used with CPU BV types, e.g. gloo in the tests) */
 PetscErrorCode B2KCommInitCallbacks(int rank, int size, B2KAllreduceFn ar, B2KSendrecvFn sr, void *user);
 PetscErrorCode B2KCommReset(void);
+/* optional, after B2KCommInitNCCL on the GPUs of one box: peer-memory (NVLink) mailboxes for the k-vector reductions of
+   every Gram-Schmidt sweep.  Handle: 64 bytes per rank (include/b2k.h b2k_comm_p2p_*), all-gathered by the launcher. */
+PetscErrorCode B2KCommP2PHandle(void *handle_out /* 64 bytes */);
+PetscErrorCode B2KCommP2POpen(const void *all_handles /* size x 64 bytes in rank order */);
+PetscErrorCode B2KCommDisableP2P(void);
+/* reductions of the BV kernels issued between Begin(global) and End are sums over the ranks when *fused comes back true */
+PetscErrorCode B2KCommReduceScope(B2KComm comm, PetscBool global, PetscBool *fused);
 PetscErrorCode B2KCommGetRank(B2KComm comm, int *rank, int *size);
 PetscErrorCode B2KCommAllreduce(B2KComm comm, double *buf, int count, int op, B2KMemType where);
 PetscErrorCode B2KCommSendrecv(B2KComm comm, const double *sbuf, PetscInt nsend, int dest, double *rbuf, PetscInt nrecv, int src,

@@ -84,6 +84,12 @@ SIGNATURES = {
     "b2k_comm_allgather": [c_vp, c_vp, c_vp, c_i64],
     "b2k_comm_reduce_scatter_sum": [c_vp, c_vp, c_vp, c_i64],
     "b2k_comm_barrier": [c_vp],
+    "b2k_comm_p2p_handle": [c_vp, c_vp],
+    "b2k_comm_p2p_open": [c_vp, c_vp],
+    "b2k_comm_p2p_close": [c_vp],
+    "b2k_comm_p2p_enabled": [c_vp],
+    "b2k_comm_reduce_scope": [c_vp, c_int, ctypes.POINTER(c_int)],
+    "b2k_comm_p2p_error": [c_vp, ctypes.POINTER(c_int)],
 }
 _SPECIAL = {
     "b2k_last_error": ([], ctypes.c_char_p),

@@ -130,6 +130,53 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
   if (lane == 0) out[c] = s;
 }
 
+/* second stage FUSED with the sum over the GPUs of the box (replaces k_reduce_partials + ncclAllReduce, i.e. the
+ * MPIU_Allreduce of bvcuda.cu:228-248): the warp that has summed column c over this GPU's CTAs stores the value straight
+ * into the mailbox of every rank over NVLink (peer-mapped HBM), the CTA publishes a sequence-numbered flag to every
+ * rank, waits for the same flag from every rank in its OWN mailbox, and adds the `size` contributions in rank order —
+ * all ranks get bit-identical sums.  One-shot, latency-bound (<= 1025 doubles): no ring, no NCCL launch.
+ * Mailbox = [parity][source rank][column]; two parities suffice because a rank can only be one reduction ahead of the
+ * slowest peer (it cannot finish reduction s+1 before every peer has started it, i.e. finished reading s). */
+__global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *__restrict__ part, int nblk, int pstride, int ncols,
+                                                            double *__restrict__ out, const b2k_xg_s xg, unsigned long long seq)
+{
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const size_t par = (size_t)(seq & 1ull);
+  double s = 0.0;
+  if (c < ncols) {
+    for (int b = lane; b < nblk; b += 32) s += part[(int64_t)b * pstride + c];
+    s = warp_sum(s);
+    if (lane < xg.size) {                         /* lane p delivers to rank p (itself included) */
+      volatile double *dst = xg.box[lane] + (par * B2K_XG_MAXR + xg.rank) * B2K_XG_MAXC + c;
+      *dst = s;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < xg.size) {
+    const int p = threadIdx.x;
+    __threadfence_system();                       /* cumulative: orders the CTA's data stores before the flag */
+    volatile unsigned long long *theirs =
+        reinterpret_cast<unsigned long long *>(xg.box[p] + B2K_XG_DATA_ELEMS) + (par * B2K_XG_MAXR + xg.rank) * B2K_XG_MAXB + blockIdx.x;
+    *theirs = seq;
+    volatile unsigned long long *mine =
+        reinterpret_cast<unsigned long long *>(xg.box[xg.rank] + B2K_XG_DATA_ELEMS) + (par * B2K_XG_MAXR + p) * B2K_XG_MAXB + blockIdx.x;
+    const long long t0 = clock64();
+    while (*mine < seq) {
+      if (clock64() - t0 > 120000000000LL) { *((volatile int *)xg.err) = 1; break; }   /* ~60 s: a peer is missing; fail, do not hang */
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (c < ncols && lane == 0) {
+    const volatile double *src = xg.box[xg.rank] + par * B2K_XG_MAXR * B2K_XG_MAXC + c;
+    double t = 0.0;
+    for (int p = 0; p < xg.size; p++) t += src[(size_t)p * B2K_XG_MAXC];
+    out[c] = t;
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * multvec: y = beta*y + alpha * V(:,0:k) q, optionally emitting partial sums of ||y_new||^2.
  * One thread per row pair, coefficients in shared memory (broadcast reads), 8 independent 16 B
@@ -383,7 +430,12 @@ __global__ void __launch_bounds__((RB / 4) * 16) k_gemm_ts(double *Out, int64_t 
 /* =================================== host-side launchers ======================================== */
 int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, double *out)
 {
-  k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out);
+  if (ctx->xg && ctx->xg_on && ncols <= B2K_XG_MAXC && (ncols + 7) / 8 <= B2K_XG_MAXB)
+    k_reduce_partials_xg<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out, *ctx->xg, ++ctx->xg_seq);
+  else {
+    ARGCHK(!(ctx->xg && ctx->xg_on), "reduction too wide for the peer-memory mailbox");
+    k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out);
+  }
   CKLAUNCH(ctx);
   return B2K_OK;
 }
@@ -401,7 +453,11 @@ static int launch_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, in
   ARGCHK(k >= 0 && k <= B2K_MAX_K, "k out of range");
   const int ncols = k + (with_ww ? 1 : 0);
   if (ncols == 0) return B2K_OK;
-  if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(double) * ncols, ctx->stream)); return B2K_OK; }
+  if (n == 0) {                                   /* a rank without rows still takes part in a cross-GPU reduction */
+    if (ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, ncols, ncols, out);
+    CK(cudaMemsetAsync(out, 0, sizeof(double) * ncols, ctx->stream));
+    return B2K_OK;
+  }
   const int CT = 16;
   int ntiles = (k + CT - 1) / CT;
   if (ntiles < 1) ntiles = 1;
@@ -422,9 +478,7 @@ static int launch_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, in
   else      k_dotvec<16, false><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
   PROF_END(ctx);
   CKLAUNCH(ctx);
-  k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, pstride, ncols, out);
-  CKLAUNCH(ctx);
-  return B2K_OK;
+  return b2k_launch_reduce_partials(ctx, gx, pstride, ncols, out);
 }
 
 extern "C" int b2k_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, const double *y, double *q)
@@ -440,7 +494,11 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
                           const double *q, double *nrm_out)
 {
   ARGCHK(k >= 0 && k <= B2K_MAX_K, "k out of range");
-  if (n == 0) { if (nrm_out) CK(cudaMemsetAsync(nrm_out, 0, sizeof(double), ctx->stream)); return B2K_OK; }
+  if (n == 0) {
+    if (nrm_out && ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, 1, 1, nrm_out);
+    if (nrm_out) CK(cudaMemsetAsync(nrm_out, 0, sizeof(double), ctx->stream));
+    return B2K_OK;
+  }
   const bool vec2 = b2k_is_aligned16(V) && b2k_is_aligned16(y) && (ld % 2 == 0);
   const int64_t items = vec2 ? (n >> 1) : n;
   int gx = grid_rows(ctx, items > 0 ? items : 1, 6);
@@ -452,8 +510,7 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
     else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
     PROF_END(ctx);
     CKLAUNCH(ctx);
-    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, gx, 1, 1, nrm_out);
-    CKLAUNCH(ctx);
+    { const int rc_ = b2k_launch_reduce_partials(ctx, gx, 1, 1, nrm_out); if (rc_) return rc_; }
   } else {
     if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
     else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
@@ -521,7 +578,11 @@ extern "C" int b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int6
 extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out)
 {
   ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
-  if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream)); return B2K_OK; }
+  if (n == 0) {
+    if (ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, 1, 1, out);
+    CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream));
+    return B2K_OK;
+  }
   int gx = grid_rows(ctx, n, 4);
   if ((int64_t)gx * k > (int64_t)ctx->sm_count * 8) gx = (ctx->sm_count * 8 + k - 1) / k;
   if (gx < 1) gx = 1;
@@ -530,8 +591,7 @@ extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, in
   k_sumsq<<<grid, 256, 0, ctx->stream>>>(X, ld, n, ctx->partials, k);
   CKLAUNCH(ctx);
   double *tmp = ctx->dscratch;           /* per-column sums */
-  k_reduce_partials<<<(k + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, k, k, tmp);
-  CKLAUNCH(ctx);
+  { const int rc_ = b2k_launch_reduce_partials(ctx, gx, k, k, tmp); if (rc_) return rc_; }
   k_sum_small<<<1, 32, 0, ctx->stream>>>(tmp, k, out);
   CKLAUNCH(ctx);
   return B2K_OK;
@@ -540,15 +600,18 @@ extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, in
 extern "C" int b2k_colabssum(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out_k)
 {
   ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
-  if (n == 0) { CK(cudaMemsetAsync(out_k, 0, sizeof(double) * k, ctx->stream)); return B2K_OK; }
+  if (n == 0) {
+    if (ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, k, k, out_k);
+    CK(cudaMemsetAsync(out_k, 0, sizeof(double) * k, ctx->stream));
+    return B2K_OK;
+  }
   int gx = grid_rows(ctx, n, 4);
   if ((int64_t)gx * k > (int64_t)ctx->sm_count * 8) gx = (ctx->sm_count * 8 + k - 1) / k;
   if (gx < 1) gx = 1;
   dim3 grid(gx, k);
   k_colabssum<<<grid, 256, 0, ctx->stream>>>(X, ld, n, ctx->partials, k);
   CKLAUNCH(ctx);
-  k_reduce_partials<<<(k + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, gx, k, k, out_k);
-  CKLAUNCH(ctx);
+  { const int rc_ = b2k_launch_reduce_partials(ctx, gx, k, k, out_k); if (rc_) return rc_; }
   return B2K_OK;
 }
 

@@ -79,6 +79,12 @@ struct b2k_comm_s {
   b2k_ctx    ctx;
   int        rank, size;
   ncclComm_t nccl;
+  /* peer-memory mailboxes of the one-shot reduction (b2k_comm_p2p_*) */
+  double    *box_local;                 /* cudaMalloc'ed here, exported with cudaIpcGetMemHandle  */
+  void      *box_peer[B2K_XG_MAXR];     /* cudaIpcOpenMemHandle mappings of the other ranks       */
+  int       *err_host;                  /* pinned + mapped                                        */
+  b2k_xg_s   xg;
+  int        p2p_open;
 };
 
 extern "C" int b2k_comm_unique_id(void *id_host)
@@ -109,10 +115,90 @@ extern "C" int b2k_comm_create(b2k_ctx ctx, int rank, int size, const void *id_h
   return B2K_OK;
 }
 
+/* ---- one-shot reductions over NVLink peer memory ------------------------------------------------------------------
+ * Set-up (once per communicator): every rank allocates a mailbox, exports it with CUDA IPC, the launcher all-gathers the
+ * 64-byte handles (like the NCCL id) and every rank maps the mailboxes of its peers.  From then on, while the reduce
+ * scope is "global" (b2k_comm_reduce_scope), the second stage of every two-stage reduction of the BV kernels
+ * (k_reduce_partials_xg, b2k_bv.cu) sums over the ranks itself and the ncclAllReduce that followed it is skipped. */
+extern "C" int b2k_comm_p2p_handle(b2k_comm c, void *handle_out)
+{
+  ARGCHK(c && handle_out, "null argument");
+  ARGCHK(c->size <= B2K_XG_MAXR, "peer-memory reductions support up to 8 ranks");
+  CK(cudaSetDevice(c->ctx->device));
+  if (!c->box_local) {
+    CK(cudaMalloc(&c->box_local, B2K_XG_BYTES));
+    CK(cudaMemset(c->box_local, 0, B2K_XG_BYTES));
+    CK(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
+    *c->err_host = 0;
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->box_local));
+  static_assert(sizeof(h) == B2K_COMM_P2P_HANDLE_BYTES, "CUDA IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_p2p_open(b2k_comm c, const void *all_handles)
+{
+  ARGCHK(c && all_handles && c->box_local, "b2k_comm_p2p_handle() must be called first");
+  CK(cudaSetDevice(c->ctx->device));
+  c->xg.rank = c->rank; c->xg.size = c->size;
+  for (int p = 0; p < c->size; p++) {
+    if (p == c->rank) { c->xg.box[p] = c->box_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)all_handles + (size_t)p * sizeof(h), sizeof(h));
+    CK(cudaIpcOpenMemHandle(&c->box_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+    c->xg.box[p] = (double *)c->box_peer[p];
+  }
+  int *derr = NULL;
+  CK(cudaHostGetDevicePointer((void **)&derr, c->err_host, 0));
+  c->xg.err = derr;
+  c->p2p_open = 1;
+  c->ctx->xg = &c->xg;
+  c->ctx->xg_on = 0;
+  c->ctx->xg_seq = 0;
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_p2p_close(b2k_comm c)
+{
+  if (!c) return B2K_OK;
+  c->p2p_open = 0;
+  if (c->ctx->xg == &c->xg) { c->ctx->xg = NULL; c->ctx->xg_on = 0; }
+  return B2K_OK;
+}
+
+extern "C" int b2k_comm_p2p_enabled(b2k_comm c) { return (c && c->p2p_open) ? 1 : 0; }
+
+/* on != 0: reductions of the BV kernels launched from now on are sums over the ranks (collective: every rank must issue
+   the same reductions in the same order); 0: local again.  Returns 1 through *fused when the peer-memory path is active
+   (the caller then skips its all-reduce), 0 otherwise. */
+extern "C" int b2k_comm_reduce_scope(b2k_comm c, int on, int *fused)
+{
+  const int act = (c && c->p2p_open && c->size > 1) ? 1 : 0;
+  if (act) c->ctx->xg_on = on ? 1 : 0;
+  if (fused) *fused = (act && on) ? 1 : 0;
+  return B2K_OK;
+}
+
+/* non-zero once a peer failed to show up within the kernel's time-out (the sums of that reduction are then invalid) */
+extern "C" int b2k_comm_p2p_error(b2k_comm c, int *flag)
+{
+  if (flag) *flag = (c && c->err_host) ? *(volatile int *)c->err_host : 0;
+  return B2K_OK;
+}
+
 extern "C" int b2k_comm_destroy(b2k_comm c)
 {
   if (!c) return B2K_OK;
-  if (c->nccl) { cudaStreamSynchronize(c->ctx->stream); g_nccl.CommDestroy(c->nccl); }
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->ctx->xg == &c->xg) { c->ctx->xg = NULL; c->ctx->xg_on = 0; }
+  for (int p = 0; p < B2K_XG_MAXR; p++) if (c->box_peer[p]) cudaIpcCloseMemHandle(c->box_peer[p]);
+  if (c->p2p_open && c->nccl && c->size > 1) b2k_comm_barrier(c);   /* nobody maps my mailbox any more: safe to free it */
+  if (c->box_local) cudaFree(c->box_local);
+  if (c->err_host) cudaFreeHost(c->err_host);
+  if (c->nccl) g_nccl.CommDestroy(c->nccl);
   free(c);
   return B2K_OK;
 }

@@ -6,6 +6,20 @@
 #include <stdio.h>
 #include "b2k.h"
 
+/* cross-GPU one-shot reduction over NVLink peer memory (b2k_comm.cu, k_reduce_partials_xg in b2k_bv.cu): every rank owns
+   a mailbox in its HBM that all ranks of the box map through CUDA IPC; passed BY VALUE to the reduction kernel */
+#define B2K_XG_MAXR 8                 /* ranks (GPUs of one NVSwitch box)                                  */
+#define B2K_XG_MAXC 1032              /* doubles per (parity, source rank): >= B2K_MAX_K + 1               */
+#define B2K_XG_MAXB 136               /* flags per (parity, source rank): one per reduction CTA (8 columns) */
+#define B2K_XG_DATA_ELEMS (2 * B2K_XG_MAXR * B2K_XG_MAXC)
+#define B2K_XG_FLAG_ELEMS (2 * B2K_XG_MAXR * B2K_XG_MAXB)
+#define B2K_XG_BYTES      (sizeof(double) * B2K_XG_DATA_ELEMS + sizeof(unsigned long long) * B2K_XG_FLAG_ELEMS)
+struct b2k_xg_s {
+  int     rank, size;
+  double *box[B2K_XG_MAXR];           /* box[p] = mailbox of rank p as mapped in THIS process (box[rank] is local) */
+  int    *err;                        /* mapped pinned host flag: set when a peer did not show up in time  */
+};
+
 struct b2k_ctx_s {
   int          device;
   int          sm_count;
@@ -24,7 +38,13 @@ struct b2k_ctx_s {
   double      *prof_bytes;
   double       prof_ms[B2K_PROF_NCLASS], prof_b[B2K_PROF_NCLASS];
   uint64_t     prof_cnt[B2K_PROF_NCLASS];
+  /* when xg_on, every two-stage reduction launched through b2k_launch_reduce_partials also sums over the ranks */
+  b2k_xg_s    *xg;
+  int          xg_on;
+  unsigned long long xg_seq;
 };
+
+int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, double *out);   /* b2k_bv.cu */
 
 /* bracket the dominant kernel of an entry point; `bytes` = algorithmic bytes of this launch */
 #define PROF_BEGIN(ctx, cls, bytes)                                                          \

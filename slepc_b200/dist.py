@@ -12,6 +12,9 @@ from . import slepc as SL
 from .slepc import S
 
 
+P2P = False      # set by init(): True when the Gram-Schmidt reductions run over peer-memory mailboxes instead of NCCL
+
+
 def env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,7 +40,42 @@ def init(backend="nccl"):
         t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
         S.B2KCommInitNCCL(rank, world, ctypes.c_char_p(bytes(t.cpu().numpy().tobytes())))
+        if world <= 8 and os.environ.get("B2K_COMM_P2P", "1") != "0":
+            global P2P
+            P2P = enable_p2p(rank, world)
     return rank, world
+
+
+def enable_p2p(rank, world):
+    """Peer-memory (NVLink) mailboxes for the k-vector reductions of the Gram-Schmidt sweeps: every rank exports a CUDA IPC
+    handle of its mailbox, the handles are all-gathered here, every rank maps its peers (include/b2k.h b2k_comm_p2p_*).
+    All ranks take the same decision (a rank that cannot export or map vetoes it for everyone): NCCL stays the fallback."""
+    import torch
+    import torch.distributed as dist
+    h = (ctypes.c_char * 64)()
+    ok = 1
+    try:
+        S.B2KCommP2PHandle(h)
+    except Exception:
+        ok = 0
+    t = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).cuda()
+    allh = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return False
+    blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+    try:
+        S.B2KCommP2POpen(ctypes.c_char_p(blob))
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        S.B2KCommDisableP2P()
+        return False
+    return True
 
 
 def finalize():

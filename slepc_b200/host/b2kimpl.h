@@ -219,6 +219,7 @@ struct _p_SVD {
   PetscReal    tol;
   SVDWhich     which;
   PetscBool    impltrans, swapped, oneside, lock, owns_AT;
+  PetscScalar *swork;         /* ncv+1 coefficients of the one-sided recurrence (trlanczos.c:463) */
   PetscReal    keep;
   Mat          OP, A, AT;        /* user matrix; working pair after the M<N swap (svdsetup.c:301-306) */
   Mat          userAT;

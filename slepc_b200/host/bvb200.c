@@ -66,14 +66,30 @@ static PetscErrorCode BVFreeScratch_B200(BV_B200 *d)
   return PETSC_SUCCESS;
 }
 
-/* sum over ranks of `count` doubles in slot memory, then bring them to the pinned mirror and wait */
-static PetscErrorCode BVFetch_B200(BV bv, BV_B200 *d, double *dptr, PetscInt count, PetscBool reduce, double **hptr)
+/* Reductions over the ranks: when the communicator has peer-memory mailboxes (B2KCommP2POpen) the second stage of the
+   kernels' own reduction already sums over the GPUs (k_reduce_partials_xg) and the all-reduce below is skipped.
+   BVScope_B200(bv, reduce, &fused) opens the scope before the kernels are launched; BVFetch_B200 closes it. */
+static PetscErrorCode BVScope_B200(BV bv, PetscBool reduce, PetscBool *fused)
+{
+  *fused = PETSC_FALSE;
+  if (reduce) PetscCall(B2KCommReduceScope(bv->comm, PETSC_TRUE, fused));
+  return PETSC_SUCCESS;
+}
+
+/* sum over ranks of `count` doubles in slot memory (unless the kernels did it), then bring them to the pinned mirror and wait */
+static PetscErrorCode BVFetch_B200(BV bv, BV_B200 *d, double *dptr, PetscInt count, PetscBool reduce, PetscBool fused, double **hptr)
 {
   b2k_ctx ctx = CTX();
-  if (reduce) PetscCall(B2KCommAllreduce(bv->comm, dptr, count, 0, B2K_MEM_DEVICE));
+  if (fused) PetscCall(B2KCommReduceScope(bv->comm, PETSC_FALSE, NULL));
+  else if (reduce) PetscCall(B2KCommAllreduce(bv->comm, dptr, count, 0, B2K_MEM_DEVICE));
   double *hp = d->hco + (dptr - d->dco);
   B2KCall(b2k_d2h_async(ctx, hp, dptr, sizeof(double) * (size_t)count));
   B2KCall(b2k_ctx_sync(ctx));
+  if (fused) {
+    int bad = 0;
+    B2KCall(b2k_comm_p2p_error(bv->comm->nccl, &bad));
+    PetscCheck(!bad, PETSC_ERR_LIB, "peer-memory reduction timed out: a rank did not take part in the collective");
+  }
   *hptr = hp;
   return PETSC_SUCCESS;
 }
@@ -86,9 +102,11 @@ static PetscErrorCode BVDotVec_B200_Private(BV X, Vec y, PetscScalar *q, PetscBo
   PetscScalar *qq = q ? q : X->buffer;
   if (k <= 0) return PETSC_SUCCESS;
   PetscCheck(y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors");
+  PetscBool fused;
+  PetscCall(BVScope_B200(X, reduce, &fused));
   B2KCall(b2k_dotvec(CTX(), COL(X, d, X->l), X->ld, X->n, k, y->array, SLOT(d, 0)));
   double *hp;
-  PetscCall(BVFetch_B200(X, d, SLOT(d, 0), k, reduce, &hp));
+  PetscCall(BVFetch_B200(X, d, SLOT(d, 0), k, reduce, fused, &hp));
   memcpy(qq, hp, sizeof(double) * (size_t)k);
   return PETSC_SUCCESS;
 }
@@ -117,6 +135,7 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
   const PetscInt kk = bv->nc + j;                 /* columns to project against: physical 0..kk-1 (l = -nc) */
   PetscScalar *cc = c ? c : bv->buffer;
   double *w, *hp;
+  PetscBool fused = PETSC_FALSE;
   if (v) { PetscCheck(v->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors"); w = v->array; }
   else w = COL(bv, d, j);
   bv->k = j;                                      /* as bvorthog.c:99 */
@@ -124,8 +143,9 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
   if (kk == 0) {                                  /* nothing to project: only the norm */
     if (onorm || norm) {
       PetscReal beta;
+      PetscCall(BVScope_B200(bv, PETSC_TRUE, &fused));
       B2KCall(b2k_sumsq(ctx, w, bv->ld, bv->n, 1, SLOT(d, 0)));
-      PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 1, PETSC_TRUE, &hp));
+      PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 1, PETSC_TRUE, fused, &hp));
       beta = sqrt(hp[0]);
       if (onorm) *onorm = beta;
       if (norm) *norm = beta;
@@ -141,8 +161,9 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
     const PetscReal beta2 = d->pend_nrm2;
     const PetscBool need_norm = norm ? PETSC_TRUE : PETSC_FALSE;
     if (need_norm) {
+      PetscCall(BVScope_B200(bv, PETSC_TRUE, &fused));
       B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 1), SLOT(d, 3)));   /* c2 still sits in slot 1 */
-      PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, &hp));
+      PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, fused, &hp));
       *norm = sqrt(hp[0]);
     } else {
       B2KCall(b2k_multvec(ctx, d->V, bv->ld, bv->n, kk, -1.0, 1.0, w, SLOT(d, 1)));
@@ -158,22 +179,23 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
   d->last_j = v ? -1 : j; d->last_state = bv->state;
 
   /* sweep 1: c = V^T w and w^T w in one reduction (BVDotColumnInc bvorthog.c:32-47) */
+  PetscCall(BVScope_B200(bv, PETSC_TRUE, &fused));
   B2KCall(b2k_gs_dot(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0)));
-  PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0), kk + 1, 0, B2K_MEM_DEVICE));
+  if (!fused) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0), kk + 1, 0, B2K_MEM_DEVICE));
   const PetscBool fuse = (!v && !repeat && (d->fuse_mode == 1 || (d->fuse_mode == 2 && (d->expect_refine || bv->orthog_ref == BV_ORTHOG_REFINE_ALWAYS)))) ? PETSC_TRUE : PETSC_FALSE;
   if (fuse) {
     /* sweep 2: w -= V c, and from the same read of V the next pass' V^T w_new and ||w_new||^2 */
     B2KCall(b2k_gs_update_dot(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 1)));
-    PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 1), kk + 1, 0, B2K_MEM_DEVICE));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 2 * d->slot, PETSC_FALSE, &hp));
+    if (!fused) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 1), kk + 1, 0, B2K_MEM_DEVICE));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 2 * d->slot, PETSC_FALSE, fused, &hp));
     memcpy(d->pend_c, hp + d->slot, sizeof(double) * (size_t)(kk + 1));
     d->pend_nrm2 = hp[d->slot + kk];
     d->pend_j = j; d->pend_state = bv->state; d->pend_valid = PETSC_TRUE;
   } else {
     /* sweep 2: w -= V c with the explicit ||w_new||^2 folded in */
     B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 0) + kk + 1));
-    PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0) + kk + 1, 1, 0, B2K_MEM_DEVICE));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), kk + 2, PETSC_FALSE, &hp));
+    if (!fused) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 0) + kk + 1, 1, 0, B2K_MEM_DEVICE));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), kk + 2, PETSC_FALSE, fused, &hp));
     d->pend_nrm2 = hp[kk + 1];
   }
   memcpy(cc, hp, sizeof(double) * (size_t)kk);
@@ -205,17 +227,22 @@ static PetscErrorCode BVNorm_B200_Private(BV bv, PetscInt j, NormType type, Pets
   const PetscInt k = (j < 0) ? bv->k - bv->l : 1;
   double *hp;
   if (k <= 0) { *val = 0.0; return PETSC_SUCCESS; }
+  PetscBool fused;
+  PetscCall(BVScope_B200(bv, reduce, &fused));
   if (type == NORM_2 || type == NORM_FROBENIUS) {
     B2KCall(b2k_sumsq(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, reduce, &hp));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, reduce, fused, &hp));
     *val = sqrt(hp[0]);
   } else if (type == NORM_1) {
     B2KCall(b2k_colabssum(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), k, reduce, &hp));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), k, reduce, fused, &hp));
     PetscReal mx = 0.0;
     for (PetscInt i = 0; i < k; i++) mx = PetscMax(mx, hp[i]);
     *val = mx;
-  } else SETERRQ(PETSC_ERR_SUP, "NORM_INFINITY is not implemented for BV type b200 (not on the Krylov path)");
+  } else {
+    if (fused) PetscCall(B2KCommReduceScope(bv->comm, PETSC_FALSE, NULL));
+    SETERRQ(PETSC_ERR_SUP, "NORM_INFINITY is not implemented for BV type b200 (not on the Krylov path)");
+  }
   return PETSC_SUCCESS;
 }
 static PetscErrorCode BVNorm_B200(BV bv, PetscInt j, NormType type, PetscReal *val) { return BVNorm_B200_Private(bv, j, type, val, PETSC_TRUE); }
@@ -228,8 +255,10 @@ static PetscErrorCode BVNormalize_B200(BV bv, PetscScalar *eigi)
   double *hp;
   for (PetscInt i = bv->l; i < bv->k; i++) {
     const PetscInt cols = (eigi && eigi[i] != 0.0 && i + 1 < bv->k) ? 2 : 1;   /* complex conjugate pair stored as two columns */
+    PetscBool fused;
+    PetscCall(BVScope_B200(bv, PETSC_TRUE, &fused));
     B2KCall(b2k_sumsq(ctx, COL(bv, d, i), bv->ld, bv->n, cols, SLOT(d, 3)));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, &hp));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, fused, &hp));
     const PetscReal nrm = sqrt(hp[0]);
     if (nrm != 0.0 && nrm != 1.0) B2KCall(b2k_scale(ctx, COL(bv, d, i), bv->ld, bv->n, cols, 1.0 / nrm));
     i += cols - 1;

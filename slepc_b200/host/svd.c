@@ -5,8 +5,8 @@
  *   SVDSetUp_TRLanczos / SVDSolve_TRLanczos       src/svd/impls/trlanczos/trlanczos.c:203-262, 450-551
  *   SVDTwoSideLanczos, SVDKrylovConvergence       src/svd/impls/lanczos/gklanczos.c:58-113, 189-216
  *   SVDSolve, SVDGetSingularTriplet, SVDComputeError   src/svd/interface/svdsolve.c:116, 313, 486
- * The generalized / hyperbolic branches (trlanczos.c:553-1620) and the one-sided variant are outside
- * the named path.
+ *   SVDOneSideTRLanczosCGS/MGS, SVDOrthogonalizeCGS    src/svd/impls/trlanczos/trlanczos.c:264-448 (SVDTRLanczosSetOneSide)
+ * The generalized / hyperbolic branches (trlanczos.c:553-1620) are outside the named path.
  */
 #include "b2kimpl.h"
 
@@ -36,7 +36,7 @@ PetscErrorCode SVDDestroy(SVD *psvd)
   PetscCall(VecDestroy(&svd->iniV));
   PetscCall(VecDestroy(&svd->iniU));
   for (int i = 0; i < 4; i++) PetscCall(VecDestroy(&svd->work[i]));
-  free(svd->sigma); free(svd->errest); free(svd->perm);
+  free(svd->sigma); free(svd->errest); free(svd->perm); free(svd->swork);
   free(svd);
   *psvd = NULL;
   return PETSC_SUCCESS;
@@ -100,7 +100,6 @@ PetscErrorCode SVDTRLanczosSetRestart(SVD svd, PetscReal keep)
 PetscErrorCode SVDTRLanczosSetLocking(SVD svd, PetscBool lock) { svd->lock = lock; return PETSC_SUCCESS; }
 PetscErrorCode SVDTRLanczosSetOneSide(SVD svd, PetscBool oneside)
 {
-  PetscCheck(!oneside, PETSC_ERR_SUP, "the one-sided variant (trlanczos.c:357-448) is not part of this build yet; the two-sided default is");
   svd->oneside = oneside;
   return PETSC_SUCCESS;
 }
@@ -172,11 +171,12 @@ PetscErrorCode SVDSetUp(SVD svd)
   /* SVDAllocateSolution(svd,1) svdsetup.c */
   const PetscInt requested = svd->ncv + 1;
   if (requested != svd->allocated) {
-    free(svd->sigma); free(svd->errest); free(svd->perm);
+    free(svd->sigma); free(svd->errest); free(svd->perm); free(svd->swork);
+    svd->swork = (PetscScalar *)calloc((size_t)requested + 1, sizeof(PetscScalar));
     svd->sigma = (PetscReal *)calloc((size_t)requested, sizeof(PetscReal));
     svd->errest = (PetscReal *)calloc((size_t)requested, sizeof(PetscReal));
     svd->perm = (PetscInt *)calloc((size_t)requested, sizeof(PetscInt));
-    PetscCheck(svd->sigma && svd->errest && svd->perm, PETSC_ERR_MEM, "out of memory");
+    PetscCheck(svd->sigma && svd->errest && svd->perm && svd->swork, PETSC_ERR_MEM, "out of memory");
     svd->allocated = requested;
   }
   BV bvs[2] = {svd->V, svd->U};
@@ -243,6 +243,145 @@ static PetscErrorCode SVDTwoSideLanczos(SVD svd, PetscReal *alpha, PetscReal *be
   return PETSC_SUCCESS;
 }
 
+/* SVDOrthogonalizeCGS trlanczos.c:319-355: post-processing of the merged first CGS pass of the one-sided recurrence;
+   h[0:i] = scaled coefficients, h[i] = v_i^T v_i taken before the update, a = ||u_{i-1}|| */
+static PetscErrorCode SVDOrthogonalizeCGS_Private(BV V, PetscInt i, PetscScalar *h, PetscReal a, BVOrthogRefineType refine, PetscReal eta, PetscReal *norm)
+{
+  switch (refine) {
+  case BV_ORTHOG_REFINE_NEVER:
+    PetscCall(BVNormColumn(V, i, NORM_2, norm));
+    break;
+  case BV_ORTHOG_REFINE_ALWAYS:
+    PetscCall(BVSetActiveColumns(V, 0, i));
+    PetscCall(BVDotColumn(V, i, h));
+    PetscCall(BVMultColumn(V, -1.0, 1.0, i, h));
+    PetscCall(BVNormColumn(V, i, NORM_2, norm));
+    break;
+  case BV_ORTHOG_REFINE_IFNEEDED: {
+    const PetscScalar dot = h[i];
+    const PetscReal onorm = sqrt(dot) / a;
+    PetscReal sum = 0.0;
+    for (PetscInt j = 0; j < i; j++) sum += h[j] * h[j];
+    *norm = dot / (a * a) - sum;
+    if (*norm > 0.0) *norm = sqrt(*norm);
+    else PetscCall(BVNormColumn(V, i, NORM_2, norm));
+    if (*norm < eta * onorm) {
+      PetscCall(BVSetActiveColumns(V, 0, i));
+      PetscCall(BVDotColumn(V, i, h));
+      PetscCall(BVMultColumn(V, -1.0, 1.0, i, h));
+      PetscCall(BVNormColumn(V, i, NORM_2, norm));
+    }
+  } break;
+  }
+  return PETSC_SUCCESS;
+}
+
+/* ||u_{i-1}|| together with the first CGS pass of v_i (the reference merges both reductions into one MPI_Allreduce with
+   the Begin/End split calls, trlanczos.c:385-400; here they are two device reductions on the same stream), then the
+   scaled update v_i <- v_i/a - V (h/a) and the refinement decision */
+static PetscErrorCode SVDOneSideStep_Private(SVD svd, PetscInt i, PetscScalar *work, BVOrthogRefineType refine, PetscReal eta, PetscReal *pa, PetscReal *pb)
+{
+  BV V = svd->V, U = svd->U;
+  PetscReal a, b;
+  PetscCall(BVNormColumn(U, i - 1, NORM_2, &a));
+  if (refine == BV_ORTHOG_REFINE_IFNEEDED) {
+    Vec vi;
+    PetscCall(BVSetActiveColumns(V, 0, i + 1));
+    PetscCall(BVGetColumn(V, i, &vi));
+    PetscErrorCode ierr = BVDotVec(V, vi, work);        /* work[i] = v_i^T v_i comes with the same sweep */
+    PetscCall(BVRestoreColumn(V, i, &vi));
+    PetscCall(ierr);
+    PetscCall(BVSetActiveColumns(V, 0, i));
+  } else {
+    PetscCall(BVSetActiveColumns(V, 0, i));
+    PetscCall(BVDotColumn(V, i, work));
+  }
+  PetscCall(BVScaleColumn(U, i - 1, 1.0 / a));
+  for (PetscInt j = 0; j < i; j++) work[j] = work[j] / a;
+  PetscCall(BVMultColumn(V, -1.0, 1.0 / a, i, work));
+  PetscCall(SVDOrthogonalizeCGS_Private(V, i, work, a, refine, eta, &b));
+  *pa = a; *pb = b;
+  return PETSC_SUCCESS;
+}
+
+/* u_i = A v_i - b u_{i-1}  (trlanczos.c:408-416) */
+static PetscErrorCode SVDOneSideNextU_Private(SVD svd, PetscInt i, PetscReal b)
+{
+  Vec ui, ui1;
+  PetscCall(SVDMatMultColumns_Private(svd->A, svd->V, i, svd->U, i));
+  PetscCall(BVGetColumn(svd->U, i, &ui));
+  PetscCall(BVGetColumn(svd->U, i - 1, &ui1));
+  PetscErrorCode ierr = VecAXPY(ui, -b, ui1);
+  PetscCall(BVRestoreColumn(svd->U, i, &ui));
+  PetscCall(BVRestoreColumn(svd->U, i - 1, &ui1));
+  PetscCall(ierr);
+  svd->U->state++;
+  return PETSC_SUCCESS;
+}
+
+/* u_k = A v_k - U(:,nconv:k) beta(nconv:k)  (trlanczos.c:365-374, :272-281) */
+static PetscErrorCode SVDOneSideFirstU_Private(SVD svd, PetscReal *beta, PetscInt nconv, PetscInt l, PetscInt n, PetscScalar *work)
+{
+  const PetscInt k = nconv + l;
+  PetscCall(SVDMatMultColumns_Private(svd->A, svd->V, k, svd->U, k));
+  if (l > 0) {
+    PetscCall(BVSetActiveColumns(svd->U, nconv, n));
+    for (PetscInt i = 0; i < l; i++) work[i] = beta[i + nconv];
+    PetscCall(BVMultColumn(svd->U, -1.0, 1.0, k, work));
+  }
+  return PETSC_SUCCESS;
+}
+
+/* SVDOneSideTRLanczosCGS trlanczos.c:357-448: only V is orthogonalised (one merged CGS pass + refinement if needed);
+   U comes from the three-term recurrence and is re-orthonormalised once, after convergence */
+static PetscErrorCode SVDOneSideTRLanczosCGS(SVD svd, PetscReal *alpha, PetscReal *beta, PetscInt nconv, PetscInt l, PetscInt n, PetscScalar *work)
+{
+  PetscReal a, b, eta;
+  const PetscInt k = nconv + l;
+  BVOrthogRefineType refine;
+  PetscCall(SVDOneSideFirstU_Private(svd, beta, nconv, l, n, work));
+  PetscCall(BVGetOrthogonalization(svd->V, NULL, &refine, &eta, NULL));
+  for (PetscInt i = k + 1; i < n; i++) {
+    PetscCall(SVDMatMultColumns_Private(svd->AT, svd->U, i - 1, svd->V, i));
+    PetscCall(SVDOneSideStep_Private(svd, i, work, refine, eta, &a, &b));
+    PetscCall(BVScaleColumn(svd->V, i, 1.0 / b));
+    PetscCheck(fabs(b) > 10 * PETSC_MACHINE_EPSILON, PETSC_ERR_PLIB, "Recurrence generated a zero vector; use a two-sided variant");
+    PetscCall(SVDOneSideNextU_Private(svd, i, b));
+    alpha[i - 1] = a;
+    beta[i - 1] = b;
+  }
+  PetscCall(SVDMatMultColumns_Private(svd->AT, svd->U, n - 1, svd->V, n));
+  PetscCall(SVDOneSideStep_Private(svd, n, work, refine, eta, &a, &b));
+  PetscCall(BVSetActiveColumns(svd->V, nconv, n));
+  alpha[n - 1] = a;
+  beta[n - 1] = b;
+  return PETSC_SUCCESS;
+}
+
+/* SVDOneSideTRLanczosMGS trlanczos.c:264-314 (taken when the BV orthogonalisation type is MGS, :481) */
+static PetscErrorCode SVDOneSideTRLanczosMGS(SVD svd, PetscReal *alpha, PetscReal *beta, PetscInt nconv, PetscInt l, PetscInt n, PetscScalar *work)
+{
+  PetscReal a, b;
+  const PetscInt k = nconv + l;
+  PetscCall(SVDOneSideFirstU_Private(svd, beta, nconv, l, n, work));
+  PetscCall(BVNormColumn(svd->U, k, NORM_2, &a));
+  PetscCall(BVScaleColumn(svd->U, k, 1.0 / a));
+  alpha[k] = a;
+  for (PetscInt i = k + 1; i < n; i++) {
+    PetscCall(SVDMatMultColumns_Private(svd->AT, svd->U, i - 1, svd->V, i));
+    PetscCall(BVOrthonormalizeColumn(svd->V, i, PETSC_FALSE, &b, NULL));
+    beta[i - 1] = b;
+    PetscCall(SVDOneSideNextU_Private(svd, i, b));
+    PetscCall(BVNormColumn(svd->U, i, NORM_2, &a));
+    PetscCall(BVScaleColumn(svd->U, i, 1.0 / a));
+    alpha[i] = a;
+  }
+  PetscCall(SVDMatMultColumns_Private(svd->AT, svd->U, n - 1, svd->V, n));
+  PetscCall(BVOrthogonalizeColumn(svd->V, n, NULL, &b, NULL));
+  beta[n - 1] = b;
+  return PETSC_SUCCESS;
+}
+
 /* one pass of the restart loop of SVDSolve_TRLanczos, trlanczos.c:475-537 */
 static PetscErrorCode SVDTRLanczosCycle_Private(SVD svd)
 {
@@ -257,7 +396,11 @@ static PetscErrorCode SVDTRLanczosCycle_Private(SVD svd)
   nv = PetscMin(svd->nconv + svd->mpd, svd->ncv);
   PetscCall(DSGetArrayReal(svd->ds, DS_MAT_T, &alpha));
   beta = alpha + ld;
-  PetscCall(SVDTwoSideLanczos(svd, alpha, beta, svd->nconv + l, &nv, &breakdown));
+  if (svd->oneside) {                             /* trlanczos.c:480-483 */
+    PetscScalar *swork = svd->swork;
+    if (svd->V->orthog_type == BV_ORTHOG_MGS) PetscCall(SVDOneSideTRLanczosMGS(svd, alpha, beta, svd->nconv, l, nv, swork));
+    else PetscCall(SVDOneSideTRLanczosCGS(svd, alpha, beta, svd->nconv, l, nv, swork));
+  } else PetscCall(SVDTwoSideLanczos(svd, alpha, beta, svd->nconv + l, &nv, &breakdown));
   PetscCall(BVScaleColumn(svd->V, nv, 1.0 / beta[nv - 1]));
   PetscCall(BVSetActiveColumns(svd->V, svd->nconv, nv));
   PetscCall(BVSetActiveColumns(svd->U, svd->nconv, nv));
@@ -327,6 +470,8 @@ PetscErrorCode SVDSolve(SVD svd)
   }
   svd->l = 0;
   while (svd->reason == SVD_CONVERGED_ITERATING) PetscCall(SVDTRLanczosCycle_Private(svd));
+  if (svd->oneside)                               /* orthonormalize U columns in one side method, trlanczos.c:540-542 */
+    for (PetscInt i = 0; i < svd->nconv; i++) PetscCall(BVOrthonormalizeColumn(svd->U, i, PETSC_FALSE, NULL, NULL));
   PetscCall(DSTruncate(svd->ds, svd->nconv, PETSC_TRUE));
   svd->solved = PETSC_TRUE;
   /* sort singular triplets, svdsolve.c:149-157 */

@@ -81,6 +81,34 @@ PetscErrorCode B2KCommInitNCCL(int rank, int size, const void *id)
   return PETSC_SUCCESS;
 }
 
+PetscErrorCode B2KCommP2PHandle(void *handle_out)
+{
+  PetscCheck(g_world.kind == 1 && g_world.nccl, PETSC_ERR_ORDER, "B2KCommInitNCCL() must be called before B2KCommP2PHandle()");
+  B2KCall(b2k_comm_p2p_handle(g_world.nccl, handle_out));
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode B2KCommP2POpen(const void *all_handles)
+{
+  PetscCheck(g_world.kind == 1 && g_world.nccl, PETSC_ERR_ORDER, "B2KCommInitNCCL() must be called before B2KCommP2POpen()");
+  B2KCall(b2k_comm_p2p_open(g_world.nccl, all_handles));
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode B2KCommDisableP2P(void)
+{
+  if (g_world.kind == 1 && g_world.nccl) B2KCall(b2k_comm_p2p_close(g_world.nccl));
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode B2KCommReduceScope(B2KComm comm, PetscBool global, PetscBool *fused)
+{
+  int f = 0;
+  if (comm && comm->kind == 1 && comm->size > 1 && comm->nccl) B2KCall(b2k_comm_reduce_scope(comm->nccl, global ? 1 : 0, &f));
+  if (fused) *fused = f ? PETSC_TRUE : PETSC_FALSE;
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode B2KCommInitCallbacks(int rank, int size, B2KAllreduceFn ar, B2KSendrecvFn sr, void *user)
 {
   PetscCall(B2KCommReset());

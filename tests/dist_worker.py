@@ -142,7 +142,7 @@ def main():
         r.pop("X")
         ref = O.eps_krylovschur(A, A.shape[0], nev=4, which="largest_real", hermitian=False, v0=v0)
         res.update(r, ref=list(ref.eigr[:ref.nconv]), ref_nconv=ref.nconv)
-    elif case == "svd":
+    elif case in ("svd", "svd_oneside"):
         Mr, Nc = 35, 30
         A = O.grcar_rect(Mr, Nc)
         AT = A.T.tocsr()
@@ -151,8 +151,9 @@ def main():
         svd = SL.SVD(Ma, Mt)
         CP.use_cpu_bv(svd)
         S.SVDSetDimensions(svd.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+        S.SVDTRLanczosSetOneSide(svd.h, 1 if case == "svd_oneside" else 0)
         svd.solve()
-        ref = O.svd_trlanczos(A, AT, Mr, Nc, nsv=4)
+        ref = O.svd_trlanczos(A, AT, Mr, Nc, nsv=4, oneside=(case == "svd_oneside"))
         res.update(nconv=svd.nconv, sigma=[svd.triplet(i) for i in range(svd.nconv)], errs=[svd.error(i) for i in range(svd.nconv)],
                    ref=list(ref.sigma[:ref.nconv]), ref_nconv=ref.nconv)
     else:

@@ -67,8 +67,9 @@ def test_eps_nhep_split_rows(tmp_path):
     assert abs(lam[0] - 1.0) < 1e-9
 
 
-def test_svd_split_rows(tmp_path):
-    r = run_case("svd", 2, tmp_path)
+@pytest.mark.parametrize("case", ["svd", "svd_oneside"])
+def test_svd_split_rows(case, tmp_path):
+    r = run_case(case, 2, tmp_path)
     assert r["nconv"] == r["ref_nconv"] >= 4
     assert np.allclose(r["sigma"][:4], r["ref"][:4], rtol=1e-10, atol=0)
     assert max(r["errs"][:4]) < 5e-8

@@ -209,6 +209,33 @@ def test_svd_test3_golden(lock):
         assert svd.error(i) < 5e-8
 
 
+ONESIDE = [("cgs", SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED), ("mgs", SL.BV_ORTHOG_MGS, SL.BV_ORTHOG_REFINE_IFNEEDED),
+           ("always", SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_ALWAYS), ("never", SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_NEVER)]
+
+
+@pytest.mark.parametrize("name,otype,oref", ONESIDE)
+def test_svd_test3_oneside_golden(name, otype, oref):
+    """test3.c 1_trlanczos_one / _one_mgs / _one_always (output/test3_1.out): SVDOneSideTRLanczosCGS/MGS, trlanczos.c:264-448"""
+    Mr, N = 35, 30
+    A = O.grcar_rect(Mr, N)
+    MA, MT = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(MA, MT)
+    CP.use_cpu_bv(svd)
+    S.SVDSetDimensions(svd.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.SVDTRLanczosSetOneSide(svd.h, 1)
+    for bv in svd.bvs():
+        S.BVSetOrthogonalization(bv.h, otype, oref, 0.7071, 0)
+    svd.solve()
+    assert svd.reason > 0 and svd.nconv >= 4
+    sig = [svd.triplet(i) for i in range(4)]
+    assert fmt5(sig) == ["3.22175", "3.21797", "3.16825", "3.15128"]
+    ref = O.svd_trlanczos(A, A.T.tocsr(), Mr, N, nsv=4, oneside=True, orthog=(otype, oref, 0.7071))
+    assert svd.its == ref.its and svd.nconv == ref.nconv
+    assert np.allclose(sig, ref.sigma[:4], rtol=1e-12)
+    for i in range(4):
+        assert svd.error(i) < 5e-8
+
+
 def test_svd_wide_matrix_swaps():
     """M < N: SVDSetUp works with the transpose and swaps U/V (svdsetup.c:301-343)"""
     A = O.grcar_rect(35, 30).T.tocsr()          # 30 x 35

@@ -285,6 +285,52 @@ def test_svd_test3_golden(lock):
         assert svd.error(i) < 5e-8
 
 
+@pytest.mark.parametrize("otype,oref", [(SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED), (SL.BV_ORTHOG_MGS, SL.BV_ORTHOG_REFINE_IFNEEDED),
+                                        (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_ALWAYS)])
+def test_svd_test3_oneside_golden(otype, oref):
+    """one-sided thick-restart Lanczos (trlanczos.c:264-448) on the device BVs: test3.c 1_trlanczos_one* share test3_1.out"""
+    Mr, N = 35, 30
+    A = O.grcar_rect(Mr, N)
+    svd = SL.SVD(SL.Mat.b200csr(A))
+    S.SVDSetDimensions(svd.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.SVDTRLanczosSetOneSide(svd.h, 1)
+    for bv in svd.bvs():
+        S.BVSetOrthogonalization(bv.h, otype, oref, 0.7071, 0)
+    svd.solve()
+    assert svd.reason > 0 and svd.nconv >= 4
+    sig = [svd.triplet(i) for i in range(4)]
+    assert fmt5(sig) == ["3.22175", "3.21797", "3.16825", "3.15128"]
+    ref = O.svd_trlanczos(A, A.T.tocsr(), Mr, N, nsv=4, oneside=True, orthog=(otype, oref, 0.7071))
+    assert svd.nconv == ref.nconv
+    assert np.allclose(sig, ref.sigma[:4], rtol=1e-10)
+    for i in range(4):
+        assert svd.error(i) < 5e-8
+
+
+def test_svd_oneside_random_sparse_vs_two_sided():
+    """C5 shape at a small size: the one-sided variant returns the singular triplets of the two-sided one"""
+    A = O_random_sparse(20000, 4000)
+    out = []
+    for one in (0, 1):
+        svd = SL.SVD(SL.Mat.b200csr(A))
+        S.SVDSetDimensions(svd.h, 5, 20, SL.PETSC_DETERMINE)
+        S.SVDTRLanczosSetOneSide(svd.h, one)
+        svd.solve()
+        assert svd.reason > 0 and svd.nconv >= 5
+        assert max(svd.error(i) for i in range(5)) < 5e-8
+        out.append([svd.triplet(i) for i in range(5)])
+    assert np.allclose(out[0], out[1], rtol=1e-10)
+
+
+def O_random_sparse(Mr, N):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(20261017)
+    rows = np.repeat(np.arange(Mr), 20)
+    cols = rng.integers(0, N, size=Mr * 20)
+    vals = rng.standard_normal(Mr * 20)
+    return sp.csr_matrix((vals, (rows, cols)), shape=(Mr, N))
+
+
 def test_svd_random_sparse_vs_oracle():
     """BASELINE config 5 shape (tall random sparse, ~20 nnz/row) at a size the oracle finishes in seconds"""
     import scipy.sparse as sp

@@ -114,7 +114,7 @@ def main():
     for i in range(nconv):
         vals.append(solver.triplet(i) if is_svd else solver.eigenvalue(i)[0])
         errs.append(solver.error(i))
-    out = dict(case=args.case, n_gpus=world, **info, tol=args.tol, seconds_solve=t_solve, seconds_build=t_build, its=solver.its,
+    out = dict(case=args.case, n_gpus=world, reductions=("peer-memory one-shot" if D.P2P else ("nccl" if world > 1 else "local")), **info, tol=args.tol, seconds_solve=t_solve, seconds_build=t_build, its=solver.its,
                reason=solver.reason, nconv=nconv, values=vals[:12], max_rel_residual=max(errs) if errs else None,
                kernel_launches=n1.value - n0.value)
     if not is_svd:
