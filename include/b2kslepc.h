@@ -160,7 +160,8 @@ PetscErrorCode MatB200CSRGetInfo(Mat A, int64_t *nnz, int64_t *nghost);
 /* ---- BV (include/slepcbv.h) ------------------------------------------------------------------- */
 typedef enum { BV_ORTHOG_CGS = 0, BV_ORTHOG_MGS = 1 } BVOrthogType;
 typedef enum { BV_ORTHOG_REFINE_IFNEEDED = 0, BV_ORTHOG_REFINE_NEVER = 1, BV_ORTHOG_REFINE_ALWAYS = 2 } BVOrthogRefineType;
-typedef enum { BV_ORTHOG_BLOCK_GS = 0 } BVOrthogBlockType;
+typedef enum { BV_ORTHOG_BLOCK_GS = 0, BV_ORTHOG_BLOCK_CHOL = 1, BV_ORTHOG_BLOCK_TSQR = 2, BV_ORTHOG_BLOCK_TSQRCHOL = 3,
+               BV_ORTHOG_BLOCK_SVQB = 4 } BVOrthogBlockType;   /* include/slepcbv.h:84-88; TSQR/TSQRCHOL: PETSC_ERR_SUP here */
 #define BVB200 "b200"
 
 PetscErrorCode BVRegister(const char *name, PetscErrorCode (*ctor)(BV));      /* slepcbv.h:259, bvfunc.c:646 */

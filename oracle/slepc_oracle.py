@@ -303,6 +303,47 @@ class BV:
             R[j, j] = nrm
         return R
 
+    def orthogonalize_block(self, method="chol", want_R=False):
+        """BVOrthogonalize with BV_ORTHOG_BLOCK_CHOL / SVQB (bvorthog.c:586-601, 660-675; bvlapack.c:136-202, 261-345)
+        on the active columns l..k-1 (leading columns 0..l-1 assumed orthonormal).  Returns R (k x k; upper triangular
+        for chol, full inv(S) for svqb) when want_R, with R[0:l, l:k] = V1^T V2 of the block Gram-Schmidt step."""
+        import scipy.linalg as sla
+        assert self.nc == 0
+        l, k = self.l, self.k
+        Rbuf = np.zeros((self.m, self.m), order="F")
+        if l:                                                   # BVOrthogonalize_BlockGS bvorthog.c:488-499
+            V1 = self.V[:, 0:l]
+            R12 = V1.T @ self.V[:, l:k]
+            Rbuf[0:l, l:k] = R12
+            self.V[:, l:k] -= V1 @ R12
+        G = self.V[:, l:k].T @ self.V[:, l:k]                   # BVDot(V,V,R)
+        n = k - l
+        if method == "chol":
+            try:
+                C = sla.cholesky(G, lower=False)
+            except np.linalg.LinAlgError:                       # bvlapack.c:172-180
+                C = sla.cholesky(G + 50.0 * EPS_MACH * np.eye(n), lower=False)
+            S = sla.solve_triangular(C, np.eye(n), lower=False)
+            S = np.triu(S)
+            Rbuf[l:k, l:k] = np.triu(C)
+        elif method == "svqb":
+            D = 1.0 / np.sqrt(np.diag(G))
+            lam, U = np.linalg.eigh((G * D[:, None]) * D[None, :])
+            S = (U * D[:, None]) / np.sqrt(lam)[None, :]
+            Rbuf[l:k, l:k] = (U.T * np.sqrt(lam)[:, None]) / D[None, :]
+        else:
+            raise ValueError(method)
+        self.V[:, l:k] = self.V[:, l:k] @ S                     # BVMultInPlace(V,S,l,k)
+        if want_R:
+            R = np.zeros((k, k), order="F")
+            if method == "chol":                                # BV_StoreCoeffsBlock_Default tri=TRUE: rows 0..j of column j
+                for j in range(l, k):
+                    R[0:j + 1, j] = Rbuf[0:j + 1, j]
+            else:
+                R[0:k, l:k] = Rbuf[0:k, l:k]
+            return R
+        return None
+
     # ---- Krylov recurrences (bvkrylov.c) ------------------------------------------------------
     def mat_mult_column(self, A, j):
         """BVMatMultColumn, bvops.c:862-885: V[j+1] = A V[j]."""

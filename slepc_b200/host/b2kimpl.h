@@ -49,6 +49,9 @@ void LAPACK(dbdsqr)(const char *, const int *, const int *, const int *, const i
 void LAPACK(dgemv)(const char *, const int *, const int *, const double *, const double *, const int *, const double *,
                    const int *, const double *, double *, const int *, size_t);
 double LAPACK(dnrm2)(const int *, const double *, const int *);
+void LAPACK(dpotrf)(const char *, const int *, double *, const int *, int *, size_t);
+void LAPACK(dtrtri)(const char *, const char *, const int *, double *, const int *, int *, size_t, size_t);
+void LAPACK(dsyev)(const char *, const char *, const int *, double *, const int *, double *, double *, const int *, int *, size_t, size_t);
 
 /* ---- communicator ------------------------------------------------------------------------------- */
 struct _p_B2KComm {

@@ -176,7 +176,8 @@ PetscErrorCode BVSetOrthogonalization(BV bv, BVOrthogType type, BVOrthogRefineTy
   if (eta == (PetscReal)PETSC_DEFAULT || eta == (PetscReal)PETSC_DETERMINE) eta = 0.7071;
   else if (eta != (PetscReal)PETSC_CURRENT) { PetscCheck(eta > 0.0 && eta <= 1.0, PETSC_ERR_ARG_OUTOFRANGE, "Invalid eta value"); }
   else eta = bv->orthog_eta;
-  PetscCheck(block == BV_ORTHOG_BLOCK_GS, PETSC_ERR_SUP, "only the GS block orthogonalization is available (CHOL/TSQR/SVQB are outside the Krylov hot path)");
+  PetscCheck(block == BV_ORTHOG_BLOCK_GS || block == BV_ORTHOG_BLOCK_CHOL || block == BV_ORTHOG_BLOCK_SVQB || block == BV_ORTHOG_BLOCK_TSQR || block == BV_ORTHOG_BLOCK_TSQRCHOL,
+             PETSC_ERR_ARG_WRONG, "Unknown block orthogonalization type");
   bv->orthog_type = type; bv->orthog_ref = refine; bv->orthog_eta = eta; bv->orthog_block = block;
   return PETSC_SUCCESS;
 }
@@ -747,18 +748,132 @@ PetscErrorCode BVOrthonormalizeColumn(BV bv, PetscInt j, PetscBool replace, Pets
 }
 
 /* BVOrthogonalize with BV_ORTHOG_BLOCK_GS — bvorthog.c:560-594, 682-740 */
-PetscErrorCode BVOrthogonalize(BV V, Mat R)
+/* ---- block orthogonalisation: bvorthog.c:488-765, bvlapack.c:136-345 ------------------------------------------
+   CHOL and SVQB are two BLAS-3 sweeps of the basis (BVDot = V^T V, BVMultInPlace = V S) around a k x k host
+   factorisation, i.e. the level-3 kernels of the restart; TSQR/TSQRCHOL (host Householder panels over a raw
+   BVGetArray pointer, bvlapack.c:347-560) have no device counterpart in this build. */
+
+/* the buffer seen as an (nc+m) x m dense matrix, BV_GetBufferMat bvorthog.c:545-559 */
+static PetscErrorCode BV_GetBufferMat(BV bv, Mat *R)
 {
-  BVCheckSizes(V);
+  PetscCall(MatCreateSeqDense(bv->nc + bv->m, bv->m, bv->buffer, R));
+  return PETSC_SUCCESS;
+}
+
+/* BV_StoreCoeffsBlock_Default bvorthog.c:566-581 */
+static PetscErrorCode BV_StoreCoeffsBlock(BV bv, Mat R, PetscBool tri)
+{
+  const PetscInt ldb = bv->m + bv->nc, ldr = R->lda;
+  for (PetscInt j = bv->l; j < bv->k; j++)
+    memcpy(R->dense + (size_t)j * ldr, bv->buffer + (size_t)j * ldb, sizeof(PetscScalar) * (size_t)((tri ? (j + 1) : bv->k) + bv->nc));
+  return PETSC_SUCCESS;
+}
+
+/* Block Gram-Schmidt against the leading columns: V2 = V2 - V1*R12, R12 = V1'*V2 (bvorthog.c:488-499).  The split view V1
+   of BVGetSplit is an alias of V restricted to columns 0..l-1 (same storage, svec.c:427-461). */
+static PetscErrorCode BVOrthogonalize_BlockGS(BV V, Mat R)
+{
+  struct _p_BV V1 = *V;
+  V1.l = 0; V1.k = V->l;
+  V1.ci[0] = V1.ci[1] = -V->nc - 1;
+  PetscCall(BVDot(V, &V1, R));
+  PetscCall(BVMult(V, -1.0, 1.0, &V1, R));
+  return PETSC_SUCCESS;
+}
+
+/* BVMatCholInv_LAPACK_Private bvlapack.c:136-202: upper Cholesky factor in R(l:k,l:k), its inverse in S */
+static PetscErrorCode BVMatCholInv_Private(BV bv, Mat R, Mat S)
+{
+  const PetscInt l = bv->l, k = bv->k, n = k - l, ld = R->lda;
+  int n_ = n, ld_ = ld, lds_, info = 0;
+  PetscScalar *pR = R->dense, *pS;
+  PetscInt lds;
+  PetscScalar *tmp = NULL;
+  if (S == R) {
+    tmp = (PetscScalar *)calloc((size_t)ld * (size_t)k + 1, sizeof(PetscScalar));
+    PetscCheck(tmp, PETSC_ERR_MEM, "out of memory");
+    pS = tmp; lds = ld;
+  } else { pS = S->dense; lds = S->lda; }
+  lds_ = lds;
+  for (PetscInt i = l; i < k; i++) memcpy(pS + (size_t)i * lds + l, pR + (size_t)i * ld + l, sizeof(PetscScalar) * (size_t)n);   /* save a copy */
+  LAPACK(dpotrf)("U", &n_, pR + (size_t)l * ld + l, &ld_, &info, 1);
+  if (info) {                                     /* retry on a diagonally perturbed matrix, bvlapack.c:172-180 */
+    for (PetscInt i = l; i < k; i++) {
+      memcpy(pR + (size_t)i * ld + l, pS + (size_t)i * lds + l, sizeof(PetscScalar) * (size_t)n);
+      pR[i + (size_t)i * ld] += 50.0 * PETSC_MACHINE_EPSILON;
+    }
+    LAPACK(dpotrf)("U", &n_, pR + (size_t)l * ld + l, &ld_, &info, 1);
+    if (info) { free(tmp); SETERRQ(PETSC_ERR_LIB, "Error in LAPACK subroutine potrf: info=%d", info); }
+  }
+  if (S == R) LAPACK(dtrtri)("U", "N", &n_, pR + (size_t)l * ld + l, &ld_, &info, 1, 1);
+  else {
+    memset(pS + (size_t)l * lds, 0, sizeof(PetscScalar) * (size_t)(k - l) * (size_t)lds);
+    for (PetscInt i = l; i < k; i++) memcpy(pS + (size_t)i * lds + l, pR + (size_t)i * ld + l, sizeof(PetscScalar) * (size_t)n);
+    LAPACK(dtrtri)("U", "N", &n_, pS + (size_t)l * lds + l, &lds_, &info, 1, 1);
+  }
+  free(tmp);
+  PetscCheck(!info, PETSC_ERR_LIB, "Error in LAPACK subroutine trtri: info=%d", info);
+  for (PetscInt i = l; i < k - 1; i++) {          /* zero out entries below the diagonal */
+    memset(pR + (size_t)i * ld + i + 1, 0, sizeof(PetscScalar) * (size_t)(k - i - 1));
+    if (S != R) memset(pS + (size_t)i * lds + i + 1, 0, sizeof(PetscScalar) * (size_t)(k - i - 1));
+  }
+  return PETSC_SUCCESS;
+}
+
+/* BVMatSVQB_LAPACK_Private bvlapack.c:261-345: on input R = V'V; on output S = D U Lambda^{-1/2}, (U,Lambda) the
+   eigendecomposition of D R D, D = diag(R)^{-1/2}; and R = inv(S) = Lambda^{1/2} U' / D when S != R */
+static PetscErrorCode BVMatSVQB_Private(BV bv, Mat R, Mat S)
+{
+  const PetscInt l = bv->l, k = bv->k, n = k - l, ld = R->lda;
+  PetscScalar *pR = R->dense, *pS = (S == R) ? pR : S->dense;
+  const PetscInt lds = (S == R) ? ld : S->lda;
+  int n_ = n, lds_ = lds, info = 0, lwork = -1;
+  double wq = 0.0, dummy = 0.0;
+  LAPACK(dsyev)("V", "L", &n_, pS, &lds_, &dummy, &wq, &lwork, &info, 1, 1);
+  lwork = (int)wq;
+  if (lwork < 3 * n + 8) lwork = 3 * n + 8;
+  double *eig = (double *)malloc(sizeof(double) * (size_t)(2 * n + lwork + 2));
+  PetscCheck(eig, PETSC_ERR_MEM, "out of memory");
+  double *D = eig + n, *work = D + n;
+  for (PetscInt i = l; i < k; i++) D[i - l] = 1.0 / sqrt(pR[i + (size_t)i * ld]);
+  for (PetscInt i = l; i < k; i++) for (PetscInt j = l; j < k; j++) pS[i + (size_t)j * lds] = pR[i + (size_t)j * ld] * D[i - l];
+  for (PetscInt j = l; j < k; j++) for (PetscInt i = l; i < k; i++) pS[i + (size_t)j * lds] *= D[j - l];
+  LAPACK(dsyev)("V", "L", &n_, pS + (size_t)l * lds + l, &lds_, eig, work, &lwork, &info, 1, 1);
+  if (info) { free(eig); SETERRQ(PETSC_ERR_LIB, "Error in LAPACK subroutine syev: info=%d", info); }
+  if (S != R) for (PetscInt i = l; i < k; i++) for (PetscInt j = l; j < k; j++) pR[i + (size_t)j * ld] = pS[j + (size_t)i * lds];   /* R = U' */
+  for (PetscInt i = l; i < k; i++) for (PetscInt j = l; j < k; j++) pS[i + (size_t)j * lds] *= D[i - l];
+  for (PetscInt j = l; j < k; j++) for (PetscInt i = l; i < k; i++) pS[i + (size_t)j * lds] /= sqrt(eig[j - l]);
+  if (S != R) {
+    for (PetscInt i = l; i < k; i++) for (PetscInt j = l; j < k; j++) pR[i + (size_t)j * ld] *= sqrt(eig[i - l]);
+    for (PetscInt j = l; j < k; j++) for (PetscInt i = l; i < k; i++) pR[i + (size_t)j * ld] /= D[j - l];
+  }
+  free(eig);
+  return PETSC_SUCCESS;
+}
+
+/* BVOrthogonalize_Chol bvorthog.c:586-601 (svqb = PETSC_FALSE) and BVOrthogonalize_SVQB :660-675 */
+static PetscErrorCode BVOrthogonalize_Gram(BV V, Mat Rin, PetscBool svqb)
+{
+  Mat R, S;
+  PetscCall(BV_GetBufferMat(V, &R));
+  S = Rin ? Rin : R;                              /* use Rin as a workspace for S */
+  PetscErrorCode ierr = PETSC_SUCCESS;
+  if (V->l) ierr = BVOrthogonalize_BlockGS(V, R);
+  if (!ierr) ierr = BVDot(V, V, R);
+  if (!ierr) ierr = svqb ? BVMatSVQB_Private(V, R, S) : BVMatCholInv_Private(V, R, S);
+  if (!ierr) ierr = BVMultInPlace(V, S, V->l, V->k);
+  if (!ierr && Rin) ierr = BV_StoreCoeffsBlock(V, Rin, svqb ? PETSC_FALSE : PETSC_TRUE);
+  PetscCall(MatDestroy(&R));
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+/* BVOrthogonalize_GS bvorthog.c:504-540: column by column */
+static PetscErrorCode BVOrthogonalize_GS(BV V, Mat R)
+{
   PetscInt ldr = 0;
   PetscScalar *r = NULL;
-  if (R) {
-    PetscCheck(R->dense, PETSC_ERR_SUP, "Mat argument must be sequential dense");
-    PetscCheck(R->m == R->n, PETSC_ERR_ARG_SIZ, "Mat argument is not square, it has %d rows and %d columns", R->m, R->n);
-    PetscCheck(R->n >= V->k, PETSC_ERR_ARG_SIZ, "Mat size %d is smaller than the number of BV active columns %d", R->n, V->k);
-    ldr = R->lda; r = R->dense;
-  }
-  PetscCheck(V->nc == 0, PETSC_ERR_SUP, "Not implemented for BV with constraints, use BVOrthogonalizeColumn() instead");
+  if (R) { ldr = R->lda; r = R->dense; }
   const PetscInt lsave = V->l, ksave = V->k;
   for (PetscInt j = lsave; j < ksave; j++) {
     PetscReal norm;
@@ -774,6 +889,26 @@ PetscErrorCode BVOrthogonalize(BV V, Mat R)
     }
   }
   V->l = lsave; V->k = ksave;
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVOrthogonalize(BV V, Mat R)
+{
+  BVCheckSizes(V);
+  if (R) {
+    PetscCheck(R->dense, PETSC_ERR_SUP, "Mat argument must be sequential dense");
+    PetscCheck(R->m == R->n, PETSC_ERR_ARG_SIZ, "Mat argument is not square, it has %d rows and %d columns", R->m, R->n);
+    PetscCheck(R->n >= V->k, PETSC_ERR_ARG_SIZ, "Mat size %d is smaller than the number of BV active columns %d", R->n, V->k);
+  }
+  PetscCheck(V->nc == 0, PETSC_ERR_SUP, "Not implemented for BV with constraints, use BVOrthogonalizeColumn() instead");
+  switch (V->orthog_block) {
+  case BV_ORTHOG_BLOCK_GS: PetscCall(BVOrthogonalize_GS(V, R)); break;
+  case BV_ORTHOG_BLOCK_CHOL: PetscCall(BVOrthogonalize_Gram(V, R, PETSC_FALSE)); break;
+  case BV_ORTHOG_BLOCK_SVQB: PetscCall(BVOrthogonalize_Gram(V, R, PETSC_TRUE)); break;
+  case BV_ORTHOG_BLOCK_TSQR:
+  case BV_ORTHOG_BLOCK_TSQRCHOL:
+    SETERRQ(PETSC_ERR_SUP, "TSQR block orthogonalization (bvlapack.c:347-560: host Householder panels) is not available for device-resident BVs; use chol or svqb");
+  }
   V->state++;
   return PETSC_SUCCESS;
 }

@@ -134,6 +134,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 NORM_1, NORM_2, NORM_FROBENIUS, NORM_INFINITY = 0, 1, 2, 3
 BV_ORTHOG_CGS, BV_ORTHOG_MGS = 0, 1
 BV_ORTHOG_REFINE_IFNEEDED, BV_ORTHOG_REFINE_NEVER, BV_ORTHOG_REFINE_ALWAYS = 0, 1, 2
+BV_ORTHOG_BLOCK_GS, BV_ORTHOG_BLOCK_CHOL, BV_ORTHOG_BLOCK_TSQR, BV_ORTHOG_BLOCK_TSQRCHOL, BV_ORTHOG_BLOCK_SVQB = 0, 1, 2, 3, 4
 EPS_HEP, EPS_NHEP = 1, 3
 EPS_LARGEST_MAGNITUDE, EPS_SMALLEST_MAGNITUDE, EPS_LARGEST_REAL, EPS_SMALLEST_REAL = 1, 2, 3, 4
 EPS_LARGEST_IMAGINARY, EPS_SMALLEST_IMAGINARY, EPS_TARGET_MAGNITUDE, EPS_TARGET_REAL = 5, 6, 7, 8

@@ -173,6 +173,64 @@ def scenario_test4(make_bv, trans=False):
         o.destroy()
 
 
+def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
+    """bv/tests/test11.c:37-215 (output/test11_1.out, the `-resid` variants of :255): block orthogonalisation of the active
+    columns after orthogonalising the leading ones; every check of the reference program is `< 100*eps`.  Also compared
+    with the numpy restatement of the same method (bvorthog.c:586-675, bvlapack.c:136-345)."""
+    X = make_bv(n, k)
+    X0 = np.zeros((n, k))
+    for j in range(k):
+        for i in range(n // 2 + 1):
+            if i + j < n:
+                X0[i + j, j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
+    X.from_numpy(X0)
+    Y = SL.BV()
+    S.BVDuplicate(X.h, Y.ref)
+    S.BVCopy(X.h, Y.h)
+    S.BVSetOrthogonalization(Y.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, block)
+    M = SL.Mat.seqdense(np.zeros((k, k)))
+    R = SL.Mat.seqdense(np.zeros((k, k))) if resid else None
+    Rh = R.h if resid else None
+    name = {SL.BV_ORTHOG_BLOCK_GS: None, SL.BV_ORTHOG_BLOCK_CHOL: "chol", SL.BV_ORTHOG_BLOCK_SVQB: "svqb"}[block]
+    Yo = O.BV(n, k)
+    Yo.V[:, :] = X0
+
+    def offdiag(lo, hi):
+        S.BVDot(Y.h, Y.h, M.h)
+        A = M.dense_array()[lo:hi, lo:hi]
+        return np.linalg.norm(A - np.eye(hi - lo))
+
+    if l > 0:
+        Y.set_active(0, l)
+        S.BVOrthogonalize(Y.h, Rh)
+        assert offdiag(0, l) < 100 * EPS                      # Level of orthogonality of Q1
+        if resid:
+            assert np.linalg.norm(X0[:, :l] - Y.to_numpy()[:, :l] @ R.dense_array()[:l, :l]) < 100 * EPS
+        if name:
+            Yo.set_active(0, l)
+            Yo.orthogonalize_block(name)
+    Y.set_active(l, k)
+    S.BVOrthogonalize(Y.h, Rh)
+    if l > 0:
+        assert offdiag(l, k) < 100 * EPS                      # Level of orthogonality of Q2
+    Y.set_active(0, k)
+    assert offdiag(0, k) < 100 * EPS                          # Level of orthogonality of Q
+    Q = Y.to_numpy()
+    if resid:
+        Rm = R.dense_array()
+        assert np.linalg.norm(X0 - Q @ Rm) < 100 * EPS        # Residual ||X-Q*R||
+        if block != SL.BV_ORTHOG_BLOCK_SVQB:
+            assert np.allclose(np.tril(Rm, -1), 0.0)
+    if name:
+        Yo.set_active(l, k)
+        Ro = Yo.orthogonalize_block(name, want_R=True)
+        assert np.linalg.norm(Q - Yo.V[:, :k]) < 1e-12
+        if resid:
+            assert np.linalg.norm(R.dense_array()[:, l:k] - Ro[:, l:k]) < 1e-12
+    for o in (X, Y, M) + ((R,) if resid else ()):
+        o.destroy()
+
+
 def scenario_test13(make_bv):
     n, k = 10, 5
     X = make_bv(n, k)

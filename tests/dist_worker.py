@@ -126,6 +126,32 @@ def main():
         norms_o = [Xo.orthonormalize_column(j)[0] for j in range(k)]
         res.update(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), dq=float(np.abs(Q - Xo.V).max()),
                    dn=float(np.abs(np.array(norms) - np.array(norms_o)).max()))
+    elif case in ("bvchol", "bvsvqb"):
+        # BVOrthogonalize CHOL / SVQB (bvorthog.c:586-675) on a split basis with 2 leading columns: the Gram matrix is
+        # globally reduced by BVDot, the k x k factorisation is replicated, BVMult/BVMultInPlace are local
+        n, k, l = 57, 7, 2
+        rs, re = CP.split_rows(n, size)[rank]
+        rng = np.random.default_rng(7)
+        Aglob = rng.standard_normal((n, k))
+        name = case[2:]
+        block = SL.BV_ORTHOG_BLOCK_CHOL if name == "chol" else SL.BV_ORTHOG_BLOCK_SVQB
+        X = CP.bv_cpu(re - rs, k, N=n, rstart=rs)
+        X.from_numpy(Aglob[rs:re])
+        S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, block)
+        R = SL.Mat.seqdense(np.zeros((k, k)))
+        X.set_active(0, l)
+        S.BVOrthogonalize(X.h, R.h)
+        X.set_active(l, k)
+        S.BVOrthogonalize(X.h, R.h)
+        Q = np.concatenate(gather_obj(X.to_numpy()), axis=0)
+        Xo = O.BV(n, k)
+        Xo.V[:] = Aglob
+        Xo.set_active(0, l)
+        Xo.orthogonalize_block(name)
+        Xo.set_active(l, k)
+        Xo.orthogonalize_block(name)
+        res.update(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), dq=float(np.abs(Q - Xo.V).max()),
+                   resid=float(np.linalg.norm(Aglob - Q @ R.dense_array())))
     elif case == "hep":
         nx = 24
         A = O.laplacian_2d(nx)

@@ -46,6 +46,21 @@ def test_bv_test4_trans():
     SC.scenario_test4(make_bv, trans=True)
 
 
+@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB])
+@pytest.mark.parametrize("resid", [False, True])
+def test_bv_test11_block_orthogonalize(block, resid):
+    SC.scenario_test11(make_bv, block, resid=resid)
+
+
+def test_bv_block_orthogonalize_tsqr_unsupported():
+    X = make_bv(20, 4)
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_TSQR)
+    X.from_numpy(np.random.default_rng(0).standard_normal((20, 4)))
+    with pytest.raises(SL.SlepcError):
+        S.BVOrthogonalize(X.h, None)
+    X.destroy()
+
+
 def test_bv_test13():
     SC.scenario_test13(make_bv)
 

@@ -46,6 +46,13 @@ def test_bv_test4(trans):
     SC.scenario_test4(make_bv, trans=trans)
 
 
+@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB])
+@pytest.mark.parametrize("shape", [(20, 2, 8), (4099, 3, 17), (180, 0, 7)])
+def test_bv_test11_block_orthogonalize(block, shape):
+    n, l, k = shape
+    SC.scenario_test11(make_bv, block, n=n, l=l, k=k, resid=True)
+
+
 def test_bv_test13():
     SC.scenario_test13(make_bv)
 
