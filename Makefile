@@ -21,7 +21,9 @@ OSRC      := $(wildcard oracle/*.c)
 ifneq ($(strip $(OSRC)),)
 ORACLE_LIB := oracle/_build/liboraclecpu.so
 endif
-all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so $(ORACLE_LIB)
+EXSRC     := $(wildcard examples/*.c)
+EXBIN     := $(patsubst examples/%.c,examples/bin/%,$(EXSRC))
+all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so $(ORACLE_LIB) $(EXBIN)
 
 $(LIBDIR)/libb200krylov.so: $(KSRC) $(KHDR)
 	@mkdir -p $(LIBDIR)
@@ -36,9 +38,16 @@ oracle/_build/liboraclecpu.so: $(OSRC) $(HHDR) $(LIBDIR)/libb2kslepc.so
 	$(CC) $(CFLAGS) -O3 -march=x86-64-v3 -fopenmp -B/usr/lib/gcc/x86_64-linux-gnu/13/ -shared -o $@ $(OSRC) -L$(LIBDIR) -lb2kslepc \
 	    -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' $(OPENBLAS) -Wl,-rpath,$(OPENBLAS_DIR) -lm
 
+# the reference's tutorial programs against include/b2kslepc.h (run on the GPU only: B2KInitialize fails without one)
+examples/bin/%: examples/%.c examples/exutil.h $(HHDR) $(LIBDIR)/libb2kslepc.so
+	@mkdir -p examples/bin
+	$(CC) $(CFLAGS) -Iexamples -o $@ $< -L$(LIBDIR) -lb2kslepc -lb200krylov -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -lm
+
+examples: $(EXBIN)
+
 kernels: $(LIBDIR)/libb200krylov.so
 
 clean:
-	rm -f $(LIBDIR)/*.so oracle/_build/*.so
+	rm -f $(LIBDIR)/*.so oracle/_build/*.so examples/bin/*
 
-.PHONY: all clean kernels
+.PHONY: all clean kernels examples
