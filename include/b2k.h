@@ -86,6 +86,8 @@ int  b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, dou
 int  b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out);
 /* out[0] = max_j sum_i |X(i,j)| (local part of NORM_1), out[1] = max |X(i,j)| … used by BVNorm   */
 int  b2k_colabssum(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out_k);
+/* out[0] = max over rows of sum_c |X(r,c)|: NORM_INFINITY of the block (BVNorm_LAPACK_Private bvlapack.c:37-83, lange 'I') */
+int  b2k_rowabssum_max(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out_dev);
 /* X = alpha*X on an n x k block               — BVScale_BLAS_CUDA   bvcuda.cu:269-285 (scal)      */
 int  b2k_scale(b2k_ctx ctx, double *X, int64_t ld, int64_t n, int k, double alpha);
 /* Y = X on an n x k block                     — BVCopy_Svec_CUDA    sveccuda.cu:305-330           */

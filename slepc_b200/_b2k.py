@@ -46,6 +46,7 @@ SIGNATURES = {
     "b2k_multvec": [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_dbl, c_vp, c_vp],
     "b2k_sumsq": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
     "b2k_colabssum": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
+    "b2k_rowabssum_max": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp],
     "b2k_scale": [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl],
     "b2k_copy": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int],
     "b2k_axpby": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_dbl, c_dbl],

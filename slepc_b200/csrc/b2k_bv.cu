@@ -341,6 +341,46 @@ __global__ void __launch_bounds__(256) k_colabssum(const double *__restrict__ X,
     part[(int64_t)blockIdx.x * pstride + blockIdx.y] = t;
   }
 }
+/* infinity norm of an n x k block = max over rows of sum_c |X(r,c)| (LAPACKlange 'I' of bvlapack.c:37-83): per-CTA maxima */
+__global__ void __launch_bounds__(256) k_rowabssum_max(const double *__restrict__ X, int64_t ld, int64_t n, int k, double *__restrict__ part)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double m = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    double s = 0.0;
+    for (int c = 0; c < k; c++) s += fabs(X[r + (int64_t)c * ld]);
+    m = fmax(m, s);
+  }
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t = fmax(t, red[i]);
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_max_partials(const double *__restrict__ part, int nblk, double *__restrict__ out)
+{
+  double m = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 256) m = fmax(m, part[b]);
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t = fmax(t, red[i]);
+    out[0] = t;
+  }
+}
 /* out[0] = sum_c in[c] (single thread; tiny) */
 __global__ void k_sum_small(const double *__restrict__ in, int ncols, double *__restrict__ out)
 {
@@ -612,6 +652,20 @@ extern "C" int b2k_colabssum(b2k_ctx ctx, const double *X, int64_t ld, int64_t n
   k_colabssum<<<grid, 256, 0, ctx->stream>>>(X, ld, n, ctx->partials, k);
   CKLAUNCH(ctx);
   { const int rc_ = b2k_launch_reduce_partials(ctx, gx, k, k, out_k); if (rc_) return rc_; }
+  return B2K_OK;
+}
+
+/* out[0] = max_r sum_c |X(r,c)| over this GPU's rows (the caller combines ranks with a MAX all-reduce) */
+extern "C" int b2k_rowabssum_max(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out)
+{
+  ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
+  if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream)); return B2K_OK; }
+  int gx = grid_rows(ctx, n, 4);
+  if (gx > B2K_MAX_PART_BLOCKS) gx = B2K_MAX_PART_BLOCKS;
+  k_rowabssum_max<<<gx, 256, 0, ctx->stream>>>(X, ld, n, k, ctx->partials);
+  CKLAUNCH(ctx);
+  k_max_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, gx, out);
+  CKLAUNCH(ctx);
   return B2K_OK;
 }
 

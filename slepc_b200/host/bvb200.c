@@ -227,22 +227,25 @@ static PetscErrorCode BVNorm_B200_Private(BV bv, PetscInt j, NormType type, Pets
   const PetscInt k = (j < 0) ? bv->k - bv->l : 1;
   double *hp;
   if (k <= 0) { *val = 0.0; return PETSC_SUCCESS; }
-  PetscBool fused;
-  PetscCall(BVScope_B200(bv, reduce, &fused));
+  PetscBool fused = PETSC_FALSE;
   if (type == NORM_2 || type == NORM_FROBENIUS) {
+    PetscCall(BVScope_B200(bv, reduce, &fused));
     B2KCall(b2k_sumsq(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
     PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, reduce, fused, &hp));
     *val = sqrt(hp[0]);
   } else if (type == NORM_1) {
+    PetscCall(BVScope_B200(bv, reduce, &fused));
     B2KCall(b2k_colabssum(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
     PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), k, reduce, fused, &hp));
     PetscReal mx = 0.0;
     for (PetscInt i = 0; i < k; i++) mx = PetscMax(mx, hp[i]);
     *val = mx;
-  } else {
-    if (fused) PetscCall(B2KCommReduceScope(bv->comm, PETSC_FALSE, NULL));
-    SETERRQ(PETSC_ERR_SUP, "NORM_INFINITY is not implemented for BV type b200 (not on the Krylov path)");
-  }
+  } else if (type == NORM_INFINITY) {             /* rows are split over the ranks: local max row sum, then a MAX reduction */
+    B2KCall(b2k_rowabssum_max(ctx, X, bv->ld, bv->n, k, SLOT(d, 3)));
+    if (reduce) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 3), 1, 1, B2K_MEM_DEVICE));
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_FALSE, PETSC_FALSE, &hp));
+    *val = hp[0];
+  } else SETERRQ(PETSC_ERR_ARG_WRONG, "unknown norm type %d", (int)type);
   return PETSC_SUCCESS;
 }
 static PetscErrorCode BVNorm_B200(BV bv, PetscInt j, NormType type, PetscReal *val) { return BVNorm_B200_Private(bv, j, type, val, PETSC_TRUE); }

@@ -231,6 +231,24 @@ def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
         o.destroy()
 
 
+def scenario_norms(make_bv, n=1237, k=6, l=1):
+    """BVNorm / BVNormColumn with every NormType of bvglobal.c:455-560 (2, Frobenius, 1, infinity) on the active block
+    and on single columns, against numpy"""
+    X = make_bv(n, k)
+    A = np.random.default_rng(3).standard_normal((n, k))
+    X.from_numpy(A)
+    X.set_active(l, k)
+    B = A[:, l:k]
+    assert np.isclose(norm(X, SL.NORM_FROBENIUS), np.linalg.norm(B), rtol=1e-13)
+    assert np.isclose(norm(X, SL.NORM_1), np.abs(B).sum(0).max(), rtol=1e-13)
+    assert np.isclose(norm(X, SL.NORM_INFINITY), np.abs(B).sum(1).max(), rtol=1e-13)
+    for j in (0, k - 1):
+        assert np.isclose(norm_column(X, j, SL.NORM_2), np.linalg.norm(A[:, j]), rtol=1e-13)
+        assert np.isclose(norm_column(X, j, SL.NORM_1), np.abs(A[:, j]).sum(), rtol=1e-13)
+        assert norm_column(X, j, SL.NORM_INFINITY) == np.abs(A[:, j]).max()
+    X.destroy()
+
+
 def scenario_test13(make_bv):
     n, k = 10, 5
     X = make_bv(n, k)

@@ -61,6 +61,10 @@ def test_bv_block_orthogonalize_tsqr_unsupported():
     X.destroy()
 
 
+def test_bv_norm_types():
+    SC.scenario_norms(make_bv)
+
+
 def test_bv_test13():
     SC.scenario_test13(make_bv)
 

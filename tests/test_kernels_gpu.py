@@ -174,6 +174,11 @@ def test_level1(ctx):
     outk = ctx.empty(k)
     check(ctx.lib.b2k_colabssum(ctx.h, pX, ld, n, k, outk.ptr))
     assert np.allclose(outk.to_host(), np.abs(H[:n]).sum(0), rtol=1e-13)
+    omax = ctx.empty(1)
+    check(ctx.lib.b2k_rowabssum_max(ctx.h, pX, ld, n, k, omax.ptr))                      # NORM_INFINITY of the block
+    assert np.isclose(omax.to_host()[0], np.abs(H[:n]).sum(1).max(), rtol=1e-14)
+    check(ctx.lib.b2k_rowabssum_max(ctx.h, pX + 8 * 2 * ld, ld, 77, 1, omax.ptr))        # one column, short
+    assert omax.to_host()[0] == np.abs(H[:77, 2]).max()
     check(ctx.lib.b2k_scale(ctx.h, pX, ld, n, k, -2.5))
     G = dX.to_host((ld, k))
     assert np.array_equal(G[:n], -2.5 * H[:n]) and np.array_equal(G[n:], H[n:])

@@ -53,6 +53,10 @@ def test_bv_test11_block_orthogonalize(block, shape):
     SC.scenario_test11(make_bv, block, n=n, l=l, k=k, resid=True)
 
 
+def test_bv_norm_types():
+    SC.scenario_norms(make_bv)
+
+
 def test_bv_test13():
     SC.scenario_test13(make_bv)
 
