@@ -175,14 +175,23 @@ def scenario_test4(make_bv, trans=False):
 
 def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
     """bv/tests/test11.c:37-215 (output/test11_1.out, the `-resid` variants of :255): block orthogonalisation of the active
-    columns after orthogonalising the leading ones; every check of the reference program is `< 100*eps`.  Also compared
-    with the numpy restatement of the same method (bvorthog.c:586-675, bvlapack.c:136-345)."""
+    columns after orthogonalising the leading ones.  At the reference's sizes (n=20, l=2, k=8 and n=180, l=0, k=7 with GS)
+    every check is the reference's `< 100*eps`; other shapes scale the bound with the size and the conditioning of the
+    test matrix (Gram-matrix methods lose orthogonality like eps*cond^2).  Also compared with the numpy restatement of
+    the same method (bvorthog.c:586-675, bvlapack.c:136-345)."""
     X = make_bv(n, k)
     X0 = np.zeros((n, k))
     for j in range(k):
         for i in range(n // 2 + 1):
             if i + j < n:
                 X0[i + j, j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
+    gram = block != SL.BV_ORTHOG_BLOCK_GS
+    if (n, l, k) == (20, 2, 8) or ((n, l, k) == (180, 0, 7) and not gram):
+        tol_orth = tol_res = 100 * EPS
+    else:
+        c = np.linalg.cond(X0)
+        tol_orth = 100 * EPS * k * (c * c if gram else c)
+        tol_res = 100 * EPS * np.linalg.norm(X0)
     X.from_numpy(X0)
     Y = SL.BV()
     S.BVDuplicate(X.h, Y.ref)
@@ -203,30 +212,39 @@ def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
     if l > 0:
         Y.set_active(0, l)
         S.BVOrthogonalize(Y.h, Rh)
-        assert offdiag(0, l) < 100 * EPS                      # Level of orthogonality of Q1
+        assert offdiag(0, l) < tol_orth                       # Level of orthogonality of Q1
         if resid:
-            assert np.linalg.norm(X0[:, :l] - Y.to_numpy()[:, :l] @ R.dense_array()[:l, :l]) < 100 * EPS
+            assert np.linalg.norm(X0[:, :l] - Y.to_numpy()[:, :l] @ R.dense_array()[:l, :l]) < tol_res
         if name:
             Yo.set_active(0, l)
             Yo.orthogonalize_block(name)
     Y.set_active(l, k)
     S.BVOrthogonalize(Y.h, Rh)
     if l > 0:
-        assert offdiag(l, k) < 100 * EPS                      # Level of orthogonality of Q2
+        assert offdiag(l, k) < tol_orth                       # Level of orthogonality of Q2
     Y.set_active(0, k)
-    assert offdiag(0, k) < 100 * EPS                          # Level of orthogonality of Q
+    assert offdiag(0, k) < tol_orth                           # Level of orthogonality of Q
     Q = Y.to_numpy()
     if resid:
         Rm = R.dense_array()
-        assert np.linalg.norm(X0 - Q @ Rm) < 100 * EPS        # Residual ||X-Q*R||
+        assert np.linalg.norm(X0 - Q @ Rm) < tol_res          # Residual ||X-Q*R||
         if block != SL.BV_ORTHOG_BLOCK_SVQB:
             assert np.allclose(np.tril(Rm, -1), 0.0)
     if name:
         Yo.set_active(l, k)
         Ro = Yo.orthogonalize_block(name, want_R=True)
-        assert np.linalg.norm(Q - Yo.V[:, :k]) < 1e-12
-        if resid:
-            assert np.linalg.norm(R.dense_array()[:, l:k] - Ro[:, l:k]) < 1e-12
+        Qo = Yo.V[:, :k]
+        if name == "chol":                                    # unique factorisation: column for column
+            assert np.linalg.norm(Q - Qo) < 1e3 * tol_orth
+            if resid:
+                assert np.linalg.norm(R.dense_array()[:, l:k] - Ro[:, l:k]) < 1e3 * tol_orth * np.linalg.norm(Ro)
+        else:
+            # SVQB post-multiplies by eigenvectors of the scaled Gram matrix: each column is defined up to its sign and is
+            # as sensitive as the eigenvector (eps / spectral gap), so compare the spans of the leading and of the active block
+            for a, b in ((0, l), (l, k)):
+                if b > a:
+                    P, Po = Q[:, a:b] @ Q[:, a:b].T, Qo[:, a:b] @ Qo[:, a:b].T
+                    assert np.linalg.norm(P @ X0 - Po @ X0) < 1e3 * tol_orth * np.linalg.norm(X0)
     for o in (X, Y, M) + ((R,) if resid else ()):
         o.destroy()
 
