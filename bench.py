@@ -106,6 +106,12 @@ def run_reference(args, wl):
     from slepc_b200 import slepc as SL
     from slepc_b200.slepc import S
     CP.load()
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    if CP.threads() < avail:                       # torchrun sets OMP_NUM_THREADS=1 for every rank: use all host cores anyway
+        CP.set_threads(avail)
     cores = CP.threads()
     K = max(1, min(args.steps, 4))
     W = max(0, min(args.warmup, 1))

@@ -44,6 +44,11 @@ def threads():
     return load().OracleCPUGetMaxThreads()
 
 
+def set_threads(n):
+    """OpenMP threads of the CPU plug-in (torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU baseline must not inherit it)"""
+    load().OracleCPUSetThreads(int(n))
+
+
 def stream_triad_gbs(n=1 << 26, reps=5):
     return load().OracleCPUStreamTriad(n, reps)
 
