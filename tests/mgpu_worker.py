@@ -55,7 +55,8 @@ def main():
         Q = np.concatenate(gather(X.to_numpy()), axis=0)
         Qr, R = np.linalg.qr(Ag)
         res.update(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), span=float(np.linalg.norm(Q - Qr @ (Qr.T @ Q))),
-                   dn=float(np.abs(np.array(norms) - np.abs(np.diag(R))).max() / np.abs(np.diag(R)).max()))
+                   dn=float(np.abs(np.array(norms) - np.abs(np.diag(R))).max() / np.abs(np.diag(R)).max()),
+                   norms=norms, q_checksum=[float(x) for x in Q[::997].ravel()])
     elif case == "lap":
         nx, ny = 96, 64                                      # nx (slowest) is split over the ranks
         M = SL.Mat.laplacian(2, nx, ny)
@@ -112,6 +113,7 @@ def main():
                    errs_impl=[svd2.error(i) for i in range(svd2.nconv)])
     else:
         raise SystemExit(f"unknown case {case}")
+    res["p2p"] = bool(D.P2P)
     if rank == 0:
         json.dump(res, open(outpath, "w"))
     D.finalize()

@@ -22,14 +22,15 @@ def ngpus():
         return 0
 
 
-def run_case(case, world, tmp_path):
+def run_case(case, world, tmp_path, extra_env=None, tag=""):
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    out = tmp_path / f"{case}_{world}.json"
+    out = tmp_path / f"{case}_{world}{tag}.json"
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mgpu_worker.py"), case, str(out)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
@@ -59,6 +60,20 @@ def test_eps_laplacian_device_generator(world, tmp_path):
     for x in r["lam"][:6]:
         assert np.min(np.abs(an - x)) < 1e-10 * abs(x)
     assert max(r["errs"][:6]) < 5e-8
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_reductions_match_nccl(world, tmp_path):
+    """k_reduce_partials_xg (sum over the GPUs inside the reduction kernel, NVLink mailboxes) against k_reduce_partials +
+    ncclAllReduce on the same data: both are fixed-order sums, so norms and vectors agree to rounding of a k-term sum"""
+    a = run_case("bv", world, tmp_path, {"B2K_COMM_P2P": "1"}, "_p2p")
+    b = run_case("bv", world, tmp_path, {"B2K_COMM_P2P": "0"}, "_nccl")
+    assert not b["p2p"]
+    if not a["p2p"]:
+        pytest.skip("CUDA IPC rendezvous not available on this box: the NCCL path ran twice")
+    assert np.allclose(a["norms"], b["norms"], rtol=1e-14, atol=0)
+    assert np.allclose(a["q_checksum"], b["q_checksum"], rtol=0, atol=1e-14)
+    assert a["orth"] < 1e-13 and b["orth"] < 1e-13
 
 
 def test_eps_markov_general_halo(tmp_path):
