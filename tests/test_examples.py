@@ -1,6 +1,6 @@
 """The reference's tutorial / test programs rewritten against include/b2kslepc.h (examples/*.c): what a user of the
 reference would compile after switching.  Each program's output is compared LINE BY LINE with the reference's own output
-file (src/eps/tutorials/output/ex2_1.out, ex5_1.out, src/svd/tests/output/test3_1.out — copied below as golden text).
+file (src/eps/tutorials/output/ex2_1.out, ex3_1.out, ex5_1.out, src/svd/tests/output/test3_1.out — copied below as golden text).
   * not gpu: the programs are compiled against the CPU oracle plug-in through tests/ex_cpu_shim.h (host logic + format),
     and the product binaries are checked to FAIL LOUDLY without a GPU (no CPU fallback);
   * gpu: the product binaries (BV type b200, Mat type b200csr) run on cuda:0."""
@@ -22,6 +22,7 @@ EX2_OUT = """
      7.99630, 7.99074, 7.98519, 7.98150
 
 """
+EX3_OUT = EX2_OUT.replace("Eigenproblem,", "Eigenproblem (matrix-free version),")
 EX5_OUT = """
 Markov Model, N=120 (m=15)
 
@@ -42,6 +43,7 @@ Level of orthogonality below the tolerance
 """
 CASES = [
     ("ex2", ["-n", "72", "-eps_nev", "4", "-eps_ncv", "20", "-terse"], EX2_OUT),
+    ("ex3", ["-n", "72", "-eps_nev", "4", "-eps_ncv", "20", "-terse"], EX3_OUT),
     ("ex5", ["-m", "15", "-eps_nev", "4", "-eps_largest_real", "-terse"], EX5_OUT),
     ("svd_test3", ["-svd_nsv", "4"], TEST3_OUT),
     ("svd_test3", ["-svd_nsv", "4", "-svd_trlanczos_locking", "0"], TEST3_OUT),
@@ -53,7 +55,7 @@ IDS = [c[0] + "".join(a for a in c[1] if a.startswith("-") and a not in ("-terse
 
 
 def ensure_built():
-    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex5", "svd_test3")):
+    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex3", "ex5", "svd_test3")):
         subprocess.run(["make", "-C", ROOT, "all"], check=True, capture_output=True)
 
 
@@ -64,7 +66,7 @@ def cpu_bins(tmp_path_factory):
     out = tmp_path_factory.mktemp("ex_cpu")
     lib = os.path.join(ROOT, "slepc_b200", "lib")
     orc = os.path.join(ROOT, "oracle", "_build")
-    for name in ("ex2", "ex5", "svd_test3"):
+    for name in ("ex2", "ex3", "ex5", "svd_test3"):
         subprocess.run(["gcc", "-O1", "-std=gnu11", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "examples"),
                         "-include", os.path.join(ROOT, "tests", "ex_cpu_shim.h"), "-o", str(out / name), os.path.join(ROOT, "examples", name + ".c"),
                         "-L" + orc, "-loraclecpu", "-L" + lib, "-lb2kslepc", "-lb200krylov",
