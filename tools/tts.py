@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--maxits", type=int, default=0)
     ap.add_argument("--ncv", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--oneside", action="store_true", help="c5: one-sided thick-restart Lanczos (trlanczos.c:357-448)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     from slepc_b200 import _b2k, matgen
@@ -94,7 +95,10 @@ def main():
         del rp, ci, v
         solver = SL.SVD(M)                                         # A^T through MatMultTranspose (implicit) on > 1 rank
         S.SVDSetDimensions(solver.h, 10, args.ncv or 20, SL.PETSC_DETERMINE)
-        info = dict(matrix=f"random sparse {Mr}x{Nc}, 20 draws/row", rows=Mr, cols=Nc, nsv=10, ncv=args.ncv or 20)
+        if args.oneside:
+            S.SVDTRLanczosSetOneSide(solver.h, 1)
+        info = dict(matrix=f"random sparse {Mr}x{Nc}, 20 draws/row", rows=Mr, cols=Nc, nsv=10, ncv=args.ncv or 20,
+                    variant="one-sided" if args.oneside else "two-sided")
     is_svd = args.case == "c5"
     if is_svd:
         S.SVDSetTolerances(solver.h, args.tol, args.maxits or SL.PETSC_CURRENT)
