@@ -418,37 +418,38 @@ def test_eps_restart_cycles_api_matches_solve():
     assert np.allclose([a.eigenvalue(i)[0] for i in range(a.nconv)], [b.eigenvalue(i)[0] for i in range(b.nconv)], rtol=0, atol=0)
 
 
-# ---- BASELINE.json configs[1] at FULL size: size-independent properties ------------------------------------------
-def test_full_size_c2_properties():
-    """2-D Laplacian 4096 x 4096 (16 777 216 rows), ncv = 64 — too large for the oracle, so the path is checked through
-    properties that do not depend on the size:
-      * SpMV exactness on integer data: A*1 is the boundary indicator (4 - #neighbours), so 1^T A 1 = 4g and ||A 1||^2 = 4g + 8
-        hold bit for bit;
+# ---- BASELINE.json configs[1] and configs[2] at FULL size: size-independent properties ---------------------------
+@pytest.mark.parametrize("dim,g,nev,ncv,need_gb", [(2, 4096, 20, 64, 16), (3, 512, 10, 25, 70)], ids=["c2_4096x4096", "c3_512x512x512"])
+def test_full_size_properties(dim, g, nev, ncv, need_gb):
+    """2-D Laplacian 4096^2 (16 777 216 rows, ncv 64) and 3-D Laplacian 512^3 (134 217 728 rows, ncv 25) — too large for the
+    oracle, so the path is checked through properties that do not depend on the size:
+      * SpMV exactness on integer data: A*1 is the boundary indicator (2*dim - #neighbours): 1^T A 1 = number of boundary faces
+        (4g in 2-D, 6g^2 in 3-D) and ||A 1||^2 (4g + 8, resp. 6(g-2)^2 + 48(g-2) + 72) hold bit for bit;
       * SpMV linearity: A(2x + 3z) = 2 A x + 3 A z to rounding;
-      * after two Krylov-Schur restart cycles (64 + 32 Lanczos steps: SpMV, fused DGKS Gram-Schmidt, in-place restart) the
-        kept Ritz basis is orthonormal to 1e-12, its Rayleigh quotients v_i^T A v_i are sorted, lie below lambda_max(A) =
-        8 cos^2(pi / (2(g+1))) (Cauchy interlacing), the leading one above 7.9 (96 steps resolve the top of the spectrum that far)."""
+      * after two Krylov-Schur restart cycles (SpMV, fused DGKS Gram-Schmidt, in-place restart) the kept Ritz basis is
+        orthonormal to 1e-12, its Rayleigh quotients v_i^T A v_i are sorted, lie below lambda_max(A) = 4 dim cos^2(pi/(2(g+1)))
+        (Cauchy interlacing) and in the upper half of the spectrum."""
     from slepc_b200 import _b2k
-    g = 4096
     fr, to = ctypes.c_size_t(), ctypes.c_size_t()
     _b2k.check(_b2k.load().b2k_mem_info(S.B2KGetContext(), ctypes.byref(fr), ctypes.byref(to)))
-    if fr.value < 16 * 2 ** 30:
-        pytest.skip("needs 16 GB of free HBM")
-    N = g * g
-    M = SL.Mat.laplacian(2, g, g)
+    if fr.value < need_gb * 2 ** 30:
+        pytest.skip(f"needs {need_gb} GB of free HBM")
+    N = g ** dim
+    M = SL.Mat.laplacian(dim, g, g, g if dim == 3 else 1)
     x, y = M.create_vecs()
     z, t = M.create_vecs()
     d = c_dbl()
     S.VecSet(x.h, 1.0)
     S.MatMult(M.h, x.h, y.h)
     S.VecDot(y.h, x.h, ctypes.byref(d))
-    assert d.value == 4.0 * g
+    assert d.value == (4.0 * g if dim == 2 else 6.0 * g * g)
     S.VecDot(y.h, y.h, ctypes.byref(d))
-    assert d.value == 4.0 * g + 8.0
+    assert d.value == (4.0 * g + 8.0 if dim == 2 else 6.0 * (g - 2) ** 2 + 48.0 * (g - 2) + 72.0)
     # linearity with a pseudo-random z (deterministic hash fill)
     bz = make_bv(N, 2)
     S.BVSetRandomColumn(bz.h, 0)
     SC.with_column(bz, 0, lambda v: S.VecCopy(v, z.h))
+    bz.destroy()
     S.MatMult(M.h, z.h, t.h)                         # t = A z
     S.VecScale(y.h, 2.0)                             # y = 2 A 1
     S.VecAXPY(y.h, 3.0, t.h)                         # y = 2 A 1 + 3 A z
@@ -460,19 +461,18 @@ def test_full_size_c2_properties():
     ny = d.value
     S.VecNorm(t.h, SL.NORM_2, ctypes.byref(d))
     assert d.value < 1e-14 * ny
-    bz.destroy()
     # two restart cycles of the eigensolver
     eps = SL.EPS(M, hermitian=True)
-    S.EPSSetDimensions(eps.h, 20, 64, SL.PETSC_DETERMINE)
+    S.EPSSetDimensions(eps.h, nev, ncv, SL.PETSC_DETERMINE)
     S.EPSSetTolerances(eps.h, 1e-8, 1000000)
     assert eps.cycles(2) == 2
     bv = eps.bv()
-    kk = 16                                          # the restart keeps (64 - nconv)/2 = 32 Ritz vectors: look at the leading 16
+    kk = ncv // 4                                    # the restart keeps (ncv - nconv)/2 Ritz vectors: look at the leading half of them
     bv.set_active(0, kk)
     G = SL.Mat.seqdense(np.zeros((kk, kk)))
     S.BVDot(bv.h, bv.h, G.h)
     assert np.linalg.norm(G.dense_array() - np.eye(kk)) < 1e-12
-    lam_max = 8.0 * np.cos(np.pi / (2.0 * (g + 1))) ** 2
+    lam_max = 4.0 * dim * np.cos(np.pi / (2.0 * (g + 1))) ** 2
     theta = []
     for j in range(kk):
         def rq(v):
@@ -480,7 +480,7 @@ def test_full_size_c2_properties():
             S.VecDot(t.h, v, ctypes.byref(d))
             return d.value
         theta.append(SC.with_column(bv, j, rq))
-    assert theta[0] > 7.9 and all(4.0 < th < lam_max for th in theta)
+    assert theta[0] > 0.97 * lam_max and all(2.0 * dim < th < lam_max for th in theta)
     assert all(theta[i] >= theta[i + 1] - 1e-9 for i in range(kk - 1))
     for o in (G, eps, x, y, z, t, M):
         o.destroy()
