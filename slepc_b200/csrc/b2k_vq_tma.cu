@@ -52,22 +52,24 @@ __device__ __forceinline__ void vt_dmma(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-/* MT = m-tiles (8 rows each) per warp, NS = 8-column slabs per warp.  The 8 consumer warps tile the 128 x nout output as
+/* KB = columns of a TMA box (= of a shared-memory stage), STAGES = depth of the ring.  <.,.,64,3> is the general shape;
+   <.,.,32,6> (opt-in, B2K_VQ_NARROW=1) halves the box for kin <= 32 so that twice as many tiles are in flight.
+   MT = m-tiles (8 rows each) per warp, NS = 8-column slabs per warp.  The 8 consumer warps tile the 128 x nout output as
    (16/MT row groups) x (MT/2 column groups): <8,1> nout <= 32, <4,3> nout <= 48, <8,2> nout <= 64 — the shape that wastes
    the fewest DMMAs on padding columns. */
-template <int MT, int NS>
+template <int MT, int NS, int KB, int STAGES>
 __global__ void __launch_bounds__(VT_THREADS, 1)
 k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int64_t n, int kin, int nout, const double *__restrict__ Q,
          int ldq, int qtrans, double alpha, double beta)
 {
   extern __shared__ __align__(1024) unsigned char vt_raw[];
   unsigned long long *full = reinterpret_cast<unsigned long long *>(vt_raw);
-  unsigned long long *empty = full + VT_STAGES;
+  unsigned long long *empty = full + STAGES;
   double *stages = reinterpret_cast<double *>(vt_raw + 1024);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (n + VT_ROWS - 1) / VT_ROWS;
   if (tid == 0) {
-    for (int s = 0; s < VT_STAGES; s++) {
+    for (int s = 0; s < STAGES; s++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vt_smem_u32(&full[s])), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vt_smem_u32(&empty[s])), "r"(8));
     }
@@ -75,20 +77,20 @@ k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int
   }
   __syncthreads();
 
-  /* producer duty (thread 0): tile `it` of this CTA goes to stage it % VT_STAGES */
+  /* producer duty (thread 0): tile `it` of this CTA goes to stage it % STAGES */
   const int64_t nlocal = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   auto issue = [&](int64_t it) {
-    const int st = (int)(it % VT_STAGES);
+    const int st = (int)(it % STAGES);
     const uint32_t bar = vt_smem_u32(&full[st]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(VT_KB * VT_SROWS * sizeof(double))) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(KB * VT_SROWS * sizeof(double))) : "memory");
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     vt_smem_u32(stages + (size_t)st * VT_KB * VT_SROWS)),
+                     vt_smem_u32(stages + (size_t)st * KB * VT_SROWS)),
                  "l"(reinterpret_cast<uint64_t>(&tmIn)), "r"((int)((blockIdx.x + it * gridDim.x) * VT_ROWS)), "r"(0), "r"(bar)
                  : "memory");
   };
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmIn)) : "memory");
-    for (int64_t it = 0; it < VT_STAGES && it < nlocal; it++) issue(it);
+    for (int64_t it = 0; it < STAGES && it < nlocal; it++) issue(it);
   }
 
   /* consumers: warp = (row group rh of 8*MT rows, column group cg of NS slabs); fragment coordinates of m8n8k4: */
@@ -96,9 +98,9 @@ k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int
   const int rh = warp / CG, cg = warp % CG;
   const int fr = lane >> 2, fk = lane & 3;        /* A: row fr, k fk;  B: k fk, col fr;  C: row fr, cols 2*fk, 2*fk+1 */
   const int ksteps = (kin + 3) >> 2;
-  double bq[16][NS];
+  double bq[KB / 4][NS];
 #pragma unroll
-  for (int ks = 0; ks < 16; ks++) {
+  for (int ks = 0; ks < KB / 4; ks++) {
 #pragma unroll
     for (int sl = 0; sl < NS; sl++) {
       const int k = 4 * ks + fk, c = (cg * NS + sl) * 8 + fr;
@@ -112,7 +114,7 @@ k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int
   for (int64_t it = 0; it < nlocal; it++) {
     const int64_t t = blockIdx.x + it * gridDim.x;
     vt_wait(vt_smem_u32(&full[s]), ph);
-    const double *tile = stages + (size_t)s * VT_KB * VT_SROWS;
+    const double *tile = stages + (size_t)s * KB * VT_SROWS;
     const int64_t rbase = t * VT_ROWS + rh * WROWS;
     /* all MT m-tiles of the warp's rows at once: MT*NS independent accumulator chains per warp keep the FP64 tensor pipe
        busy (one chain is bound by the DMMA latency).  Row mapping: m-tile (mp, parity) holds rows 16*mp + 2*fr + parity, so
@@ -136,7 +138,7 @@ k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int
         }
       }
 #pragma unroll
-      for (int ks = 0; ks < 16; ks++) {
+      for (int ks = 0; ks < KB / 4; ks++) {
         if (ks < ksteps) {
           double2 a[MT / 2];
 #pragma unroll
@@ -169,13 +171,13 @@ k_vq_tma(const __grid_constant__ CUtensorMap tmIn, double *Out, int64_t ldo, int
         }
       }
     }
-    /* refill this stage with the tile VT_STAGES ahead once all 8 warps have released it (they are at most one tile
+    /* refill this stage with the tile STAGES ahead once all 8 warps have released it (they are at most one tile
        behind; the tiles they need next were requested earlier, so this wait cannot deadlock) */
-    if (tid == 0 && it + VT_STAGES < nlocal) {
+    if (tid == 0 && it + STAGES < nlocal) {
       vt_wait(vt_smem_u32(&empty[s]), ph);
-      issue(it + VT_STAGES);
+      issue(it + STAGES);
     }
-    if (++s == VT_STAGES) { s = 0; ph ^= 1; }
+    if (++s == STAGES) { s = 0; ph ^= 1; }
   }
 }
 
@@ -198,23 +200,33 @@ int b2k_vq_tma_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, i
   if (kin < 1 || kin > 64 || nout < 1 || nout > 64 || n < 32 * VT_ROWS || n >= 2147483647LL - VT_ROWS) return -1;
   if (!b2k_is_aligned16(In) || !b2k_is_aligned16(Out) || (ldi & 1) || (ldo & 1)) return -1;
   /* in place is safe only when Out's rows are In's rows: same leading dimension, Out a column of In's block */
+  static int narrow = -1;             /* env B2K_VQ_NARROW=1: 32-column boxes, 6 stages, <4,1> tiling for kin <= 32 (not yet the default) */
+  if (narrow < 0) { const char *e = getenv("B2K_VQ_NARROW"); narrow = (e && e[0] == '1') ? 1 : 0; }
+  const bool use_narrow = narrow && kin <= 32 && nout <= 32;
+  const int kb = use_narrow ? 32 : VT_KB, nst = use_narrow ? 6 : VT_STAGES;
   CUtensorMap mIn;
-  if (b2k_tm_make_map(&mIn, In, n, kin, ldi, VT_KB, VT_SROWS)) return -1;
-  const size_t shm = 1024 + (size_t)VT_STAGES * VT_KB * VT_SROWS * sizeof(double);
+  if (b2k_tm_make_map(&mIn, In, n, kin, ldi, kb, VT_SROWS)) return -1;
+  const size_t shm = 1024 + (size_t)nst * kb * VT_SROWS * sizeof(double);
   const int64_t ntiles = (n + VT_ROWS - 1) / VT_ROWS;
   int grid = ctx->sm_count;
   if ((int64_t)grid > ntiles) grid = (int)ntiles;
   static int configured = 0;
   if (!configured) {
-    CK(cudaFuncSetAttribute(k_vq_tma<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    CK(cudaFuncSetAttribute(k_vq_tma<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    CK(cudaFuncSetAttribute(k_vq_tma<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    CK(cudaFuncSetAttribute(k_vq_tma<8, 1, VT_KB, VT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + (size_t)VT_STAGES * VT_KB * VT_SROWS * sizeof(double))));
+    CK(cudaFuncSetAttribute(k_vq_tma<4, 3, VT_KB, VT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + (size_t)VT_STAGES * VT_KB * VT_SROWS * sizeof(double))));
+    CK(cudaFuncSetAttribute(k_vq_tma<8, 2, VT_KB, VT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + (size_t)VT_STAGES * VT_KB * VT_SROWS * sizeof(double))));
+    if (narrow) {
+      CK(cudaFuncSetAttribute(k_vq_tma<4, 1, 32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + (size_t)6 * 32 * VT_SROWS * sizeof(double))));
+      CK(cudaFuncSetAttribute(k_vq_tma<8, 1, 32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + (size_t)6 * 32 * VT_SROWS * sizeof(double))));
+    }
     configured = 1;
   }
   PROF_BEGIN(ctx, B2K_PROF_GEMM, 8.0 * (double)n * (kin + nout));
-  if (nout <= 32) k_vq_tma<8, 1><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
-  else if (nout <= 48) k_vq_tma<4, 3><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
-  else k_vq_tma<8, 2><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
+  if (use_narrow && nout <= 16) k_vq_tma<4, 1, 32, 6><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
+  else if (use_narrow) k_vq_tma<8, 1, 32, 6><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
+  else if (nout <= 32) k_vq_tma<8, 1, VT_KB, VT_STAGES><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
+  else if (nout <= 48) k_vq_tma<4, 3, VT_KB, VT_STAGES><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
+  else k_vq_tma<8, 2, VT_KB, VT_STAGES><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;
