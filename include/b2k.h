@@ -193,6 +193,18 @@ int  b2k_comm_p2p_enabled(b2k_comm comm);
 int  b2k_comm_reduce_scope(b2k_comm comm, int global_on, int *fused_out);
 int  b2k_comm_p2p_error(b2k_comm comm, int *flag_out);
 
+/* SpMV halo over NVLink peer memory (opt-in, B2K_HALO_P2P=1 in the host layer; default: grouped ncclSend/ncclRecv):
+   replaces the VecScatter of MatMult_MPIAIJ.  Collective set-up from the halo plan (who sends what to whom; handles and slot
+   tables travel through ncclAllGather), then per MatMult one push kernel + one wait kernel; the ghost entries arrive in a
+   double-buffered array owned by the object, *ghost_out is the buffer the SpMV of this exchange must read. */
+typedef struct b2k_halo_s *b2k_halo;
+int  b2k_halo_create(b2k_comm comm, int nrecv, const int *recvrank_host, const int *recvcount_host, int nsend, const int *sendrank_host,
+                     const int *sendcount_host, const int *sendidx_dev /* or NULL */, const int64_t *sendoff_host /* contiguous sends */,
+                     b2k_halo *halo);
+int  b2k_halo_exchange(b2k_halo halo, const double *x_dev, const double **ghost_out);
+int  b2k_halo_error(b2k_halo halo, int *flag_out);
+int  b2k_halo_destroy(b2k_halo halo);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,10 @@ SIGNATURES = {
     "b2k_comm_p2p_enabled": [c_vp],
     "b2k_comm_reduce_scope": [c_vp, c_int, ctypes.POINTER(c_int)],
     "b2k_comm_p2p_error": [c_vp, ctypes.POINTER(c_int)],
+    "b2k_halo_create": [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
+    "b2k_halo_exchange": [c_vp, c_vp, ctypes.POINTER(c_vp)],
+    "b2k_halo_error": [c_vp, ctypes.POINTER(c_int)],
+    "b2k_halo_destroy": [c_vp],
 }
 _SPECIAL = {
     "b2k_last_error": ([], ctypes.c_char_p),

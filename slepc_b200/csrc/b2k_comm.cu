@@ -203,6 +203,8 @@ extern "C" int b2k_comm_destroy(b2k_comm c)
   return B2K_OK;
 }
 
+int b2k_comm_ctx(b2k_comm c, b2k_ctx *ctx) { if (!c) return B2K_ERR_ARG; *ctx = c->ctx; return B2K_OK; }   /* for b2k_halo.cu */
+
 extern "C" int b2k_comm_rank(b2k_comm c, int *rank, int *size)
 {
   if (rank) *rank = c ? c->rank : 0;

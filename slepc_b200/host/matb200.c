@@ -28,16 +28,42 @@ typedef struct {
      built on first use; zghost/rbuf are the reverse-halo buffers */
   b2k_csr   ATown, ATgh;
   double   *zghost, *rbuf;
+  /* opt-in (B2K_HALO_P2P=1): the forward halo pushed over NVLink peer memory instead of ncclSend/ncclRecv */
+  b2k_halo  halo;
 } Mat_B200CSR;
 
 #define CTX() B2KGetContext()
 
-static PetscErrorCode MatHaloExchange_B200CSR(Mat A, const double *x)
+/* collective: turn the installed halo plan into a peer-memory halo object when asked for (B2K_HALO_P2P=1) and possible */
+static PetscErrorCode MatHaloSetUpP2P_B200CSR(Mat A)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  B2KComm comm = B2KCommWorld();
+  const char *e = getenv("B2K_HALO_P2P");
+  if (!e || e[0] != '1' || !comm || comm->kind != 1 || comm->size < 2 || comm->size > 8 || !b2k_comm_p2p_enabled(comm->nccl)) return PETSC_SUCCESS;
+  if (a->halo) { B2KCall(b2k_halo_destroy(a->halo)); a->halo = NULL; }
+  int64_t off[8] = {0};
+  for (PetscInt q = 0; q < a->nsend && q < 8; q++) off[q] = a->sendoff ? a->sendoff[q] : 0;
+  B2KCall(b2k_halo_create(comm->nccl, a->nrecv, a->recvrank, a->recvcount, a->nsend, a->sendrank, a->sendcount, a->d_sendidx,
+                          a->d_sendidx ? NULL : off, &a->halo));
+  return PETSC_SUCCESS;
+}
+
+/* on return *ghost points at the ghost values the SpMV must read */
+static PetscErrorCode MatHaloExchange_B200CSR(Mat A, const double *x, const double **ghost)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
   B2KComm comm = B2KCommWorld();
   int size = 1;
+  *ghost = a->xghost;
   PetscCall(B2KCommGetRank(comm, NULL, &size));
+  if (a->halo) {                                  /* collective: every rank of the communicator owns one */
+    int bad = 0;
+    B2KCall(b2k_halo_error(a->halo, &bad));       /* raised by an earlier exchange whose peer did not show up in time */
+    PetscCheck(!bad, PETSC_ERR_LIB, "peer-memory halo exchange timed out (code %d): a rank did not take part in MatMult", bad);
+    B2KCall(b2k_halo_exchange(a->halo, x, ghost));
+    return PETSC_SUCCESS;
+  }
   if (size == 1 || (a->nghost == 0 && a->nsend == 0)) {       /* a rank that only SENDS halo values still takes part */
     PetscCheck(a->nghost == 0, PETSC_ERR_ARG_WRONGSTATE, "matrix has %d ghost columns but the communicator has a single rank", a->nghost);
     return PETSC_SUCCESS;
@@ -64,8 +90,9 @@ static PetscErrorCode MatMult_B200CSR(Mat A, Vec x, Vec y)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
   PetscCheck(x->mem == B2K_MEM_DEVICE && y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "b200csr needs device vectors");
-  PetscCall(MatHaloExchange_B200CSR(A, x->array));
-  B2KCall(b2k_csr_spmv(CTX(), a->A, x->array, a->xghost, y->array));
+  const double *ghost;
+  PetscCall(MatHaloExchange_B200CSR(A, x->array, &ghost));
+  B2KCall(b2k_csr_spmv(CTX(), a->A, x->array, ghost, y->array));
   return PETSC_SUCCESS;
 }
 
@@ -154,6 +181,7 @@ static PetscErrorCode MatDestroy_B200CSR(Mat A)
   if (!a) return PETSC_SUCCESS;
   b2k_ctx ctx = CTX();
   if (ctx) {
+    if (a->halo) b2k_halo_destroy(a->halo);         /* collective */
     b2k_csr_destroy(ctx, a->ATown); b2k_csr_destroy(ctx, a->ATgh);
     b2k_free(ctx, a->zghost); b2k_free(ctx, a->rbuf);
     b2k_csr_destroy(ctx, a->A);
@@ -297,6 +325,7 @@ PetscErrorCode MatB200CSRSetHalo(Mat A, PetscInt nrecv, const PetscInt *recvrank
     B2KCall(b2k_malloc(ctx, (void **)&a->sendbuf, sizeof(double) * (size_t)stot));
   }
   a->halo_set = PETSC_TRUE;
+  PetscCall(MatHaloSetUpP2P_B200CSR(A));
   return PETSC_SUCCESS;
 }
 
@@ -355,6 +384,7 @@ PetscErrorCode MatCreateB200Laplacian(PetscInt dim, PetscInt nx, PetscInt ny, Pe
     for (PetscInt q = 0; q < a->nsend; q++) a->nsendtot += a->sendcount[q];
     a->halo_set = PETSC_TRUE;
   }
+  if (size > 1) PetscCall(MatHaloSetUpP2P_B200CSR(A));   /* collective, also on a rank without neighbours */
   *out = A;
   return PETSC_SUCCESS;
 }

@@ -76,6 +76,21 @@ def test_peer_memory_reductions_match_nccl(world, tmp_path):
     assert a["orth"] < 1e-13 and b["orth"] < 1e-13
 
 
+@pytest.mark.skipif(os.environ.get("B2K_TEST_EXPERIMENTAL") != "1", reason="opt-in kernel, not measured yet: set B2K_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case,world", [("lap", 2), ("lap", 4), ("markov", 2), ("svd", 2)])
+def test_peer_memory_halo_matches_nccl_halo(case, world, tmp_path):
+    """B2K_HALO_P2P=1 (b2k_halo.cu: the neighbours' entries of x pushed over NVLink into double-buffered ghost arrays, flags instead
+    of ncclSend/ncclRecv) against the default halo: contiguous planes (lap), packed general plan (markov), two row layouts (svd)"""
+    a = run_case(case, world, tmp_path, {"B2K_HALO_P2P": "1"}, "_p2phalo")
+    b = run_case(case, world, tmp_path, {"B2K_HALO_P2P": "0"}, "_ncclhalo")
+    if not a["p2p"]:
+        pytest.skip("CUDA IPC rendezvous not available on this box")
+    key = "sigma" if case == "svd" else "lam"
+    assert a["nconv"] == b["nconv"]
+    assert np.allclose(a[key][:a["nconv"]], b[key][:b["nconv"]], rtol=1e-12, atol=0)
+    assert max(a["errs"][:4]) < 5e-8
+
+
 def test_eps_markov_general_halo(tmp_path):
     r = run_case("markov", 2, tmp_path)
     assert r["nconv"] >= 4
