@@ -63,6 +63,9 @@ void        B2KClearError(void);
 typedef enum { B2K_MEM_HOST = 0, B2K_MEM_DEVICE = 1 } B2KMemType;
 typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
 
+typedef void *PetscObject;                          /* a Vec, Mat or BV handle cast as in the reference: (PetscObject)X */
+typedef struct _p_PetscViewer *PetscViewer;         /* ASCII on stdout; NULL means the same */
+typedef enum { PETSC_VIEWER_DEFAULT = 0, PETSC_VIEWER_ASCII_INFO = 1, PETSC_VIEWER_ASCII_INFO_DETAIL = 2 } PetscViewerFormat;
 typedef struct _p_B2KComm *B2KComm;
 typedef struct _p_Vec *Vec;
 typedef struct _p_Mat *Mat;
@@ -71,6 +74,14 @@ typedef struct _p_DS  *DS;
 typedef struct _p_ST  *ST;
 typedef struct _p_EPS *EPS;
 typedef struct _p_SVD *SVD;
+
+/* names and viewers: only what the reference's BV programs print (bv/tests/test1.c -verbose) */
+PetscErrorCode PetscObjectSetName(PetscObject obj, const char name[]);
+PetscErrorCode PetscViewerASCIIGetStdout(PetscViewer *viewer);
+PetscErrorCode PetscViewerPushFormat(PetscViewer viewer, PetscViewerFormat format);
+PetscErrorCode PetscViewerPopFormat(PetscViewer viewer);
+PetscErrorCode PetscViewerGetFormat(PetscViewer viewer, PetscViewerFormat *format);
+void           B2KFormatReal(double x, char buf[32]);     /* "%g" as PETSc's ASCII output shows reals: -2 prints as "-2." */
 
 /* ---- device context and communicator (stand-ins for PETSc's CUDA handle and MPI_Comm) -------- */
 PetscErrorCode B2KInitialize(int device);           /* creates the process-wide b2k_ctx; errors if no GPU */
@@ -111,6 +122,8 @@ PetscErrorCode VecResetArray(Vec v);
 PetscErrorCode VecSetValuesHost(Vec v, const PetscScalar *host_values);   /* upload n values   */
 PetscErrorCode VecGetValuesHost(Vec v, PetscScalar *host_values);         /* download n values */
 PetscErrorCode VecSet(Vec v, PetscScalar alpha);
+PetscErrorCode VecView(Vec v, PetscViewer viewer);
+PetscErrorCode B2KVecSetOwnershipStart(Vec v, PetscInt rstart);          /* first global row of a row-partitioned template vector */
 PetscErrorCode VecNorm(Vec v, NormType type, PetscReal *val);             /* collective */
 PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *val);                    /* collective */
 PetscErrorCode VecAXPY(Vec y, PetscScalar alpha, Vec x);
@@ -123,6 +136,7 @@ PetscErrorCode MatDenseSetLDA(Mat A, PetscInt lda);
 PetscErrorCode MatDenseGetLDA(Mat A, PetscInt *lda);
 PetscErrorCode MatDenseGetArray(Mat A, PetscScalar **a);
 PetscErrorCode MatDenseRestoreArray(Mat A, PetscScalar **a);
+PetscErrorCode MatView(Mat A, PetscViewer viewer);                       /* sequential dense matrices */
 PetscErrorCode MatGetSize(Mat A, PetscInt *M, PetscInt *N);
 PetscErrorCode MatGetLocalSize(Mat A, PetscInt *m, PetscInt *n);
 PetscErrorCode MatGetOwnershipRange(Mat A, PetscInt *rstart, PetscInt *rend);
@@ -213,6 +227,7 @@ PetscErrorCode BVMatMultColumn(BV V, Mat A, PetscInt j);                        
 PetscErrorCode BVOrthogonalizeVec(BV bv, Vec v, PetscScalar *H, PetscReal *norm, PetscBool *lindep);       /* bvorthog.c:249 */
 PetscErrorCode BVOrthogonalizeColumn(BV bv, PetscInt j, PetscScalar *H, PetscReal *norm, PetscBool *lindep); /* bvorthog.c:315 */
 PetscErrorCode BVOrthonormalizeColumn(BV bv, PetscInt j, PetscBool replace, PetscReal *norm, PetscBool *lindep); /* bvorthog.c:380 */
+PetscErrorCode BVView(BV bv, PetscViewer viewer);                                       /* bvfunc.c:548 + svec.c:353 */
 PetscErrorCode BVOrthogonalize(BV V, Mat R);                                            /* bvorthog.c:682 (block GS)   */
 PetscErrorCode BVMatArnoldi(BV V, Mat A, Mat H, PetscInt k, PetscInt *m, PetscReal *beta, PetscBool *breakdown);  /* bvkrylov.c:56  */
 PetscErrorCode BVMatLanczos(BV V, Mat A, Mat T, PetscInt k, PetscInt *m, PetscReal *beta, PetscBool *breakdown);  /* bvkrylov.c:165 */

@@ -63,8 +63,16 @@ struct _p_B2KComm {
   void          *user;
 };
 
+/* ---- common object header (stands in for PetscObject: class id + the name given with PetscObjectSetName) ---- */
+#define B2K_VEC_CLASSID 0x56454300
+#define B2K_MAT_CLASSID 0x4d415400
+#define B2K_BV_CLASSID  0x42560000
+typedef struct { int classid; char name[64]; } B2KObjectHeader;     /* FIRST member of _p_Vec, _p_Mat, _p_BV */
+struct _p_PetscViewer { PetscViewerFormat fmt[8]; int depth; };
+
 /* ---- Vec / Mat ------------------------------------------------------------------------------------ */
 struct _p_Vec {
+  B2KObjectHeader hdr;
   PetscInt     n, N;
   PetscInt     rstart;     /* global index of the first local entry (PetscLayout rstart) */
   B2KMemType   mem;
@@ -80,6 +88,7 @@ typedef struct _MatOps {
 } MatOps;
 
 struct _p_Mat {
+  B2KObjectHeader hdr;
   MatOps       ops;
   char         type[24];
   PetscInt     m, n, M, N;           /* local / global sizes            */
@@ -122,6 +131,7 @@ typedef struct _BVOps {
 } BVOps;
 
 struct _p_BV {
+  B2KObjectHeader    hdr;
   BVOps              ops;
   char               type_name[24];
   B2KComm            comm;

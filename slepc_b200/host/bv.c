@@ -42,6 +42,7 @@ PetscErrorCode BVCreate(BV *out)
 {
   PetscCall(BVRegisterAll());
   BV bv = (BV)calloc(1, sizeof(*bv));
+  if (bv) bv->hdr.classid = B2K_BV_CLASSID;
   PetscCheck(bv, PETSC_ERR_MEM, "out of memory");
   bv->comm = B2KCommWorld();
   bv->orthog_type = BV_ORTHOG_CGS;                /* bvfunc.c:176-179 */
@@ -748,6 +749,36 @@ PetscErrorCode BVOrthonormalizeColumn(BV bv, PetscInt j, PetscBool replace, Pets
 }
 
 /* BVOrthogonalize with BV_ORTHOG_BLOCK_GS — bvorthog.c:560-594, 682-740 */
+/* ---- BVView: bvfunc.c:548-603 + the column loop of BVView_Svec svec.c:353-382 ------------------------------------------ */
+PetscErrorCode B2KViewHeader_Private(const char *cls, const char *name, const char *type, int indent);
+PetscErrorCode BVView(BV bv, PetscViewer viewer)
+{
+  static const char *orthname[2] = {"classical", "modified"}, *refname[3] = {"if needed", "never", "always"};
+  static const char *blockname[5] = {"GS", "CHOL", "TSQR", "TSQRCHOL", "SVQB"};
+  PetscViewerFormat format;
+  BVCheckSizes(bv);
+  PetscCall(PetscViewerGetFormat(viewer, &format));
+  PetscCall(B2KViewHeader_Private("BV", bv->hdr.name, bv->type_name, 0));
+  if (format == PETSC_VIEWER_ASCII_INFO || format == PETSC_VIEWER_ASCII_INFO_DETAIL) {
+    printf("  %d columns of global length %d\n", bv->m, bv->N);
+    if (bv->nc > 0) printf("  number of constraints: %d\n", bv->nc);
+    printf("  vector orthogonalization method: %s Gram-Schmidt\n", orthname[bv->orthog_type]);
+    if (bv->orthog_ref == BV_ORTHOG_REFINE_IFNEEDED) printf("  orthogonalization refinement: %s (eta: %g)\n", refname[bv->orthog_ref], bv->orthog_eta);
+    else printf("  orthogonalization refinement: %s\n", refname[bv->orthog_ref]);
+    printf("  block orthogonalization method: %s\n", blockname[bv->orthog_block]);
+    printf("  doing matmult as matrix-vector products\n");          /* ops.matmult is a column loop of MatMult (BV_MATMULT_VECS) */
+    return PETSC_SUCCESS;                                             /* the type's view prints nothing in the INFO formats, svec.c:365 */
+  }
+  for (PetscInt j = 0; j < bv->m; j++) {
+    Vec v;
+    PetscCall(BVGetColumn(bv, j, &v));
+    PetscErrorCode ierr = VecView(v, viewer);
+    PetscCall(BVRestoreColumn(bv, j, &v));
+    PetscCall(ierr);
+  }
+  return PETSC_SUCCESS;
+}
+
 /* ---- block orthogonalisation: bvorthog.c:488-765, bvlapack.c:136-345 ------------------------------------------
    CHOL and SVQB are two BLAS-3 sweeps of the basis (BVDot = V^T V, BVMultInPlace = V S) around a k x k host
    factorisation, i.e. the level-3 kernels of the restart; TSQR/TSQRCHOL (host Householder panels over a raw

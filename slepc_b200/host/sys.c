@@ -206,6 +206,7 @@ PetscErrorCode B2KVecRegisterHostOps(const B2KVecHostOps *ops) { g_hostvec = *op
 PetscErrorCode VecCreateWithArray(B2KMemType mem, PetscInt n, PetscInt N, PetscScalar *array, Vec *v)
 {
   Vec x = (Vec)calloc(1, sizeof(*x));
+  if (x) x->hdr.classid = B2K_VEC_CLASSID;
   PetscCheck(x, PETSC_ERR_MEM, "out of memory");
   x->n = n; x->N = (N < 0) ? n : N; x->mem = mem; x->array = array; x->owns = PETSC_FALSE;
   *v = x;
@@ -334,6 +335,15 @@ PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *val)
   return PETSC_SUCCESS;
 }
 
+/* global index of the first local entry (what PetscLayout gives a real Vec): template vectors of row-partitioned objects */
+PetscErrorCode B2KVecSetOwnershipStart(Vec v, PetscInt rstart)
+{
+  PetscCheck(v, PETSC_ERR_ARG_NULL, "null vector");
+  PetscCheck(rstart >= 0 && rstart + v->n <= v->N, PETSC_ERR_ARG_OUTOFRANGE, "rows [%d,%d) outside the global length %d", rstart, rstart + v->n, v->N);
+  v->rstart = rstart;
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode VecAXPY(Vec y, PetscScalar alpha, Vec x)
 {
   PetscCheck(x->mem == y->mem && x->n == y->n, PETSC_ERR_ARG_INCOMP, "incompatible vectors");
@@ -364,6 +374,7 @@ PetscErrorCode VecCopy(Vec x, Vec y)
 PetscErrorCode MatCreate_Private(Mat *A)
 {
   Mat a = (Mat)calloc(1, sizeof(*a));
+  if (a) a->hdr.classid = B2K_MAT_CLASSID;
   PetscCheck(a, PETSC_ERR_MEM, "out of memory");
   *A = a;
   return PETSC_SUCCESS;
@@ -482,3 +493,84 @@ PetscErrorCode MatCreateShell(PetscInt m, PetscInt n, PetscInt M, PetscInt N, B2
 PetscErrorCode MatShellGetContext(Mat A, void **ctx) { *ctx = A->data; return PETSC_SUCCESS; }
 PetscErrorCode MatShellSetMult(Mat A, MatMultFn f) { A->ops.mult = f; return PETSC_SUCCESS; }
 PetscErrorCode MatShellSetMultTranspose(Mat A, MatMultFn f) { A->ops.multtranspose = f; return PETSC_SUCCESS; }
+
+/* ---- names and ASCII viewers: PetscObjectSetName, PetscViewerASCIIGetStdout / PushFormat / PopFormat, VecView, MatView --------
+   Only what the reference's BV test programs print (bv/tests/test1.c -verbose): the default ASCII format and INFO_DETAIL. */
+PetscErrorCode PetscObjectSetName(PetscObject obj, const char name[])
+{
+  PetscCheck(obj && name, PETSC_ERR_ARG_NULL, "null argument");
+  B2KObjectHeader *h = (B2KObjectHeader *)obj;
+  PetscCheck(h->classid == B2K_VEC_CLASSID || h->classid == B2K_MAT_CLASSID || h->classid == B2K_BV_CLASSID, PETSC_ERR_ARG_WRONG,
+             "PetscObjectSetName() is available for Vec, Mat and BV objects");
+  strncpy(h->name, name, sizeof(h->name) - 1);
+  h->name[sizeof(h->name) - 1] = 0;
+  return PETSC_SUCCESS;
+}
+
+static struct _p_PetscViewer g_stdout_viewer = {{PETSC_VIEWER_DEFAULT}, 0};
+PetscErrorCode PetscViewerASCIIGetStdout(PetscViewer *viewer) { *viewer = &g_stdout_viewer; return PETSC_SUCCESS; }
+PetscErrorCode PetscViewerPushFormat(PetscViewer viewer, PetscViewerFormat format)
+{
+  if (!viewer) viewer = &g_stdout_viewer;
+  PetscCheck(viewer->depth < 7, PETSC_ERR_PLIB, "Too many PetscViewerPushFormat(), perhaps you forgot PetscViewerPopFormat()?");
+  viewer->fmt[++viewer->depth] = format;
+  return PETSC_SUCCESS;
+}
+PetscErrorCode PetscViewerPopFormat(PetscViewer viewer)
+{
+  if (!viewer) viewer = &g_stdout_viewer;
+  if (viewer->depth > 0) viewer->depth--;
+  return PETSC_SUCCESS;
+}
+PetscErrorCode PetscViewerGetFormat(PetscViewer viewer, PetscViewerFormat *format)
+{
+  if (!viewer) viewer = &g_stdout_viewer;
+  *format = viewer->fmt[viewer->depth];
+  return PETSC_SUCCESS;
+}
+
+/* "%g" the way PETSc's ASCII output shows reals: a '.' is appended when the text has neither '.' nor an exponent
+   (PetscFormatConvert/PetscVSNPrintf), so that -2 prints as "-2." */
+void B2KFormatReal(double x, char buf[32])
+{
+  snprintf(buf, 30, "%g", x);
+  if (!strpbrk(buf, ".eEn")) strcat(buf, ".");    /* 'n': inf / nan stay as they are */
+}
+
+/* first line of every view: "<Class> Object: [name ]<size> MPI process[es]" + "  type: <type>" */
+PetscErrorCode B2KViewHeader_Private(const char *cls, const char *name, const char *type, int indent)
+{
+  int size = 1;
+  PetscCall(B2KCommGetRank(B2KCommWorld(), NULL, &size));
+  printf("%*s%s Object: %s%s%d MPI process%s\n", indent, "", cls, name, name[0] ? " " : "", size, size > 1 ? "es" : "");
+  printf("%*s  type: %s\n", indent, "", type);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode VecView(Vec v, PetscViewer viewer)
+{
+  (void)viewer;
+  int rank = 0, size = 1;
+  PetscCall(B2KCommGetRank(B2KCommWorld(), &rank, &size));
+  PetscCall(B2KViewHeader_Private("Vec", v->hdr.name, (size > 1 && v->N != v->n) ? "mpi" : "seq", 0));
+  PetscScalar *h = (PetscScalar *)malloc(sizeof(PetscScalar) * (size_t)(v->n > 0 ? v->n : 1));
+  PetscCheck(h, PETSC_ERR_MEM, "out of memory");
+  PetscErrorCode ierr = VecGetValuesHost(v, h);
+  char buf[32];
+  for (PetscInt i = 0; !ierr && i < v->n; i++) { B2KFormatReal(h[i], buf); printf("%s\n", buf); }   /* this rank's entries */
+  free(h);
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode MatView(Mat A, PetscViewer viewer)
+{
+  (void)viewer;
+  PetscCheck(A->dense, PETSC_ERR_SUP, "MatView is implemented for sequential dense matrices");
+  PetscCall(B2KViewHeader_Private("Mat", A->hdr.name, "seqdense", 0));
+  for (PetscInt i = 0; i < A->m; i++) {
+    for (PetscInt j = 0; j < A->n; j++) printf("%.16e ", A->dense[i + (size_t)j * A->lda]);
+    printf("\n");
+  }
+  return PETSC_SUCCESS;
+}

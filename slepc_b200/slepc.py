@@ -25,7 +25,7 @@ _SCALAR_TYPES = {
     "double": c_dbl, "PetscScalar": c_dbl, "PetscReal": c_dbl,
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t,
 }
-_ENUMS = ("B2KMemType", "NormType", "BVOrthogType", "BVOrthogRefineType", "BVOrthogBlockType", "DSStateType", "DSMatType",
+_ENUMS = ("B2KMemType", "NormType", "PetscViewerFormat", "BVOrthogType", "BVOrthogRefineType", "BVOrthogBlockType", "DSStateType", "DSMatType",
           "EPSProblemType", "EPSWhich", "EPSConvergedReason", "EPSErrorType", "EPSConv", "SVDWhich", "SVDConvergedReason",
           "SVDErrorType")
 
@@ -332,10 +332,9 @@ class BV(Handle):
 
 
 def _set_vec_rstart(vec, rstart):
-    """struct _p_Vec { PetscInt n, N, rstart; … } (slepc_b200/host/b2kimpl.h) — test/driver helper for row offsets"""
+    """first global row of a row-partitioned template vector (test/driver helper)"""
     if rstart:
-        arr = (ctypes.c_int * 3).from_address(vec.h.value)
-        arr[2] = int(rstart)
+        S.B2KVecSetOwnershipStart(vec.h, int(rstart))
 
 
 class EPS(Handle):

@@ -56,5 +56,8 @@ static PetscErrorCode ShimSVDCreate(SVD *svd)
 #define MatCreateB200CSR ShimMatCSR
 #define EPSCreate        ShimEPSCreate
 #define SVDCreate        ShimSVDCreate
+#define VecCreateB200    VecCreateHost
+#undef  BVB200
+#define BVB200           "oraclecpu"
 #define SVDSetOperators  ShimSVDSetOperators
 #endif

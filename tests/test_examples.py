@@ -41,6 +41,16 @@ SVD of a rectangular Grcar matrix, 35x30
 
 Level of orthogonality below the tolerance
 """
+BV_TEST1_OUT = open(os.path.join(ROOT, "tests", "golden", "bv_test1_1_svec.out")).read()   # bv/tests/output/test1_1_bv_type-svec.out
+
+
+def bv_test1_expected(bvtype):
+    """the reference's output for -bv_type svec with the two lines that name the implementation adapted: the type, and how
+    BVMatMult runs (this build's ops.matmult is a column loop = the reference's BV_MATMULT_VECS wording, bvfunc.c:589-595)"""
+    return BV_TEST1_OUT.replace("type: svec", "type: " + bvtype).replace("doing matmult as a single matrix-matrix product",
+                                                                           "doing matmult as matrix-vector products")
+
+
 CASES = [
     ("ex2", ["-n", "72", "-eps_nev", "4", "-eps_ncv", "20", "-terse"], EX2_OUT),
     ("ex3", ["-n", "72", "-eps_nev", "4", "-eps_ncv", "20", "-terse"], EX3_OUT),
@@ -55,7 +65,7 @@ IDS = [c[0] + "".join(a for a in c[1] if a.startswith("-") and a not in ("-terse
 
 
 def ensure_built():
-    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex3", "ex5", "svd_test3")):
+    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1")):
         subprocess.run(["make", "-C", ROOT, "all"], check=True, capture_output=True)
 
 
@@ -66,7 +76,7 @@ def cpu_bins(tmp_path_factory):
     out = tmp_path_factory.mktemp("ex_cpu")
     lib = os.path.join(ROOT, "slepc_b200", "lib")
     orc = os.path.join(ROOT, "oracle", "_build")
-    for name in ("ex2", "ex3", "ex5", "svd_test3"):
+    for name in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1"):
         subprocess.run(["gcc", "-O1", "-std=gnu11", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "examples"),
                         "-include", os.path.join(ROOT, "tests", "ex_cpu_shim.h"), "-o", str(out / name), os.path.join(ROOT, "examples", name + ".c"),
                         "-L" + orc, "-loraclecpu", "-L" + lib, "-lb2kslepc", "-lb200krylov",
@@ -79,6 +89,14 @@ def test_example_matches_reference_output_cpu_oracle(cpu_bins, name, args, gold)
     r = subprocess.run([str(cpu_bins / name)] + args, capture_output=True, text=True, timeout=120, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stderr
     assert r.stdout == gold
+
+
+def test_bv_test1_verbose_matches_reference_output_cpu_oracle(cpu_bins):
+    """bv/tests/test1.c -verbose: every BVView / MatView / VecView line of output/test1_1_bv_type-svec.out (the reference filters
+    negative zeros with sed -e 's/-0[.]/0./g', test1.c:188)"""
+    r = subprocess.run([str(cpu_bins / "bv_test1"), "-verbose"], capture_output=True, text=True, timeout=120, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.replace("-0.\n", "0.\n") == bv_test1_expected("oraclecpu")
 
 
 def test_product_binaries_fail_loudly_without_gpu():
@@ -98,3 +116,11 @@ def test_example_matches_reference_output_gpu(name, args, gold):
     r = subprocess.run([os.path.join(BIN, name)] + args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert r.stdout == gold
+
+
+@pytest.mark.gpu
+def test_bv_test1_verbose_matches_reference_output_gpu():
+    ensure_built()
+    r = subprocess.run([os.path.join(BIN, "bv_test1"), "-verbose"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.replace("-0.\n", "0.\n") == bv_test1_expected("b200")
