@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE (force-included by tests/test_examples.py with `gcc -include`): compiles the programs of examples/
+/* TEST INFRASTRUCTURE (force-included by tests/test_z_examples.py with `gcc -include`): compiles the programs of examples/
    against the CPU oracle plug-in (oracle/oracle_cpu.c) instead of the GPU types, so that their host logic — matrix assembly,
    solver set-up, output format — is checked against the reference's .out files on a box without a GPU.  The sources under
    examples/ never see this header in the product build. */

@@ -41,7 +41,7 @@ def main():
                 rows.append([float(t) for t in toks])
         out[rel] = {"source": src, "args": args, "rows": rows}
     # the one output kept verbatim (a golden OUTPUT, not source): bv/tests/test1.c -verbose, compared line by line with
-    # examples/bv_test1.c in tests/test_examples.py
+    # examples/bv_test1.c in tests/test_z_examples.py
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(REF, "sys/classes/bv/tests/output/test1_1_bv_type-svec.out")) as f, open(os.path.join(here, "bv_test1_1_svec.out"), "w") as g:
         g.write(f.read())

@@ -1,9 +1,10 @@
 """The reference's tutorial / test programs rewritten against include/b2kslepc.h (examples/*.c): what a user of the
 reference would compile after switching.  Each program's output is compared LINE BY LINE with the reference's own output
-file (src/eps/tutorials/output/ex2_1.out, ex3_1.out, ex5_1.out, src/eps/tests/output/test4_1.out, bv/tests/output/test1_1, test2_1, src/svd/tests/output/test3_1.out — copied below as golden text).
+file (src/eps/tutorials/output/ex2_1.out, ex3_1.out, ex5_1.out, src/eps/tests/output/test4_1.out, bv/tests/output/test1_1, test2_1, src/svd/tutorials/output/ex8_1.out, src/svd/tests/output/test3_1.out — copied below as golden text).
   * not gpu: the programs are compiled against the CPU oracle plug-in through tests/ex_cpu_shim.h (host logic + format),
     and the product binaries are checked to FAIL LOUDLY without a GPU (no CPU fallback);
-  * gpu: the product binaries (BV type b200, Mat type b200csr) run on cuda:0."""
+  * gpu: the product binaries (BV type b200, Mat type b200csr) run on cuda:0.
+(The file sorts last on purpose: the kernel and solver parity tests run before the example programs.)"""
 import os
 import subprocess
 
@@ -65,7 +66,15 @@ Level of orthogonality < 100*eps
 Residual ||X-QR|| < 100*eps
 Norm of ones(n,1) after orthogonalizing against X: 2.50931
 """
+EX8_OUT = """
+Estimate the condition number of a Grcar matrix, n=30
+
+ Computed singular values: sigma_1=3.2215, sigma_n=0.9551
+ Estimated condition number: sigma_1/sigma_n=3.3731
+
+"""
 CASES = [
+    ("svd_ex8", [], EX8_OUT),
     ("eps_test4", [], TEST4_OUT),
     ("bv_test2", [], BV_TEST2_OUT),
     ("bv_test2", ["-bv_orthog_type", "mgs"], BV_TEST2_OUT),
@@ -82,7 +91,7 @@ IDS = [c[0] + "".join(a for a in c[1] if a.startswith("-") and a not in ("-terse
 
 
 def ensure_built():
-    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1", "bv_test2", "eps_test4")):
+    if not all(os.path.exists(os.path.join(BIN, n)) for n in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1", "bv_test2", "eps_test4", "svd_ex8")):
         subprocess.run(["make", "-C", ROOT, "all"], check=True, capture_output=True)
 
 
@@ -93,7 +102,7 @@ def cpu_bins(tmp_path_factory):
     out = tmp_path_factory.mktemp("ex_cpu")
     lib = os.path.join(ROOT, "slepc_b200", "lib")
     orc = os.path.join(ROOT, "oracle", "_build")
-    for name in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1", "bv_test2", "eps_test4"):
+    for name in ("ex2", "ex3", "ex5", "svd_test3", "bv_test1", "bv_test2", "eps_test4", "svd_ex8"):
         subprocess.run(["gcc", "-O1", "-std=gnu11", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "examples"),
                         "-include", os.path.join(ROOT, "tests", "ex_cpu_shim.h"), "-o", str(out / name), os.path.join(ROOT, "examples", name + ".c"),
                         "-L" + orc, "-loraclecpu", "-L" + lib, "-lb2kslepc", "-lb200krylov",

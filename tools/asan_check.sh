@@ -9,7 +9,7 @@ OB=$(python -c "import scipy,os,glob;print(os.path.realpath(glob.glob(os.path.jo
 SAN="-g -O1 -fsanitize=address,undefined -fno-omit-frame-pointer -std=gnu11 -Wno-unused-function -fopenmp -I$ROOT/include -I$ROOT/slepc_b200/host -I$ROOT/examples"
 make -C "$ROOT" -s slepc_b200/lib/libb200krylov.so
 for f in "$ROOT"/slepc_b200/host/*.c "$ROOT"/oracle/oracle_cpu.c; do gcc $SAN -c "$f" -o "$OUT/$(basename "$f" .c).o"; done
-for ex in ex2 ex3 ex5 svd_test3 bv_test1 bv_test2 eps_test4; do
+for ex in ex2 ex3 ex5 svd_test3 svd_ex8 bv_test1 bv_test2 eps_test4; do
   gcc $SAN -include "$ROOT/tests/ex_cpu_shim.h" -o "$OUT/$ex" "$ROOT/examples/$ex.c" "$OUT"/*.o -L"$ROOT/slepc_b200/lib" -lb200krylov \
       -Wl,-rpath,"$ROOT/slepc_b200/lib" "$OB" -Wl,-rpath,"$(dirname "$OB")" -lm -ldl
 done
@@ -24,6 +24,7 @@ run "$OUT/bv_test1" -verbose
 run "$OUT/bv_test2"
 run "$OUT/bv_test2" -bv_orthog_type mgs
 run "$OUT/eps_test4"
+run "$OUT/svd_ex8"
 run "$OUT/svd_test3" -svd_nsv 4
 run "$OUT/svd_test3" -svd_nsv 4 -svd_trlanczos_locking 0
 run "$OUT/svd_test3" -svd_nsv 4 -svd_trlanczos_oneside
