@@ -45,9 +45,12 @@ examples/bin/%: examples/%.c examples/exutil.h $(HHDR) $(LIBDIR)/libb2kslepc.so
 
 examples: $(EXBIN)
 
+check: all
+	$(PYTHON) -m pytest tests -x -q -m "not gpu"
+
 kernels: $(LIBDIR)/libb200krylov.so
 
 clean:
 	rm -f $(LIBDIR)/*.so oracle/_build/*.so examples/bin/*
 
-.PHONY: all clean kernels examples
+.PHONY: all clean kernels examples check
