@@ -1,7 +1,7 @@
 #!/bin/bash
 # Memory/UB check of the C host side on CPU: host/*.c + the CPU oracle plug-in + the example programs (through the test-only
 # shim tests/ex_cpu_shim.h) built with -fsanitize=address,undefined and run with LeakSanitizer on.  Exits non-zero on any report.
-#     bash tools/asan_check.sh
+#     bash tests/asan_check.sh
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=$(mktemp -d)

@@ -1,3 +1,5 @@
+"""Debug helper (test infrastructure): Gram-Schmidt variants of the b200 BV type against the numpy oracle on a nearly dependent basis.
+    python tests/dbg_orthog.py        (needs a GPU)"""
 import sys, ctypes, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import slepc_oracle as O
