@@ -31,6 +31,9 @@ extern "C" {
 #define B2K_ERR_NOGPU 3   /* no CUDA device: the product path has no CPU fallback */
 #define B2K_ERR_COMM  4   /* NCCL / peer-memory failure */
 #define B2K_ERR_MEM   5
+/* widest block one reduction / projection takes (columns of V in b2k_dotvec, b2k_gs_*, b2k_sumsq …): callers validate
+   nc + ncv + 1 against it up front instead of failing inside the first orthogonalisation */
+#define B2K_MAX_COLUMNS 1024
 
 typedef struct b2k_ctx_s  *b2k_ctx;    /* one per process/GPU: device, stream, scratch */
 typedef struct b2k_csr_s  *b2k_csr;    /* FP64 CSR matrix resident in HBM */
@@ -66,12 +69,12 @@ int  b2k_timer_stop_ms(b2k_ctx ctx, double *ms);                                
 int  b2k_ctx_copy_bytes(b2k_ctx ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* per-kernel-class timing: CUDA events around every launch of the class on the context's stream
    (PetscLogGpuTimeBegin/End stand-in, bvcuda.cu:35-38).  b2k_prof_get synchronises. */
-#define B2K_PROF_DOTVEC   0   /* k_dotvec: V^T w (+ w^T w)              */
-#define B2K_PROF_MULTVEC  1   /* k_multvec: y = beta y + alpha V q      */
-#define B2K_PROF_GSFUSED  2   /* k_gs_fused: update + next dot, V once  */
-#define B2K_PROF_SPMV     3   /* k_spmv_csr_stream                      */
-#define B2K_PROF_GEMM     4   /* k_gemm_ts: V Q (restart), Y^T X        */
-#define B2K_PROF_ELEMWISE 5   /* scale / copy / axpby / fill            */
+#define B2K_PROF_DOTVEC   0   /* k_dotvec: V^T w (+ w^T w)                                        */
+#define B2K_PROF_MULTVEC  1   /* k_gs_tma<.,0,.> / k_gs_rt / k_multvec: y = beta y + alpha V q (+ norm) */
+#define B2K_PROF_GSFUSED  2   /* k_gs_tma<.,1,1>: update + next pass' V^T w + norm, V read once     */
+#define B2K_PROF_SPMV     3   /* k_spmv_sell_pipe / k_spmv_sell / k_spmv_csr_stream                */
+#define B2K_PROF_GEMM     4   /* k_vq_tma / k_vq / k_gemm_ts: V Q (restart); k_gram: Y^T X         */
+#define B2K_PROF_ELEMWISE 5   /* scale / copy / axpby / fill                                      */
 #define B2K_PROF_NCLASS   6
 int  b2k_prof_enable(b2k_ctx ctx, int on);               /* on: start a fresh recording            */
 int  b2k_prof_get(b2k_ctx ctx, int cls, uint64_t *launches, double *ms, double *algorithmic_bytes);
@@ -143,8 +146,23 @@ int  b2k_csr_adopt(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t ngho
                    int *rowptr, int *colidx, double *val, b2k_csr *A);
 int  b2k_csr_destroy(b2k_ctx ctx, b2k_csr A);
 int  b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncols_local, int64_t *nghost, int64_t *nnz);
-/* device pointers of the CSR arrays (owned by A)                                                    */
+/* device pointers of the CSR arrays (owned by A).  The matrix is stored ONCE: when the SELL-32 copy that the products read
+   exists, the CSR (col,val) arrays are freed after the conversion (the row pointer stays); asking for colidx/val here
+   rebuilds them from the SELL copy on A's stream, b2k_csr_release_arrays drops them again.  env B2K_CSR_KEEP=1 keeps both. */
 int  b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val);
+int  b2k_csr_release_arrays(b2k_csr A);
+/* HBM bytes held by the matrix, all copies (bench: footprint)                                      */
+int  b2k_csr_bytes(b2k_csr A, int64_t *bytes);
+/* which kernel the most recent product of A ran (tests assert the dispatch they mean to cover)     */
+#define B2K_SPMV_KERNEL_NONE            0
+#define B2K_SPMV_KERNEL_CSR_STREAM      1   /* k_spmv_csr_stream                      */
+#define B2K_SPMV_KERNEL_SELL            2   /* k_spmv_sell                            */
+#define B2K_SPMV_KERNEL_SELL_PIPE       3   /* k_spmv_sell_pipe<false> (no ghosts)    */
+#define B2K_SPMV_KERNEL_SELL_PIPE_GHOST 4   /* k_spmv_sell_pipe<true>  (halo columns) */
+int  b2k_csr_last_kernel(b2k_csr A, int *which);
+/* the bulk-copy pipeline kernel runs when the SELL copy has at least this many chunks (default 4 per SM, i.e. about 6e5 rows;
+   env B2K_SPMV_PIPE_MIN_CHUNKS); < 0 restores the default.  Tests lower it to push small matrices through the pipeline. */
+int  b2k_spmv_set_pipe_min_chunks(int min_chunks);
 /* y = A [x ; xghost]                                                                               */
 int  b2k_csr_spmv(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y);
 /* y = A x - sigma*xdiag   (shifted operator of STSHIFT, shift.c:79; xdiag = x rows owned here)    */

@@ -619,7 +619,14 @@ extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, in
 {
   ARGCHK(k >= 1 && k <= B2K_MAX_K, "k out of range");
   if (n == 0) {
-    if (ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, 1, 1, out);
+    /* a rank without rows issues the SAME cross-GPU reduction as the ranks with rows (k columns, then their sum) */
+    if (ctx->xg && ctx->xg_on) {
+      const int rc_ = b2k_launch_reduce_partials(ctx, 0, k, k, ctx->dscratch);
+      if (rc_) return rc_;
+      k_sum_small<<<1, 32, 0, ctx->stream>>>(ctx->dscratch, k, out);
+      CKLAUNCH(ctx);
+      return B2K_OK;
+    }
     CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream));
     return B2K_OK;
   }

@@ -58,7 +58,7 @@ int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, do
   if (prof_slot_ >= 0) cudaEventRecord((ctx)->prof_ev[2 * prof_slot_ + 1], (ctx)->stream);
 
 #define B2K_MAX_PART_BLOCKS 2048
-#define B2K_MAX_K           1024     /* max columns in one reduction (ncv+1 <= 1024)              */
+#define B2K_MAX_K           B2K_MAX_COLUMNS   /* max columns in one reduction (nc+ncv+1 <= 1024), public in b2k.h */
 
 void b2k_set_error(const char *fmt, ...);
 

@@ -35,6 +35,9 @@ struct b2k_csr_s {
   int     *sp_chunk;  /* [nchunks+1] first slice of each chunk */
   int      nchunks;
   int      sp_cap;    /* entries of the largest chunk, rounded up to 32 */
+  b2k_ctx  ctx;       /* owner (b2k_csr_arrays rebuilds the CSR copy on this context's stream)                     */
+  int      csr_dropped;   /* colidx/val were freed once the SELL copy existed: the matrix is stored ONCE            */
+  int      last_kernel;   /* B2K_SPMV_KERNEL_* of the most recent product                                           */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -218,8 +221,10 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
         meta[2 * s] = s0; meta[2 * s + 1] = s1 - s0;                              /* released by the arrive below */
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(noff * 8u + nent * 12u) : "memory");
         sp_bulk(sp_smem_u32(st), sl_off + s0, noff * 8u, bar);
-        sp_bulk(sp_smem_u32(st + SP_OFFS * 8), col + e0, nent * 4u, bar);
-        sp_bulk(sp_smem_u32(st + SP_OFFS * 8 + (size_t)cap * 4), val + e0, nent * 8u, bar);
+        if (nent) {                                                               /* a chunk of empty slices moves its offsets only */
+          sp_bulk(sp_smem_u32(st + SP_OFFS * 8), col + e0, nent * 4u, bar);
+          sp_bulk(sp_smem_u32(st + SP_OFFS * 8 + (size_t)cap * 4), val + e0, nent * 8u, bar);
+        }
         if (++s == nstages) { s = 0; ph ^= 1; }
         c = cn; s0 = n0; s1 = n1; e0 = f0; e1 = f1;
       }
@@ -325,6 +330,25 @@ __global__ void __launch_bounds__(256) k_sell_fill(const int *__restrict__ rowpt
   }
 }
 
+/* inverse of k_sell_fill: the CSR (col,val) arrays from the SELL-32 copy and the row pointer (the CSR copy is dropped once
+   the SELL copy exists; the transpose builders of the host layer ask for it back through b2k_csr_arrays) */
+__global__ void __launch_bounds__(256) k_sell_to_csr(const int *__restrict__ rowptr, int64_t nrows, int64_t nslices, const int64_t *__restrict__ sl_off,
+                                                      const int *__restrict__ scol, const double *__restrict__ sval, int *__restrict__ colidx,
+                                                      double *__restrict__ val)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slice >= nslices) return;
+  const int64_t off = sl_off[slice];
+  const int64_t row = slice * 32 + lane;
+  if (row >= nrows) return;
+  const int a = rowptr[row], len = rowptr[row + 1] - a;
+  for (int w = 0; w < len; w++) {
+    colidx[a + w] = scol[off + 32 * w + lane];
+    val[a + w] = sval[off + 32 * w + lane];
+  }
+}
+
 static int g_sell_mode = -1;      /* env B2K_SPMV_SELL: 0 never, 1 (default) when padding <= 25 %, 2 always */
 static int sell_mode(void)
 {
@@ -392,6 +416,28 @@ static int build_sell(b2k_ctx ctx, b2k_csr A)
   free(hoff);
   free(hchunk);
   A->nslices = ns; A->sell_elems = tot;
+  /* the matrix is stored once: the SELL copy is what every product reads, so the CSR (col,val) arrays go (the row pointer
+     stays: 4 B/row); b2k_csr_arrays brings them back on demand.  env B2K_CSR_KEEP=1 keeps both (debugging). */
+  const char *keep = getenv("B2K_CSR_KEEP");
+  if (!(keep && keep[0] == '1')) {
+    cudaFree(A->colidx); cudaFree(A->val);
+    A->colidx = NULL; A->val = NULL;
+    A->csr_dropped = 1;
+  }
+  return B2K_OK;
+}
+
+/* bring the CSR (col,val) arrays back when they were dropped */
+static int csr_restore(b2k_csr A)
+{
+  if (!A->csr_dropped) return B2K_OK;
+  b2k_ctx ctx = A->ctx;
+  CK(cudaMalloc(&A->colidx, sizeof(int) * (size_t)(A->nnz ? A->nnz : 1)));
+  CK(cudaMalloc(&A->val, sizeof(double) * (size_t)(A->nnz ? A->nnz : 1)));
+  const unsigned grid = (unsigned)((A->nslices + 7) / 8);
+  k_sell_to_csr<<<grid, 256, 0, ctx->stream>>>(A->rowptr, A->nrows, A->nslices, A->sl_off, A->sl_col, A->sl_val, A->colidx, A->val);
+  CKLAUNCH(ctx);
+  A->csr_dropped = 0;
   return B2K_OK;
 }
 
@@ -486,7 +532,7 @@ extern "C" int b2k_csr_create(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, i
   CK(cudaSetDevice(ctx->device));
   b2k_csr A = (b2k_csr)calloc(1, sizeof(*A));
   if (!A) return B2K_ERR_MEM;
-  A->nrows = nrows; A->ncols_local = ncols_local; A->nghost = nghost;
+  A->nrows = nrows; A->ncols_local = ncols_local; A->nghost = nghost; A->ctx = ctx;
   A->nnz = nrows ? rowptr_host[nrows] : 0;
   CK(cudaMalloc(&A->rowptr, sizeof(int) * (size_t)(nrows + 1)));
   CK(cudaMalloc(&A->colidx, sizeof(int) * (size_t)(A->nnz ? A->nnz : 1)));
@@ -510,7 +556,7 @@ extern "C" int b2k_csr_adopt(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, in
   ARGCHK(nrows >= 0 && nrows < 2147483647LL && nnz < 2147483647LL, "sizes must fit int32");
   b2k_csr A = (b2k_csr)calloc(1, sizeof(*A));
   if (!A) return B2K_ERR_MEM;
-  A->nrows = nrows; A->ncols_local = ncols_local; A->nghost = nghost; A->nnz = nnz;
+  A->nrows = nrows; A->ncols_local = ncols_local; A->nghost = nghost; A->nnz = nnz; A->ctx = ctx;
   A->rowptr = rowptr; A->colidx = colidx; A->val = val;
   int *rp = (int *)malloc(sizeof(int) * (size_t)(nrows + 1));
   if (!rp) return B2K_ERR_MEM;
@@ -544,9 +590,46 @@ extern "C" int b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncl, int64_t *ng
 
 extern "C" int b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val)
 {
+  if (colidx || val) { const int rc = csr_restore(A); if (rc) return rc; }
   if (rowptr) *rowptr = A->rowptr;
   if (colidx) *colidx = A->colidx;
   if (val) *val = A->val;
+  return B2K_OK;
+}
+
+/* the caller is done with the arrays b2k_csr_arrays lent: drop the CSR copy again when a SELL copy serves the products */
+extern "C" int b2k_csr_release_arrays(b2k_csr A)
+{
+  if (!A || A->csr_dropped || A->nslices == 0) return B2K_OK;
+  const char *keep = getenv("B2K_CSR_KEEP");
+  if (keep && keep[0] == '1') return B2K_OK;
+  CK(cudaStreamSynchronize(A->ctx->stream));
+  cudaFree(A->colidx); cudaFree(A->val);
+  A->colidx = NULL; A->val = NULL;
+  A->csr_dropped = 1;
+  return B2K_OK;
+}
+
+/* HBM bytes held by the matrix (all copies) */
+extern "C" int b2k_csr_bytes(b2k_csr A, int64_t *bytes)
+{
+  int64_t b = 4 * (A->nrows + 1) + 4 * (int64_t)(A->nblk + 1);
+  if (!A->csr_dropped) b += 12 * (A->nnz ? A->nnz : 1);
+  if (A->nslices) b += 12 * A->sell_elems + 8 * (A->nslices + 4) + 4 * (int64_t)(A->nchunks + 1);
+  *bytes = b;
+  return B2K_OK;
+}
+
+extern "C" int b2k_csr_last_kernel(b2k_csr A, int *which)
+{
+  *which = A ? A->last_kernel : 0;
+  return B2K_OK;
+}
+
+static int g_pipe_min_chunks = -2;   /* -2: read env B2K_SPMV_PIPE_MIN_CHUNKS once; -1: default (4 chunks per SM); >= 0: explicit */
+extern "C" int b2k_spmv_set_pipe_min_chunks(int min_chunks)
+{
+  g_pipe_min_chunks = min_chunks < 0 ? -1 : min_chunks;
   return B2K_OK;
 }
 
@@ -554,6 +637,7 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
 {
   if (A->nrows == 0) return B2K_OK;
   ARGCHK(x != y, "SpMV cannot run in place");
+  if (!(A->nslices > 0 && sell_mode()) && A->csr_dropped) { const int rc = csr_restore(A); if (rc) return rc; }   /* CSR-stream forced */
   /* algorithmic bytes of the CSR product whichever storage runs: the SELL copy moves 12 B per stored
      entry (padding included) and no row pointers */
   PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 4.0 * (double)(A->nrows + 1) + 8.0 * (double)(A->ncols_local + A->nghost) + 8.0 * (double)A->nrows);
@@ -567,13 +651,20 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
       if (ce != cudaSuccess) { cudaGetLastError(); pipe_mode = 0; }
     }
   }
+  if (g_pipe_min_chunks == -2) {
+    const char *e = getenv("B2K_SPMV_PIPE_MIN_CHUNKS");
+    g_pipe_min_chunks = e ? atoi(e) : -1;
+  }
+  const int min_chunks = g_pipe_min_chunks >= 0 ? (g_pipe_min_chunks > 0 ? g_pipe_min_chunks : 1) : 4 * ctx->sm_count;
   int sp_stages = 0;
   size_t sp_shm = 0;
-  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= 4 * ctx->sm_count) {
+  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= min_chunks) {
     sp_stages = (int)(SP_SMEM_BUDGET / SP_STAGE_BYTES((size_t)A->sp_cap));
     if (sp_stages > SP_STAGES) sp_stages = SP_STAGES;
     sp_shm = 128 + (size_t)sp_stages * SP_STAGE_BYTES((size_t)A->sp_cap);
   }
+  A->last_kernel = (sp_stages >= 2) ? (A->nghost > 0 ? B2K_SPMV_KERNEL_SELL_PIPE_GHOST : B2K_SPMV_KERNEL_SELL_PIPE)
+                                     : ((A->nslices > 0 && sell_mode()) ? B2K_SPMV_KERNEL_SELL : B2K_SPMV_KERNEL_CSR_STREAM);
   if (sp_stages >= 2 && A->nghost > 0)
     k_spmv_sell_pipe<true><<<ctx->sm_count, SP_THREADS, sp_shm, ctx->stream>>>(
         A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma,

@@ -21,7 +21,9 @@
 __device__ __forceinline__ double2 vq_ld2(const double *p)
 {
   double2 r;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  /* no .nc: Out may alias columns of In (BVMultInPlace) and the non-coherent path requires data that is read-only for
+     the whole kernel */
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
   return r;
 }
 

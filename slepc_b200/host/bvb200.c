@@ -421,6 +421,8 @@ PetscErrorCode BVCreate_B200(BV bv)
 {
   b2k_ctx ctx = CTX();
   PetscCheck(ctx, PETSC_ERR_ORDER, "BV type b200 needs a GPU context: call B2KInitialize() first (there is no CPU fallback)");
+  PetscCheck(bv->nc + bv->m <= B2K_MAX_COLUMNS, PETSC_ERR_SUP, "BV type b200 holds at most %d columns (constraints included), %d requested: "
+             "reduce ncv/mpd (EPS defaults to ncv = nev+500 for nev >= 500)", B2K_MAX_COLUMNS, bv->nc + bv->m);
   BV_B200 *d = (BV_B200 *)calloc(1, sizeof(*d));
   PetscCheck(d, PETSC_ERR_MEM, "out of memory");
   bv->data = d;

@@ -142,7 +142,7 @@ PetscErrorCode EPSSetInitialSpace(EPS eps, PetscInt n, Vec is[])
 static PetscErrorCode EPSCompare_Private(PetscScalar ar, PetscScalar ai, PetscScalar br, PetscScalar bi, PetscInt *res, void *ctx)
 {
   EPS eps = (EPS)ctx;
-  return eps->sc.fn(ar + eps->sc.sigma, ai, br + eps->sc.sigma, bi, res, eps->sc.ctx);
+  return eps->sc.fn(ar + eps->st->sigma, ai, br + eps->st->sigma, bi, res, eps->sc.ctx);   /* live shift (SlepcMap_ST): never stale after STSetShift */
 }
 
 PetscErrorCode EPSSetUp(EPS eps)
@@ -348,7 +348,7 @@ static PetscErrorCode EPSSortEigenvalues_Private(EPS eps, PetscInt n, PetscScala
     j = i + 1;
     if (im != 0) { i--; im = eigi[perm[i]]; }      /* complex eigenvalue */
     while (j < n) {
-      PetscCall(EPSCompare_Private(re - eps->sc.sigma, im, eigr[perm[j]] - eps->sc.sigma, eigi[perm[j]], &result, eps));
+      PetscCall(EPSCompare_Private(re - eps->st->sigma, im, eigr[perm[j]] - eps->st->sigma, eigi[perm[j]], &result, eps));
       if (result <= 0) break;
       if (!im) {
         if (eigi[perm[j]] == 0.0) { tmp = perm[j - 1]; perm[j - 1] = perm[j]; perm[j] = tmp; j++; }

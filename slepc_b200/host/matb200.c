@@ -115,6 +115,7 @@ static PetscErrorCode MatBuildLocalTranspose_B200CSR(Mat A)
   PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
   B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
   if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
+  B2KCall(b2k_csr_release_arrays(a->A));          /* the CSR copy was rebuilt from the SELL copy for this read only */
   for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
   for (PetscInt c = 0; c < nt; c++) trp[c + 2] += trp[c + 1];
   for (PetscInt r = 0; r < m; r++)
@@ -408,6 +409,7 @@ PetscErrorCode MatB200CSRTranspose(Mat A, Mat *At)
   PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
   B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
   if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
+  B2KCall(b2k_csr_release_arrays(a->A));          /* the CSR copy was rebuilt from the SELL copy for this read only */
   for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
   for (PetscInt c = 0; c < n; c++) trp[c + 2] += trp[c + 1];      /* trp[c+1] = start of column c (shifted by one) */
   for (PetscInt r = 0; r < m; r++)

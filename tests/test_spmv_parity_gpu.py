@@ -1,0 +1,281 @@
+"""Element-wise parity of the DEFAULT hot SpMV kernel — k_spmv_sell_pipe<false> and <true> (b2k_spmv.cu), the bulk-copy
+pipeline over the SELL-32 copy that PETSc's MatMult behind bvops.c:879 / stsolve.c:22 is replaced by — against independent
+answers, with the kernel that ran ASSERTED through b2k_csr_last_kernel:
+
+  * closed-form stencils  y = 2d x - (shifted copies of x)  evaluated by numpy in O(n) at the full sizes of BASELINE.json
+    (4096^2 = 16.8 M rows, 512^3 = 134 M rows) with hash-random x;
+  * a 512^3 slab with BOTH ghost planes (what a middle rank of an 8-GPU run multiplies): the <true> instantiation;
+  * scipy on a 1 M-row random matrix with 20 draws per row (with and without ghost columns) and on the Markov model m = 1200;
+  * small irregular matrices forced through the pipeline (b2k_spmv_set_pipe_min_chunks): widths > 8, empty rows, chunks made
+    only of empty slices (zero-byte stages), odd slice tails, ghost columns.
+
+Tolerance (written here, from the verdict): max|y - y_ref| <= 1e-13 * ||x||_inf * max nnz per row * max|a_ij|.
+Nothing here is skipped for lack of memory on a B200: a full-size test that cannot allocate FAILS.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import slepc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+K_CSR, K_SELL, K_PIPE, K_PIPE_GHOST = 1, 2, 3, 4
+
+
+def _check(rc):
+    from slepc_b200._b2k import check
+    check(rc)
+
+
+def _last_kernel(ctx, h):
+    w = ctypes.c_int()
+    _check(ctx.lib.b2k_csr_last_kernel(h, ctypes.byref(w)))
+    return w.value
+
+
+def _is_b200(ctx):
+    fr, to = ctypes.c_size_t(), ctypes.c_size_t()
+    _check(ctx.lib.b2k_mem_info(ctx.h, ctypes.byref(fr), ctypes.byref(to)))
+    return to.value >= 150 * 2 ** 30, fr.value
+
+
+def _need(ctx, gb):
+    """a full-size case needs `gb` GB of HBM: on a B200 (>= 150 GB) that is an assertion, elsewhere a skip"""
+    big, free = _is_b200(ctx)
+    if free >= gb * 2 ** 30:
+        return
+    if big:
+        pytest.fail(f"needs {gb} GB of free HBM but only {free / 2**30:.1f} GB are free on a B200: full-size parity must not be skipped")
+    pytest.skip(f"needs {gb} GB of free HBM (not a B200)")
+
+
+def _hash_x(ctx, n, row0=0, seed=7):
+    """hash-random x in [-1,1) generated on the device (bit-identical to oracle hash_uniform), returned as (device, host)"""
+    dx = ctx.empty(n)
+    _check(ctx.lib.b2k_set_random(ctx.h, dx.ptr, n, row0, seed))
+    return dx, dx.to_host()
+
+
+def _stencil_ref(xfull, dim, shape, p0, p1):
+    """rows of planes [p0,p1) of the d-dimensional Laplacian stencil applied to xfull (planes [p0-1 or 0, p1+1 or nx) given as
+    a (planes, ny, nz) array whose first plane is global plane q0); returns the flat y of the owned planes"""
+    nx, ny, nz = shape
+    q0 = max(p0 - 1, 0)
+    X = xfull.reshape(-1, ny, nz)
+    a, b = p0 - q0, p1 - q0                      # owned planes inside X
+    Y = (2.0 * dim) * X[a:b]
+    lo = X[a - 1:b - 1] if a > 0 else np.concatenate([np.zeros((1, ny, nz)), X[a:b - 1]])
+    Y -= lo
+    hi = X[a + 1:b + 1] if b < X.shape[0] else np.concatenate([X[a + 1:b], np.zeros((1, ny, nz))])
+    Y -= hi
+    if dim >= 2:
+        Y[:, 1:, :] -= X[a:b, :-1, :]
+        Y[:, :-1, :] -= X[a:b, 1:, :]
+    if dim >= 3:
+        Y[:, :, 1:] -= X[a:b, :, :-1]
+        Y[:, :, :-1] -= X[a:b, :, 1:]
+    return Y.ravel()
+
+
+def _run_laplacian(ctx, dim, shape, p0, p1, expect, seed=7):
+    nx, ny, nz = shape
+    plane = ny * nz
+    row0, nrows = p0 * plane, (p1 - p0) * plane
+    h = ctypes.c_void_p()
+    glo, ghi = ctypes.c_int64(), ctypes.c_int64()
+    _check(ctx.lib.b2k_csr_laplacian(ctx.h, dim, nx, ny, nz, row0, nrows, ctypes.byref(h), ctypes.byref(glo), ctypes.byref(ghi)))
+    q0, q1 = max(p0 - 1, 0), min(p1 + 1, nx)
+    dxall, xall = _hash_x(ctx, (q1 - q0) * plane, q0 * plane, seed)       # owned planes + the neighbour planes, one hash stream
+    off = (p0 - q0) * plane
+    dg = ctx.empty(max(glo.value + ghi.value, 1))
+    if glo.value:
+        _check(ctx.lib.b2k_d2d(ctx.h, dg.ptr, dxall.ptr, 8 * plane))
+    if ghi.value:
+        _check(ctx.lib.b2k_d2d(ctx.h, dg.at(glo.value), dxall.at(off + nrows), 8 * plane))
+    dy = ctx.empty(nrows)
+    _check(ctx.lib.b2k_csr_spmv(ctx.h, h, dxall.at(off), dg.ptr, dy.ptr))
+    ctx.sync()
+    kern = _last_kernel(ctx, h)
+    y = dy.to_host()
+    for d in (dy, dg, dxall):
+        d.free()
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    ref = _stencil_ref(xall, dim, shape, p0, p1)
+    tol = 1e-13 * np.abs(xall).max() * (2 * dim + 1) * (2.0 * dim)
+    err = float(np.abs(y - ref).max())
+    assert kern == expect, f"dispatch ran kernel {kern}, the test is meant to cover {expect}"
+    assert err <= tol, (err, tol)
+    return err
+
+
+# ---- full-size closed-form checks (BASELINE.json configs[1], configs[2]) -------------------------------------------------
+def test_pipe_full_size_2d_4096(ctx):
+    _need(ctx, 4)
+    _run_laplacian(ctx, 2, (4096, 4096, 1), 0, 4096, K_PIPE)
+
+
+def test_pipe_full_size_3d_512(ctx):
+    _need(ctx, 20)
+    _run_laplacian(ctx, 3, (512, 512, 512), 0, 512, K_PIPE)
+
+
+@pytest.mark.parametrize("p0,p1", [(64, 128), (192, 448)], ids=["slab_of_8", "slab_of_2_wide"])
+def test_pipe_ghost_slab_3d_512_both_planes(ctx, p0, p1):
+    """a middle slab of the 512^3 grid (what rank r of an N-GPU run owns): lower AND upper ghost plane, <GHOST=true>"""
+    _need(ctx, 12)
+    _run_laplacian(ctx, 3, (512, 512, 512), p0, p1, K_PIPE_GHOST)
+
+
+@pytest.mark.parametrize("p0,p1", [(0, 2048), (2048, 4096), (1024, 3072)], ids=["first", "last", "middle"])
+def test_pipe_ghost_slab_2d_4096(ctx, p0, p1):
+    _run_laplacian(ctx, 2, (4096, 4096, 1), p0, p1, K_PIPE_GHOST)
+
+
+# ---- scipy comparisons at sizes that reach the pipeline by themselves -----------------------------------------------------
+def _spmv_host_csr(ctx, rp, ci, va, nrows, ncl, x, xg=None, sigma=None):
+    h = ctypes.c_void_p()
+    ng = 0 if xg is None else len(xg)
+    rp = np.ascontiguousarray(rp, dtype=np.int32); ci = np.ascontiguousarray(ci, dtype=np.int32); va = np.ascontiguousarray(va, dtype=np.float64)
+    _check(ctx.lib.b2k_csr_create(ctx.h, nrows, ncl, ng, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h)))
+    dx = ctx.to_device(np.ascontiguousarray(x))
+    dg = ctx.to_device(np.ascontiguousarray(xg)) if ng else None
+    dy = ctx.empty(max(nrows, 1))
+    if sigma is None:
+        _check(ctx.lib.b2k_csr_spmv(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr))
+    else:
+        _check(ctx.lib.b2k_csr_spmv_shift(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr, sigma))
+    ctx.sync()
+    kern = _last_kernel(ctx, h)
+    y = dy.to_host()[:nrows]
+    nb = ctypes.c_int64()
+    _check(ctx.lib.b2k_csr_bytes(h, ctypes.byref(nb)))
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    for d in (dx, dg, dy):
+        if d is not None:
+            d.free()
+    return y, kern, nb.value
+
+
+@pytest.mark.parametrize("ghost", [False, True], ids=["owned_columns", "ghost_columns"])
+def test_pipe_random_1m_rows_20_per_row_vs_scipy(ctx, ghost):
+    import scipy.sparse as sp
+    from slepc_b200 import matgen
+    M, N = 1 << 20, 900001
+    rp, ci, va = matgen.random_sparse_rows(M, N, 20, seed=5)
+    A = sp.csr_matrix((va, ci, rp), shape=(M, N))
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, N)
+    ncl = 600000 if ghost else N
+    y, kern, nbytes = _spmv_host_csr(ctx, rp, ci, va, M, ncl, x[:ncl], x[ncl:] if ghost else None)
+    ref = A @ x
+    nnz_row = int(np.diff(rp).max())
+    tol = 1e-13 * np.abs(x).max() * nnz_row * np.abs(va).max()
+    assert kern == (K_PIPE_GHOST if ghost else K_PIPE)
+    assert np.abs(y - ref).max() <= tol
+    # the matrix is stored ONCE (SELL copy + row pointer), not CSR + SELL
+    assert nbytes < 1.3 * 12 * A.nnz + 16 * M
+
+
+def test_pipe_markov_m1200_vs_scipy(ctx):
+    import scipy.sparse as sp
+    from slepc_b200 import matgen
+    m = 1200
+    N = matgen.markov_size(m)
+    rp, ci, va = matgen.markov_rows(m)
+    A = sp.csr_matrix((va, ci, rp), shape=(N, N))
+    x = np.random.default_rng(4).uniform(-1, 1, N)
+    y, kern, _ = _spmv_host_csr(ctx, rp, ci, va, N, N, x)
+    assert kern == K_PIPE
+    assert np.abs(y - A @ x).max() <= 1e-13 * 5
+    y, kern, _ = _spmv_host_csr(ctx, rp, ci, va, N, N, x, sigma=0.3)      # STSHIFT operator A - sigma I
+    assert kern == K_PIPE
+    assert np.abs(y - (A @ x - 0.3 * x)).max() <= 1e-13 * 5
+
+
+# ---- small irregular matrices forced through the pipeline -------------------------------------------------------------------
+def _irregular(kind, rng):
+    import scipy.sparse as sp
+    if kind == "wide_rows":                         # widths 9..40: beyond the width-specialised fast path (<= 8)
+        n = 6000
+        lens = rng.integers(9, 41, n)
+    elif kind == "empty_rows":
+        n = 7003                                    # odd slice tail: 7003 = 218 slices + 27 rows
+        lens = rng.integers(0, 7, n)
+        lens[rng.random(n) < 0.4] = 0
+    elif kind == "empty_chunks":                    # 4096 leading rows and a 2048-row band without entries: whole chunks of empty slices
+        n = 12000
+        lens = rng.integers(1, 6, n)
+        lens[:4096] = 0
+        lens[8192:10240] = 0
+    elif kind == "mixed_widths":                    # neighbouring slices of different widths, some pairs equal, some not
+        n = 9000
+        lens = np.repeat(rng.integers(1, 13, (n + 31) // 32), 32)[:n]
+        lens[::7] = np.maximum(lens[::7] - 1, 0)
+    elif kind == "one_slice_pair":
+        n = 64
+        lens = rng.integers(1, 5, n)
+    else:
+        raise ValueError(kind)
+    ncols = n + 500
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(ncols, l, replace=False)) for l in lens]) if rp[-1] else np.zeros(0, np.int64)
+    va = rng.standard_normal(int(rp[-1]))
+    A = sp.csr_matrix((va, ci, rp), shape=(n, ncols))
+    return A
+
+
+@pytest.mark.parametrize("ghost", [False, True], ids=["noghost", "ghost"])
+@pytest.mark.parametrize("kind", ["wide_rows", "empty_rows", "empty_chunks", "mixed_widths", "one_slice_pair"])
+def test_pipe_forced_on_small_irregular(ctx, kind, ghost):
+    rng = np.random.default_rng({"wide_rows": 11, "empty_rows": 12, "empty_chunks": 13, "mixed_widths": 14, "one_slice_pair": 15}[kind])
+    A = _irregular(kind, rng)
+    n, ncols = A.shape
+    x = rng.standard_normal(ncols)
+    ncl = n if ghost else ncols
+    _check(ctx.lib.b2k_spmv_set_pipe_min_chunks(1))
+    try:
+        y, kern, _ = _spmv_host_csr(ctx, A.indptr, A.indices, A.data, n, ncl, x[:ncl], x[ncl:] if ghost else None)
+        ys, kern_s, _ = _spmv_host_csr(ctx, A.indptr, A.indices, A.data, n, ncl, x[:ncl], x[ncl:] if ghost else None, sigma=-1.25)
+    finally:
+        _check(ctx.lib.b2k_spmv_set_pipe_min_chunks(-1))
+    ref = A @ x
+    assert kern == (K_PIPE_GHOST if ghost else K_PIPE) and kern_s == kern
+    tol = 1e-13 * np.abs(x).max() * max(int(np.diff(A.indptr).max()), 1) * max(np.abs(A.data).max(), 1.0)
+    assert np.abs(y - ref).max() <= tol
+    assert np.abs(ys - (ref + 1.25 * x[:n])).max() <= tol + 1e-15 * np.abs(x).max()
+
+
+def test_small_matrix_keeps_the_small_kernel(ctx):
+    """below the chunk threshold the plain SELL kernel runs (the pipeline needs >= 4 chunks per SM to fill its ring)"""
+    A = O.laplacian_2d(64, 64).tocsr()
+    x = np.random.default_rng(1).standard_normal(A.shape[1])
+    y, kern, _ = _spmv_host_csr(ctx, A.indptr, A.indices, A.data, A.shape[0], A.shape[1], x)
+    assert kern == K_SELL
+    assert np.abs(y - A @ x).max() <= 1e-13 * 5 * 4
+
+
+def test_csr_arrays_come_back_after_the_drop(ctx):
+    """b2k_csr_arrays rebuilds the CSR (col,val) copy from the SELL copy bit for bit; b2k_csr_release_arrays drops it again"""
+    A = O.markov_model(120).tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    h = ctypes.c_void_p()
+    rp = A.indptr.astype(np.int32); ci = A.indices.astype(np.int32); va = A.data.astype(np.float64)
+    _check(ctx.lib.b2k_csr_create(ctx.h, n, n, 0, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h)))
+    b0, b1 = ctypes.c_int64(), ctypes.c_int64()
+    _check(ctx.lib.b2k_csr_bytes(h, ctypes.byref(b0)))
+    prp, pci, pva = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    _check(ctx.lib.b2k_csr_arrays(h, ctypes.byref(prp), ctypes.byref(pci), ctypes.byref(pva)))
+    _check(ctx.lib.b2k_csr_bytes(h, ctypes.byref(b1)))
+    assert b1.value == b0.value + 12 * A.nnz
+    gci, gva = np.empty(A.nnz, np.int32), np.empty(A.nnz)
+    _check(ctx.lib.b2k_d2h(ctx.h, gci.ctypes.data, pci, gci.nbytes))
+    _check(ctx.lib.b2k_d2h(ctx.h, gva.ctypes.data, pva, gva.nbytes))
+    assert np.array_equal(gci, ci) and np.array_equal(gva, va)
+    _check(ctx.lib.b2k_csr_release_arrays(h))
+    _check(ctx.lib.b2k_csr_bytes(h, ctypes.byref(b1)))
+    assert b1.value == b0.value
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
