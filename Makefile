@@ -23,7 +23,11 @@ ORACLE_LIB := oracle/_build/liboraclecpu.so
 endif
 EXSRC     := $(wildcard examples/*.c)
 EXBIN     := $(patsubst examples/%.c,examples/bin/%,$(EXSRC))
-all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so $(ORACLE_LIB) $(EXBIN)
+all: $(LIBDIR)/libb200krylov.so $(LIBDIR)/libb2kslepc.so $(ORACLE_LIB) $(EXBIN) baseline/libbase.so
+
+# library baseline (cuBLAS / cuSPARSE in the reference's schedule) timed by bench.py next to the product; not part of it
+baseline/libbase.so: baseline/libbase.cu
+	$(NVCC) $(ARCH) -O3 -std=c++17 -Xcompiler -fPIC -shared -o $@ $< -lcublas -lcusparse -Xlinker -rpath=/usr/local/cuda/lib64
 
 $(LIBDIR)/libb200krylov.so: $(KSRC) $(KHDR)
 	@mkdir -p $(LIBDIR)
@@ -51,6 +55,6 @@ check: all
 kernels: $(LIBDIR)/libb200krylov.so
 
 clean:
-	rm -f $(LIBDIR)/*.so oracle/_build/*.so examples/bin/*
+	rm -f $(LIBDIR)/*.so oracle/_build/*.so examples/bin/* baseline/libbase.so
 
 .PHONY: all clean kernels examples check

@@ -207,6 +207,7 @@ int  b2k_comm_barrier(b2k_comm comm);
 int  b2k_comm_p2p_handle(b2k_comm comm, void *handle_out_host);
 int  b2k_comm_p2p_open(b2k_comm comm, const void *all_handles_host /* size x 64 bytes, rank order */);
 int  b2k_comm_p2p_close(b2k_comm comm);           /* back to NCCL for the reductions (mappings are released by destroy) */
+int  b2k_comm_p2p_resume(b2k_comm comm);          /* mailboxes on again after a close (collective)                      */
 int  b2k_comm_p2p_enabled(b2k_comm comm);
 int  b2k_comm_reduce_scope(b2k_comm comm, int global_on, int *fused_out);
 int  b2k_comm_p2p_error(b2k_comm comm, int *flag_out);

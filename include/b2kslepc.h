@@ -100,7 +100,8 @@ PetscErrorCode B2KCommReset(void);
    every Gram-Schmidt sweep.  Handle: 64 bytes per rank (include/b2k.h b2k_comm_p2p_*), all-gathered by the launcher. */
 PetscErrorCode B2KCommP2PHandle(void *handle_out /* 64 bytes */);
 PetscErrorCode B2KCommP2POpen(const void *all_handles /* size x 64 bytes in rank order */);
-PetscErrorCode B2KCommDisableP2P(void);
+PetscErrorCode B2KCommDisableP2P(void);           /* reductions through ncclAllReduce again (collective)                   */
+PetscErrorCode B2KCommEnableP2P(void);            /* back to the mapped mailboxes after a B2KCommDisableP2P (collective)   */
 /* reductions of the BV kernels issued between Begin(global) and End are sums over the ranks when *fused comes back true */
 PetscErrorCode B2KCommReduceScope(B2KComm comm, PetscBool global, PetscBool *fused);
 PetscErrorCode B2KCommGetRank(B2KComm comm, int *rank, int *size);

@@ -92,6 +92,7 @@ SIGNATURES = {
     "b2k_comm_p2p_handle": [c_vp, c_vp],
     "b2k_comm_p2p_open": [c_vp, c_vp],
     "b2k_comm_p2p_close": [c_vp],
+    "b2k_comm_p2p_resume": [c_vp],
     "b2k_comm_p2p_enabled": [c_vp],
     "b2k_comm_reduce_scope": [c_vp, c_int, ctypes.POINTER(c_int)],
     "b2k_comm_p2p_error": [c_vp, ctypes.POINTER(c_int)],

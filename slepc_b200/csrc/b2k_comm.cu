@@ -169,6 +169,18 @@ extern "C" int b2k_comm_p2p_close(b2k_comm c)
   return B2K_OK;
 }
 
+/* after b2k_comm_p2p_close: route the reductions through the (still mapped) mailboxes again.  Collective: every rank toggles at
+   the same point of the program (tests and bench compare the two transports on the same data). */
+extern "C" int b2k_comm_p2p_resume(b2k_comm c)
+{
+  ARGCHK(c && c->box_local && c->xg.box[c->rank] == c->box_local, "b2k_comm_p2p_open() has not mapped the mailboxes");
+  CK(cudaStreamSynchronize(c->ctx->stream));
+  c->p2p_open = 1;
+  c->ctx->xg = &c->xg;
+  c->ctx->xg_on = 0;
+  return B2K_OK;
+}
+
 extern "C" int b2k_comm_p2p_enabled(b2k_comm c) { return (c && c->p2p_open) ? 1 : 0; }
 
 /* on != 0: reductions of the BV kernels launched from now on are sums over the ranks (collective: every rank must issue

@@ -101,6 +101,13 @@ PetscErrorCode B2KCommDisableP2P(void)
   return PETSC_SUCCESS;
 }
 
+PetscErrorCode B2KCommEnableP2P(void)
+{
+  PetscCheck(g_world.kind == 1 && g_world.nccl, PETSC_ERR_ORDER, "B2KCommInitNCCL() and B2KCommP2POpen() come first");
+  B2KCall(b2k_comm_p2p_resume(g_world.nccl));
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode B2KCommReduceScope(B2KComm comm, PetscBool global, PetscBool *fused)
 {
   int f = 0;

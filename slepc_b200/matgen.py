@@ -152,3 +152,14 @@ def laplacian_rows(dim, nx, ny=1, nz=1, r0=0, r1=None):
     rowptr = np.zeros(g.size + 1, dtype=np.int32)
     np.cumsum(valid.sum(axis=1), out=rowptr[1:])
     return rowptr, cols[valid].astype(np.int32), np.ascontiguousarray(vals[valid])
+
+
+def hash_uniform(idx, seed):
+    """uniform [-1,1) value of global index `idx` (uint64 array) under `seed`: the splitmix64-finaliser hash of b2k_set_random
+    (b2k_bv.cu b2k_hash_uniform) evaluated on the host, bit for bit — lets a caller reproduce a device-generated vector"""
+    with np.errstate(over="ignore"):
+        x = (np.asarray(idx, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed) * np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return 2.0 * ((x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)) - 1.0

@@ -21,8 +21,8 @@ ctx = _b2k.Context(0)
 rng = np.random.default_rng(5)
 for (n, k, s, e) in [(4099, 25, 0, 13), (100003, 32, 0, 16), (70000, 32, 3, 32), (4096, 8, 0, 8), (50000, 17, 5, 9), (1 << 22, 25, 0, 13)]:
     ld = n + (n %% 2)
-    H = rng.standard_normal((ld, k)); H[n:] = 0.0
-    Q = rng.standard_normal((k, k))
+    H = np.asfortranarray(rng.standard_normal((ld, k))); H[n:] = 0.0      # column-major, as the basis lies in HBM
+    Q = np.asfortranarray(rng.standard_normal((k, k)))
     dV, dQ = ctx.to_device(H), ctx.to_device(Q)
     check(ctx.lib.b2k_mult_inplace(ctx.h, dV.ptr, ld, n, k, s, e, dQ.ptr, k, 0))
     G = dV.to_host((ld, k))

@@ -236,11 +236,13 @@ def test_pipe_forced_on_small_irregular(ctx, kind, ghost):
     x = rng.standard_normal(ncols)
     ncl = n if ghost else ncols
     _check(ctx.lib.b2k_spmv_set_pipe_min_chunks(1))
+    _check(ctx.lib.b2k_spmv_set_sell(2))            # SELL copy whatever the padding (the default keeps CSR-stream above 25 % padding)
     try:
         y, kern, _ = _spmv_host_csr(ctx, A.indptr, A.indices, A.data, n, ncl, x[:ncl], x[ncl:] if ghost else None)
         ys, kern_s, _ = _spmv_host_csr(ctx, A.indptr, A.indices, A.data, n, ncl, x[:ncl], x[ncl:] if ghost else None, sigma=-1.25)
     finally:
         _check(ctx.lib.b2k_spmv_set_pipe_min_chunks(-1))
+        _check(ctx.lib.b2k_spmv_set_sell(1))
     ref = A @ x
     assert kern == (K_PIPE_GHOST if ghost else K_PIPE) and kern_s == kern
     tol = 1e-13 * np.abs(x).max() * max(int(np.diff(A.indptr).max()), 1) * max(np.abs(A.data).max(), 1.0)
