@@ -298,6 +298,11 @@ def run_b200(args, wl):
         lib.b2k_ctx_launches(ctx, ctypes.byref(n))
         return n.value
 
+    def syncs():
+        n = ctypes.c_uint64()
+        lib.b2k_ctx_syncs(ctx, ctypes.byref(n))
+        return n.value
+
     def hbm_used():
         fr, to = ctypes.c_size_t(), ctypes.c_size_t()
         lib.b2k_mem_info(ctx, ctypes.byref(fr), ctypes.byref(to))
@@ -320,7 +325,7 @@ def run_b200(args, wl):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     _b2k.check(lib.b2k_prof_enable(ctx, 1))
-    m0, l0, g0 = bv.counters()[1], launches(), bv.counters()[0]
+    m0, l0, g0, s0 = bv.counters()[1], launches(), bv.counters()[0], syncs()
     _b2k.check(lib.b2k_timer_start(ctx))
     done = 0
     for _ in range(args.steps):
@@ -332,6 +337,7 @@ def run_b200(args, wl):
     steps = bv.counters()[1] - m0
     gs_passes = bv.counters()[0] - g0
     nl = launches() - l0
+    nsync = syncs() - s0 - 1                      # the timer's own wait is not the path's
     t_ms = allmax(ms.value)
     prof = {}
     for cid, name in enumerate(KCLASS):
@@ -426,14 +432,15 @@ def run_b200(args, wl):
         S.EPSSetDimensions(et.h, 20, 64, SL.PETSC_DETERMINE)
         S.EPSSetTolerances(et.h, TOL, SL.PETSC_CURRENT)
         barrier()
+        s0, l0 = syncs(), launches()
         t0 = time.perf_counter()
         et.solve()
         barrier()
         dt = allmax(time.perf_counter() - t0)
         nst = et.bv().counters()[1]
-        lat = {"workload": "2-D Laplacian 1024x1024 (global, split over the ranks), nev=20 ncv=64: launch/latency-bound regime",
-               "seconds": dt, "restarts": et.its, "nconv": et.nconv, "lanczos_steps": nst, "us_per_lanczos_step": 1e6 * dt / max(nst, 1),
-               "max_rel_residual": max(et.error(i) for i in range(et.nconv)) if et.nconv else None}
+        lat = {"host_syncs_per_lanczos_step": (syncs() - s0) / max(nst, 1), "kernel_launches_per_lanczos_step": (launches() - l0) / max(nst, 1),"workload": "2-D Laplacian 1024x1024 (global, split over the ranks), nev=20 ncv=64: launch/latency-bound regime",
+               "seconds": dt, "restarts": et.its, "nconv": et.nconv, "lanczos_steps": nst, "us_per_lanczos_step": 1e6 * dt / max(nst, 1)}
+        lat["max_rel_residual"] = max(et.error(i) for i in range(et.nconv)) if et.nconv else None
         et.destroy()
         Mt.destroy()
 
@@ -531,7 +538,8 @@ def run_b200(args, wl):
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "lanczos_steps": steps, "lanczos_steps_per_s": steps / (t_ms / 1e3), "gs_passes_per_step": gs_passes / max(steps, 1),
-            "seconds_per_restart_cycle": t_ms / 1e3 / args.steps,
+            "seconds_per_restart_cycle": t_ms / 1e3 / args.steps, "host_syncs_per_lanczos_step": nsync / max(steps, 1),
+            "kernel_launches_per_lanczos_step": nl / max(steps, 1),
             "hbm_bytes_per_gpu": {"matrix": hbm_matrix, "matrix_plus_basis_and_scratch": hbm_solver,
                                   "note": "cudaMemGetInfo deltas; the matrix is stored once (SELL-32 copy + row pointer)"},
             "kernels": kernels, "gs_sweeps_gbs": (gs_bytes / gs_ms / 1e6) if gs_ms else None,

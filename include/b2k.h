@@ -50,6 +50,7 @@ int  b2k_ctx_sync(b2k_ctx ctx);
 void *b2k_ctx_stream(b2k_ctx ctx);                       /* cudaStream_t */
 int  b2k_ctx_sm_count(b2k_ctx ctx);
 int  b2k_ctx_launches(b2k_ctx ctx, uint64_t *count);     /* kernels launched through this ctx */
+int  b2k_ctx_syncs(b2k_ctx ctx, uint64_t *count);        /* host waits on the stream (b2k_ctx_sync + blocking copies) */
 int  b2k_malloc(b2k_ctx ctx, void **dptr, size_t bytes);
 int  b2k_free(b2k_ctx ctx, void *dptr);
 int  b2k_memset0(b2k_ctx ctx, void *dptr, size_t bytes);
@@ -128,11 +129,16 @@ int  b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int 
    folded in (used when no refinement pass is expected)                                              */
 int  b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w,
                         const double *cin, double *nrm2_out);
+/* b2k_gs_update_norm launched speculatively: every CTA evaluates the DGKS refinement criterion of bvorthog.c:180 from two device
+   scalars (onrm2 = w^T w before the previous pass, nrm2 = ||w||^2 after it) and the sweep runs only if
+   nrm != 0 && nrm < eta*onrm — the host learns the outcome of BOTH passes from one read (one synchronisation per column) */
+int  b2k_gs_update_norm_gated(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                              double *nrm2_out, const double *onrm2, const double *nrm2, double eta);
 /* x *= 1/sqrt(sumsq[0]) guarded (no-op if sumsq is 0 or 1): normalisation with the norm still on
    the device                                  — BVOrthonormalizeColumn bvorthog.c:417-422        */
 int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
 /* implementation of the update sweeps (b2k_multvec, b2k_gs_update_norm, b2k_gs_update_dot); env B2K_GS_FUSED:
-   0 generic kernels, two sweeps for update+dot; 1 register-tile single sweep; 2 1-D bulk-copy staged single sweep;
+   0 generic kernels, two sweeps for update+dot; 1 register-tile single sweep;
    3 (default) 2-D tensor-map (TMA) pipelined single sweep, register tile for k <= 4 or fewer than 4096 rows       */
 int  b2k_gs_set_fused(int mode);
 

@@ -26,6 +26,7 @@ SIGNATURES = {
     "b2k_ctx_sync": [c_vp],
     "b2k_ctx_sm_count": [c_vp],
     "b2k_ctx_launches": [c_vp, ctypes.POINTER(c_u64)],
+    "b2k_ctx_syncs": [c_vp, ctypes.POINTER(c_u64)],
     "b2k_ctx_copy_bytes": [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)],
     "b2k_prof_enable": [c_vp, c_int],
     "b2k_prof_get": [c_vp, c_int, ctypes.POINTER(c_u64), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
@@ -58,6 +59,7 @@ SIGNATURES = {
     "b2k_gs_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     "b2k_gs_update_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
     "b2k_gs_update_norm": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
+    "b2k_gs_update_norm_gated": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl],
     "b2k_scale_rsqrt": [c_vp, c_vp, c_i64, c_vp],
     "b2k_gs_set_fused": [c_int],
     "b2k_spmv_set_sell": [c_int],

@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *__rest
 template <bool VEC2, bool NRM>
 __global__ void __launch_bounds__(256) k_multvec(const double *__restrict__ V, int64_t ld, int64_t n, int k, double alpha,
                                                   double beta, double *__restrict__ y, const double *__restrict__ q,
-                                                  double *__restrict__ part, int pstride, int pcol)
+                                                  double *__restrict__ part, int pstride, int pcol, const b2k_gate_s gate)
 {
+  if (b2k_gate_closed(gate)) return;
   extern __shared__ double qs[];
   for (int i = threadIdx.x; i < k; i += blockDim.x) qs[i] = q[i];
   __syncthreads();
@@ -531,8 +532,9 @@ extern "C" int b2k_gs_dot(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
 }
 
 static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
-                          const double *q, double *nrm_out)
+                          const double *q, double *nrm_out, const b2k_gate_s *gatep = nullptr)
 {
+  const b2k_gate_s gate = gatep ? *gatep : b2k_gate_s{nullptr, nullptr, 0.0};
   ARGCHK(k >= 0 && k <= B2K_MAX_K, "k out of range");
   if (n == 0) {
     if (nrm_out && ctx->xg && ctx->xg_on) return b2k_launch_reduce_partials(ctx, 0, 1, 1, nrm_out);
@@ -546,37 +548,47 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
   const size_t shm = sizeof(double) * (size_t)(k > 0 ? k : 1);
   PROF_BEGIN(ctx, B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
   if (nrm_out) {
-    if (vec2) k_multvec<true, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
-    else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0);
+    if (vec2) k_multvec<true, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
+    else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
     PROF_END(ctx);
     CKLAUNCH(ctx);
     { const int rc_ = b2k_launch_reduce_partials(ctx, gx, 1, 1, nrm_out); if (rc_) return rc_; }
   } else {
-    if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
-    else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0);
+    if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0, gate);
+    else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0, gate);
     PROF_END(ctx);
     CKLAUNCH(ctx);
   }
   return B2K_OK;
 }
 
-int b2k_gs_update_dot_fused(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
-                            double *cout);   /* b2k_gs_fused.cu (TMA-staged) */
 int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
-                     const double *q, int dot, double *out);   /* b2k_gs_rt.cu (register tile) */
+                     const double *q, int dot, double *out, const b2k_gate_s *gate);   /* b2k_gs_rt.cu (register tile) */
 int b2k_gs_tma_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
-                      const double *q, int dot, double *out);  /* b2k_gs_tma.cu (2-D tensor-map pipeline) */
-int b2k_gs_fused_enabled(void);
+                      const double *q, int dot, double *out, const b2k_gate_s *gate);  /* b2k_gs_tma.cu (2-D tensor-map pipeline) */
+
+/* implementation of the update sweeps; env B2K_GS_FUSED: 0 generic kernels (two sweeps for update+dot), 1 register-tile single
+   sweep, 3 (default) 2-D tensor-map (TMA) pipelined single sweep with the register tile below 4096 rows or k <= 4 */
+static int g_fused_enabled = -1;
+static int b2k_gs_fused_enabled(void)
+{
+  if (g_fused_enabled < 0) {
+    const char *e = getenv("B2K_GS_FUSED");
+    g_fused_enabled = (e && (e[0] == '0' || e[0] == '1' || e[0] == '3')) ? e[0] - '0' : 3;
+  }
+  return g_fused_enabled;
+}
+extern "C" int b2k_gs_set_fused(int mode) { g_fused_enabled = (mode == 0 || mode == 1 || mode == 3) ? mode : 3; return B2K_OK; }
 
 /* single-sweep update kernels in order of preference for the selected mode; -1 = shape not supported */
 static int gs_single_sweep(b2k_ctx ctx, int mode, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
-                           const double *q, int dot, double *out)
+                           const double *q, int dot, double *out, const b2k_gate_s *gate = nullptr)
 {
   if (mode == 3) {
-    int rc = b2k_gs_tma_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out);
+    int rc = b2k_gs_tma_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out, gate);
     if (rc != -1) return rc;
   }
-  return b2k_gs_rt_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out);
+  return b2k_gs_rt_launch(ctx, V, ld, n, k, alpha, beta, w, q, dot, out, gate);
 }
 
 extern "C" int b2k_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *y,
@@ -594,8 +606,7 @@ extern "C" int b2k_gs_update_dot(b2k_ctx ctx, const double *V, int64_t ld, int64
 {
   const int mode = b2k_gs_fused_enabled();
   if (mode && k > 0 && n > 0) {
-    int rc = (mode == 2) ? b2k_gs_update_dot_fused(ctx, V, ld, n, k, w, cin, cout)
-                         : gs_single_sweep(ctx, mode, V, ld, n, k, -1.0, 1.0, w, cin, 1, cout);
+    int rc = gs_single_sweep(ctx, mode, V, ld, n, k, -1.0, 1.0, w, cin, 1, cout);
     if (rc != -1) return rc;       /* -1: shape not supported by the single-sweep kernels → two-sweep path */
   }
   /* two-sweep path: update sweep, then dot sweep (V read twice) */
@@ -613,6 +624,21 @@ extern "C" int b2k_gs_update_norm(b2k_ctx ctx, const double *V, int64_t ld, int6
     if (rc != -1) return rc;
   }
   return launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nrm2_out);
+}
+
+/* the same sweep launched SPECULATIVELY behind the sweep that produced *onrm2 and *nrm2 (device scalars): it runs only if the
+   DGKS criterion of bvorthog.c:180 asks for a refinement, nrm != 0 && nrm < eta*onrm with onrm = sqrt(max(*onrm2,0)),
+   nrm = sqrt(max(*nrm2,0)); otherwise w and (apart from the reduction of stale partials) nrm2_out are left alone */
+extern "C" int b2k_gs_update_norm_gated(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double *w, const double *cin,
+                                        double *nrm2_out, const double *onrm2, const double *nrm2, double eta)
+{
+  ARGCHK(onrm2 && nrm2 && nrm2_out, "null gate / output pointer");
+  const b2k_gate_s gate = {onrm2, nrm2, eta};
+  if (b2k_gs_fused_enabled() && k > 0 && n > 0) {
+    int rc = gs_single_sweep(ctx, b2k_gs_fused_enabled(), V, ld, n, k, -1.0, 1.0, w, cin, 0, nrm2_out, &gate);
+    if (rc != -1) return rc;
+  }
+  return launch_multvec(ctx, V, ld, n, k, -1.0, 1.0, w, cin, nrm2_out, &gate);
 }
 
 extern "C" int b2k_sumsq(b2k_ctx ctx, const double *X, int64_t ld, int64_t n, int k, double *out)

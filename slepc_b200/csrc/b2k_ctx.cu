@@ -68,7 +68,8 @@ extern "C" int b2k_ctx_destroy(b2k_ctx c)
   return B2K_OK;
 }
 
-extern "C" int b2k_ctx_sync(b2k_ctx c) { CK(cudaStreamSynchronize(c->stream)); return B2K_OK; }
+extern "C" int b2k_ctx_sync(b2k_ctx c) { c->syncs++; CK(cudaStreamSynchronize(c->stream)); return B2K_OK; }
+extern "C" int b2k_ctx_syncs(b2k_ctx c, uint64_t *n) { *n = c->syncs; return B2K_OK; }
 extern "C" void *b2k_ctx_stream(b2k_ctx c) { return (void *)c->stream; }
 extern "C" int b2k_ctx_sm_count(b2k_ctx c) { return c->sm_count; }
 extern "C" int b2k_ctx_launches(b2k_ctx c, uint64_t *n) { *n = c->launches; return B2K_OK; }
@@ -145,6 +146,7 @@ extern "C" int b2k_memset0(b2k_ctx c, void *p, size_t bytes) { CK(cudaMemsetAsyn
 extern "C" int b2k_h2d(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
   c->h2d_bytes += bytes;
+  c->syncs++;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return B2K_OK;
@@ -152,6 +154,7 @@ extern "C" int b2k_h2d(b2k_ctx c, void *dst, const void *src, size_t bytes)
 extern "C" int b2k_d2h(b2k_ctx c, void *dst, const void *src, size_t bytes)
 {
   c->d2h_bytes += bytes;
+  c->syncs++;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return B2K_OK;

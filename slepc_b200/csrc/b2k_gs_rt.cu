@@ -37,8 +37,9 @@ __device__ __forceinline__ double rt_ld1(const double *p)
 template <int CPT, bool DOT, bool NRM>
 __global__ void __launch_bounds__(RT_THREADS, (CPT >= 16 ? 4 : (CPT >= 8 ? 5 : 6)))
 k_gs_rt(const double *__restrict__ V, int64_t ld, int64_t n, int k, double alpha, double beta, double *__restrict__ w,
-        const double *__restrict__ q, double *__restrict__ part, int pstride)
+        const double *__restrict__ q, double *__restrict__ part, int pstride, const b2k_gate_s gate)
 {
+  if (b2k_gate_closed(gate)) return;              /* DGKS does not refine: the whole grid leaves (uniform) */
   __shared__ double  qs[4 * CPT];
   __shared__ double2 psum[2][4][32];
   const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
@@ -122,8 +123,9 @@ int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, do
 /* returns -1 when the shape is not supported (k > 64, unaligned): the caller falls back to the generic kernels.
    cout: DOT ? k+1 values (V^T w_new, ||w_new||^2) : (nrm_out ? 1 value ||w_new||^2 : nothing) */
 int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w,
-                     const double *q, int dot, double *out)
+                     const double *q, int dot, double *out, const b2k_gate_s *gatep)
 {
+  const b2k_gate_s gate = gatep ? *gatep : b2k_gate_s{nullptr, nullptr, 0.0};
   if (k < 1 || k > 64 || n < 1) return -1;
   if (!b2k_is_aligned16(V) || !b2k_is_aligned16(w) || (ld & 1)) return -1;
   const int kq = (k + 3) >> 2;
@@ -137,9 +139,9 @@ int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k,
   PROF_BEGIN(ctx, dot ? B2K_PROF_GSFUSED : B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
 #define RT_LAUNCH(CPT)                                                                                                          \
   do {                                                                                                                          \
-    if (dot) k_gs_rt<CPT, true, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride); \
-    else if (nrm) k_gs_rt<CPT, false, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride); \
-    else k_gs_rt<CPT, false, false><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride); \
+    if (dot) k_gs_rt<CPT, true, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
+    else if (nrm) k_gs_rt<CPT, false, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
+    else k_gs_rt<CPT, false, false><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
   } while (0)
   if (kq <= 4) RT_LAUNCH(4);
   else if (kq <= 8) RT_LAUNCH(8);

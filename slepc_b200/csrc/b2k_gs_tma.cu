@@ -79,8 +79,9 @@ struct TmSmem {
 template <int CPT, bool DOT, bool NRM>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 k_gs_tma(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmW, int64_t n, int k, double alpha, double beta,
-         double *__restrict__ w, const double *__restrict__ q, double *__restrict__ part, int pstride, int nstages)
+         double *__restrict__ w, const double *__restrict__ q, double *__restrict__ part, int pstride, int nstages, const b2k_gate_s gate)
 {
+  if (b2k_gate_closed(gate)) return;                            /* DGKS does not refine: the whole grid leaves (uniform) */
   constexpr int KB = 4 * CPT;                                   /* columns per stage (box width)   */
   constexpr int STAGE_DOUBLES = (KB + 1) * TM_ROWS;            /* V box + w box                   */
   extern __shared__ __align__(1024) unsigned char tm_raw[];
@@ -226,7 +227,7 @@ int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, do
 
 template <int CPT>
 static int tm_launch(b2k_ctx ctx, const CUtensorMap &mV, const CUtensorMap &mW, int64_t n, int k, double alpha, double beta, double *w,
-                     const double *q, int dot, int nrm, int grid, int pstride)
+                     const double *q, int dot, int nrm, int grid, int pstride, const b2k_gate_s &gate)
 {
   constexpr int KB = 4 * CPT;
   const size_t stage_bytes = (size_t)(KB + 1) * TM_ROWS * sizeof(double);
@@ -241,7 +242,7 @@ static int tm_launch(b2k_ctx ctx, const CUtensorMap &mV, const CUtensorMap &mW, 
       CK(cudaFuncSetAttribute(k_gs_tma<CPT, D, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));                  \
       configured = 1;                                                                                                           \
     }                                                                                                                           \
-    k_gs_tma<CPT, D, N><<<grid, TM_THREADS, shm, ctx->stream>>>(mV, mW, n, k, alpha, beta, w, q, ctx->partials, pstride, nstages); \
+    k_gs_tma<CPT, D, N><<<grid, TM_THREADS, shm, ctx->stream>>>(mV, mW, n, k, alpha, beta, w, q, ctx->partials, pstride, nstages, gate); \
   } while (0)
   if (dot) TM_GO(true, true);
   else if (nrm) TM_GO(false, true);
@@ -253,8 +254,9 @@ static int tm_launch(b2k_ctx ctx, const CUtensorMap &mV, const CUtensorMap &mW, 
 /* returns -1 when the shape is not supported (k > 64, small or unaligned blocks, no driver entry point): the caller
    falls back to the register-tile kernel.  Semantics of b2k_gs_rt_launch. */
 int b2k_gs_tma_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k, double alpha, double beta, double *w, const double *q,
-                      int dot, double *out)
+                      int dot, double *out, const b2k_gate_s *gatep)
 {
+  const b2k_gate_s gate = gatep ? *gatep : b2k_gate_s{nullptr, nullptr, 0.0};
   if (k < 5 || k > 64 || n < 32 * TM_ROWS || n >= 2147483647LL - TM_ROWS) return -1;   /* k <= 4: the register tile wins */
   if (!b2k_is_aligned16(V) || !b2k_is_aligned16(w) || (ld & 1)) return -1;
   CUtensorMap mV, mW;
@@ -269,10 +271,10 @@ int b2k_gs_tma_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k
   PROF_BEGIN(ctx, dot ? B2K_PROF_GSFUSED : B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
   int rc;
   switch (cpt) {
-    case 4: rc = tm_launch<4>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride); break;
-    case 8: rc = tm_launch<8>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride); break;
-    case 12: rc = tm_launch<12>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride); break;
-    default: rc = tm_launch<16>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride); break;
+    case 4: rc = tm_launch<4>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride, gate); break;
+    case 8: rc = tm_launch<8>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride, gate); break;
+    case 12: rc = tm_launch<12>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride, gate); break;
+    default: rc = tm_launch<16>(ctx, mV, mW, n, k, alpha, beta, w, q, dot, nrm, grid, pstride, gate); break;
   }
   PROF_END(ctx);
   if (rc) return rc;

@@ -23,7 +23,7 @@
 #include "b2k_internal.h"
 
 #define HL_MAXP 8                      /* peers per direction (= ranks of one box)                  */
-#define HL_CTAS 8                      /* CTAs per destination in k_halo_push                       */
+#define HL_CTAS 16                     /* CTAs per destination in k_halo_push                       */
 
 typedef unsigned long long u64;
 
@@ -59,7 +59,8 @@ struct b2k_halo_s {
 /* the communicator internals this file needs (b2k_comm.cu) */
 int b2k_comm_ctx(b2k_comm c, b2k_ctx *ctx);
 
-static inline size_t hl_data_bytes(long long nghost) { return ((size_t)(2 * nghost) * sizeof(double) + 255) & ~(size_t)255; }
+__host__ __device__ static inline long long hl_stride(long long nghost) { return (nghost + 1) & ~1LL; }   /* doubles per parity buffer: even, so both are 16-byte aligned */
+static inline size_t hl_data_bytes(long long nghost) { return ((size_t)(2 * hl_stride(nghost)) * sizeof(double) + 255) & ~(size_t)255; }
 static inline size_t hl_block_bytes(long long nghost) { return hl_data_bytes(nghost) + 3 * HL_MAXP * sizeof(u64); }
 __host__ __device__ static inline u64 *hl_arrived(void *block, size_t data_bytes) { return (u64 *)((char *)block + data_bytes); }
 __host__ __device__ static inline u64 *hl_ack(void *block, size_t data_bytes) { return hl_arrived(block, data_bytes) + HL_MAXP; }
@@ -84,10 +85,17 @@ __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ x,
   }
   __syncthreads();
   if (go) {
-    double *dst = d.peer_data + (seq & 1ull) * d.peer_nghost + d.peer_off;
+    double *dst = d.peer_data + (seq & 1ull) * hl_stride(d.peer_nghost) + d.peer_off;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    if (d.idx) for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.count; i += stride) dst[i] = x[d.idx[i]];
-    else for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.count; i += stride) dst[i] = x[d.xoff + i];
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d.idx) for (long long i = t0; i < d.count; i += stride) dst[i] = x[d.idx[i]];
+    else if ((((unsigned long long)(x + d.xoff) | (unsigned long long)dst) & 15ull) == 0) {      /* contiguous plane, aligned: 16-byte stores over NVLink */
+      const double2 *s2 = reinterpret_cast<const double2 *>(x + d.xoff);
+      double2 *d2 = reinterpret_cast<double2 *>(dst);
+      const long long n2 = d.count >> 1;
+      for (long long i = t0; i < n2; i += stride) d2[i] = s2[i];
+      if ((d.count & 1) && t0 == 0) dst[d.count - 1] = x[d.xoff + d.count - 1];
+    } else for (long long i = t0; i < d.count; i += stride) dst[i] = x[d.xoff + i];
   }
   __threadfence_system();
   __syncthreads();
@@ -236,7 +244,7 @@ extern "C" int b2k_halo_exchange(b2k_halo h, const double *x, const double **gho
     k_halo_wait<<<1, 32, 0, ctx->stream>>>(h->args, seq);
     CKLAUNCH(ctx);
   }
-  if (ghost_out) *ghost_out = (const double *)h->block + (seq & 1ull) * h->nghost;
+  if (ghost_out) *ghost_out = (const double *)h->block + (seq & 1ull) * hl_stride(h->nghost);
   return B2K_OK;
 }
 

@@ -30,6 +30,7 @@ struct b2k_ctx_s {
   size_t       dscratch_elems;
   cudaEvent_t  ev0, ev1;
   uint64_t     launches;
+  uint64_t     syncs;           /* host waits on the stream issued through this context (b2k_ctx_sync, blocking copies) */
   uint64_t     h2d_bytes, d2h_bytes;
   /* optional per-kernel-class timing with CUDA events on the launching stream (b2k_prof_*) */
   int          prof_on, prof_n, prof_cap;
@@ -45,6 +46,22 @@ struct b2k_ctx_s {
 };
 
 int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, double *out);   /* b2k_bv.cu */
+
+/* Device-side DGKS decision (bvorthog.c:180, `while (l<3 && nrm && nrm < eta*onrm)`): a GATED update sweep is launched
+   speculatively right behind the sweep that produces the two norms and runs only when the refinement criterion holds, so the
+   host needs ONE synchronisation per column instead of one per pass.  Every CTA evaluates the predicate itself from the two
+   device scalars with the host's own IEEE operations (sqrt, one multiply), so host and device always take the same decision.
+   onrm2 == NULL: not gated. */
+struct b2k_gate_s { const double *onrm2, *nrm2; double eta; };
+#ifdef __CUDACC__
+__device__ __forceinline__ bool b2k_gate_closed(const b2k_gate_s &g)
+{
+  if (!g.onrm2) return false;
+  const double a = *reinterpret_cast<const volatile double *>(g.onrm2), b = *reinterpret_cast<const volatile double *>(g.nrm2);
+  const double onrm = sqrt(a > 0.0 ? a : 0.0), nrm = sqrt(b > 0.0 ? b : 0.0);
+  return !(nrm != 0.0 && fabs(nrm) < g.eta * fabs(onrm));
+}
+#endif
 
 /* bracket the dominant kernel of an entry point; `bytes` = algorithmic bytes of this launch */
 #define PROF_BEGIN(ctx, cls, bytes)                                                          \

@@ -32,6 +32,13 @@ typedef struct {
   PetscBool expect_refine;
   PetscInt  last_j;      /* column and state of the last uncached pass: a repeat means DGKS refined  */
   uint64_t  last_state;
+  /* one synchronisation per column: the update sweep of the refinement pass is launched speculatively behind the first pass,
+     gated on the device by the DGKS criterion (b2k_gs_update_norm_gated); the host takes the same decision from the same
+     numbers, so it knows whether the pass ran */
+  int       onesync;     /* env B2K_BV_ONESYNC, default 1                                         */
+  PetscBool pend2_valid; /* the second pass was issued with the first                              */
+  PetscBool pend2_ran;   /* ... and the criterion let it run                                       */
+  PetscReal pend2_nrm2;  /* ||w||^2 after it                                                       */
 } BV_B200;
 
 #define CTX() B2KGetContext()
@@ -160,18 +167,25 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
     memcpy(cc, d->pend_c, sizeof(double) * (size_t)kk);
     const PetscReal beta2 = d->pend_nrm2;
     const PetscBool need_norm = norm ? PETSC_TRUE : PETSC_FALSE;
-    if (need_norm) {
+    if (d->pend2_valid && d->pend2_ran) {
+      /* the update sweep of this pass already ran behind the first one (gated on the device): nothing to launch, nothing to wait for */
+      d->pend2_valid = PETSC_FALSE;
+      if (norm) *norm = sqrt(d->pend2_nrm2 > 0.0 ? d->pend2_nrm2 : 0.0);
+    } else if (need_norm) {
+      d->pend2_valid = PETSC_FALSE;
       PetscCall(BVScope_B200(bv, PETSC_TRUE, &fused));
       B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 1), SLOT(d, 3)));   /* c2 still sits in slot 1 */
       PetscCall(BVFetch_B200(bv, d, SLOT(d, 3), 1, PETSC_TRUE, fused, &hp));
       *norm = sqrt(hp[0]);
     } else {
+      d->pend2_valid = PETSC_FALSE;
       B2KCall(b2k_multvec(ctx, d->V, bv->ld, bv->n, kk, -1.0, 1.0, w, SLOT(d, 1)));
     }
     if (onorm) *onorm = sqrt(beta2 > 0.0 ? beta2 : 0.0);
     BV_AddCoefficients(bv, j, h, c);
     return PETSC_SUCCESS;
   }
+  PetscCheck(!(d->pend_valid && d->pend2_valid && d->pend2_ran), PETSC_ERR_PLIB, "column %d was refined on the device but the host never collected the pass", (int)d->pend_j);
   if (d->pend_valid) d->expect_refine = PETSC_FALSE;   /* the cached second pass was never asked for */
   d->pend_valid = PETSC_FALSE;
   const PetscBool repeat = (!v && d->last_j == j && d->last_state == bv->state) ? PETSC_TRUE : PETSC_FALSE;
@@ -187,10 +201,25 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
     /* sweep 2: w -= V c, and from the same read of V the next pass' V^T w_new and ||w_new||^2 */
     B2KCall(b2k_gs_update_dot(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 1)));
     if (!fused) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 1), kk + 1, 0, B2K_MEM_DEVICE));
-    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), 2 * d->slot, PETSC_FALSE, fused, &hp));
+    /* sweep 3, speculative: the refinement's update w -= V c2 (+ ||w||^2).  REFINE_IFNEEDED: gated on the device by the
+       criterion of bvorthog.c:180 evaluated from (w^T w, ||w_1||^2) = (slot 0, slot 1)[kk]; REFINE_ALWAYS: unconditional */
+    const PetscBool ifneeded = (bv->orthog_ref == BV_ORTHOG_REFINE_IFNEEDED && onorm && norm) ? PETSC_TRUE : PETSC_FALSE;
+    const PetscBool spec = (d->onesync && (ifneeded || bv->orthog_ref == BV_ORTHOG_REFINE_ALWAYS)) ? PETSC_TRUE : PETSC_FALSE;
+    if (spec) {
+      if (ifneeded) B2KCall(b2k_gs_update_norm_gated(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 1), SLOT(d, 3), SLOT(d, 0) + kk, SLOT(d, 1) + kk, bv->orthog_eta));
+      else B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 1), SLOT(d, 3)));
+      if (!fused) PetscCall(B2KCommAllreduce(bv->comm, SLOT(d, 3), 1, 0, B2K_MEM_DEVICE));
+    }
+    PetscCall(BVFetch_B200(bv, d, SLOT(d, 0), spec ? 3 * d->slot + 1 : 2 * d->slot, PETSC_FALSE, fused, &hp));
     memcpy(d->pend_c, hp + d->slot, sizeof(double) * (size_t)(kk + 1));
     d->pend_nrm2 = hp[d->slot + kk];
     d->pend_j = j; d->pend_state = bv->state; d->pend_valid = PETSC_TRUE;
+    d->pend2_valid = spec;
+    if (spec) {
+      const PetscReal on = sqrt(hp[kk] > 0.0 ? hp[kk] : 0.0), nr = sqrt(d->pend_nrm2 > 0.0 ? d->pend_nrm2 : 0.0);
+      d->pend2_ran = (!ifneeded || (nr != 0.0 && fabs(nr) < bv->orthog_eta * fabs(on))) ? PETSC_TRUE : PETSC_FALSE;   /* the gate, bit for bit */
+      d->pend2_nrm2 = hp[3 * d->slot];
+    }
   } else {
     /* sweep 2: w -= V c with the explicit ||w_new||^2 folded in */
     B2KCall(b2k_gs_update_norm(ctx, d->V, bv->ld, bv->n, kk, w, SLOT(d, 0), SLOT(d, 0) + kk + 1));
@@ -433,6 +462,8 @@ PetscErrorCode BVCreate_B200(BV bv)
   PetscCall(BVAllocScratch_B200(bv, d));
   const char *e = getenv("B2K_BV_FUSE");
   d->fuse_mode = e ? atoi(e) : 2;
+  e = getenv("B2K_BV_ONESYNC");
+  d->onesync = e ? atoi(e) : 1;
   d->expect_refine = PETSC_TRUE;
   d->last_j = -1;
 

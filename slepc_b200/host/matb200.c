@@ -28,19 +28,20 @@ typedef struct {
      built on first use; zghost/rbuf are the reverse-halo buffers */
   b2k_csr   ATown, ATgh;
   double   *zghost, *rbuf;
-  /* opt-in (B2K_HALO_P2P=1): the forward halo pushed over NVLink peer memory instead of ncclSend/ncclRecv */
+  /* default on one NVSwitch box (B2K_HALO_P2P=0 turns it off): the forward halo pushed over NVLink peer memory instead of ncclSend/ncclRecv */
   b2k_halo  halo;
 } Mat_B200CSR;
 
 #define CTX() B2KGetContext()
 
-/* collective: turn the installed halo plan into a peer-memory halo object when asked for (B2K_HALO_P2P=1) and possible */
+/* collective: turn the installed halo plan into a peer-memory halo object whenever the NVLink mailboxes are up (default;
+   B2K_HALO_P2P=0 keeps the grouped ncclSend/ncclRecv) */
 static PetscErrorCode MatHaloSetUpP2P_B200CSR(Mat A)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
   B2KComm comm = B2KCommWorld();
   const char *e = getenv("B2K_HALO_P2P");
-  if (!e || e[0] != '1' || !comm || comm->kind != 1 || comm->size < 2 || comm->size > 8 || !b2k_comm_p2p_enabled(comm->nccl)) return PETSC_SUCCESS;
+  if ((e && e[0] == '0') || !comm || comm->kind != 1 || comm->size < 2 || comm->size > 8 || !b2k_comm_p2p_enabled(comm->nccl)) return PETSC_SUCCESS;
   if (a->halo) { B2KCall(b2k_halo_destroy(a->halo)); a->halo = NULL; }
   int64_t off[8] = {0};
   for (PetscInt q = 0; q < a->nsend && q < 8; q++) off[q] = a->sendoff ? a->sendoff[q] : 0;

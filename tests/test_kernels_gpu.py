@@ -100,7 +100,7 @@ def test_gs_update_dot_matches_cgs_pass(ctx, n, k):
 @pytest.mark.parametrize("k", [1, 5, 8, 9, 16, 17, 31, 33, 48, 64])
 @pytest.mark.parametrize("n", [1, 63, 128, 130, 128 * 7 + 1, 4096, 4097, 12345, 128 * 148 * 3 + 77, 1 << 20])
 def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
-    """The single-sweep kernels (1: register tile, 2: 1-D bulk-copy staged, 3: 2-D tensor-map TMA pipeline; 3 falls back to 1
+    """The single-sweep kernels (1: register tile, 3: 2-D tensor-map TMA pipeline; 3 falls back to 1
     below 4096 rows) and the two-sweep path (0) compute the same w
     and c (different reduction order ⇒ compare to rounding, and each against the float64 reference)."""
     from slepc_b200._b2k import check
@@ -112,7 +112,7 @@ def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
     cin = rng.standard_normal(k + 1)
     dV, dc = ctx.to_device(H), ctx.to_device(cin)
     out = {}
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 3):
         check(ctx.lib.b2k_gs_set_fused(mode))
         dw = ctx.to_device(w)
         co = ctx.empty(k + 1)
@@ -126,7 +126,7 @@ def test_gs_fused_single_sweep_equals_two_sweep(ctx, n, k):
     check(ctx.lib.b2k_gs_set_fused(3))
     wref = w - H[:n] @ cin[:k]
     cref = np.concatenate([H[:n].T @ wref, [wref @ wref]])
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 3):
         assert np.allclose(out[mode][0], wref, rtol=1e-13, atol=1e-13 * np.sqrt(k)), mode
         assert np.allclose(out[mode][1], cref, rtol=1e-12, atol=1e-12 * np.sqrt(n)), mode
 
@@ -350,3 +350,40 @@ def test_laplacian_device_generator(ctx, dim, dims, part):
     assert nnz.value == A[row0:row0 + rows_per].nnz
     assert np.array_equal(dy.to_host(), (A @ x)[row0:row0 + rows_per]) or np.allclose(dy.to_host(), (A @ x)[row0:row0 + rows_per], rtol=1e-14, atol=1e-14)
     check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+
+
+@pytest.mark.parametrize("n,k", [(1000, 7), (5000, 3), (50001, 17), (300007, 64), (20000, 70)])
+def test_gs_update_norm_gated_device_side_dgks_decision(ctx, n, k):
+    """b2k_gs_update_norm_gated: the speculative refinement sweep runs iff  nrm != 0 && nrm < eta*onrm  (bvorthog.c:180), evaluated
+    on the device from two scalars — through the register-tile kernel (small n / k <= 4), the tensor-map kernel and the generic
+    kernel (k > 64).  Closed gate: w untouched bit for bit; open gate: identical to b2k_gs_update_norm."""
+    from slepc_b200._b2k import check
+    ld = n + (n % 2)
+    rng = np.random.default_rng(n + 3 * k)
+    H = np.zeros((ld, k), order="F")
+    H[:n] = rng.standard_normal((n, k))
+    w = rng.standard_normal(n)
+    q = rng.standard_normal(k)
+    dV, dq = ctx.to_device(H), ctx.to_device(q)
+    eta = 0.7071
+    wref = w - H[:n] @ q
+    for onrm2, nrm2, runs in [(4.0, 1.0, True), (4.0, 2.0001, False), (4.0, 0.0, False), (1.0, 1.0, False), (2.0, 0.99, True), (-1.0, 1.0, False),
+                              (4.0, float(np.nextafter((eta * 2.0) ** 2, 0)), None)]:
+        g = ctx.to_device(np.array([onrm2, nrm2]))
+        dw, out = ctx.to_device(w), ctx.to_device(np.array([-7.0]))
+        check(ctx.lib.b2k_gs_update_norm_gated(ctx.h, dV.ptr, ld, n, k, dw.ptr, dq.ptr, out.ptr, g.ptr, g.at(1), eta))
+        got = dw.to_host()
+        on, nr = np.sqrt(max(onrm2, 0.0)), np.sqrt(max(nrm2, 0.0))
+        expect = bool(nr != 0.0 and abs(nr) < eta * abs(on))             # the host's own expression (bvorthog.c:180)
+        if runs is not None:
+            assert expect == runs
+        if expect:
+            assert np.allclose(got, wref, rtol=1e-13, atol=1e-12 * k)
+            assert np.isclose(out.to_host()[0], wref @ wref, rtol=1e-12)
+            dw2, out2 = ctx.to_device(w), ctx.empty(1)
+            check(ctx.lib.b2k_gs_update_norm(ctx.h, dV.ptr, ld, n, k, dw2.ptr, dq.ptr, out2.ptr))
+            assert np.array_equal(dw2.to_host(), got) and out2.to_host()[0] == out.to_host()[0]
+        else:
+            assert np.array_equal(got, w)
+        for a in (g, dw, out):
+            a.free()

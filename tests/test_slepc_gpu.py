@@ -4,6 +4,8 @@ golden outputs.  Tolerances: eigen/singular values 1e-10 relative (north star), 
 tol (5*tol as the reference's -terse check, epsview.c:314-320), subspace angles 1e-6.
 """
 import ctypes
+import json
+import os
 
 import numpy as np
 import pytest
@@ -16,6 +18,7 @@ import bv_scenarios as SC
 
 pytestmark = pytest.mark.gpu
 EPS = np.finfo(float).eps
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -486,3 +489,51 @@ def test_full_size_properties(dim, g, nev, ncv, need_gb):
     assert all(theta[i] >= theta[i + 1] - 1e-9 for i in range(kk - 1))
     for o in (G, eps, x, y, z, t, M):
         o.destroy()
+
+
+def _ctx_counter(name):
+    from slepc_b200 import _b2k
+    n = ctypes.c_uint64()
+    _b2k.check(getattr(_b2k.load(), name)(S.B2KGetContext(), ctypes.byref(n)))
+    return n.value
+
+
+@pytest.mark.parametrize("refine", ["ifneeded", "always"])
+def test_one_host_sync_per_lanczos_step(refine):
+    """DGKS decision on the device (b2k_gs_update_norm_gated): a Lanczos step whose orthogonalisation is refined costs ONE host
+    synchronisation (the read of both passes' coefficients), not one per pass; results equal the two-sync path bit for bit."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, ctypes, json
+sys.path.insert(0, %r)
+from slepc_b200 import slepc as SL, _b2k
+from slepc_b200.slepc import S
+SL.initialize(0)
+M = SL.Mat.laplacian(2, 300, 300)
+eps = SL.EPS(M, hermitian=True)
+S.EPSSetDimensions(eps.h, 6, 32, SL.PETSC_DETERMINE)
+S.EPSSetUp(eps.h)
+bv = eps.bv()
+S.BVSetOrthogonalization(bv.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_%s, 0.7071, SL.BV_ORTHOG_BLOCK_GS)
+eps.cycles(2)
+n = ctypes.c_uint64(); lib = _b2k.load(); ctx = S.B2KGetContext()
+lib.b2k_ctx_syncs(ctx, ctypes.byref(n)); s0 = n.value
+m0, g0 = bv.counters()[1], bv.counters()[0]
+eps.cycles(20)
+lib.b2k_ctx_syncs(ctx, ctypes.byref(n))
+steps, passes = bv.counters()[1] - m0, bv.counters()[0] - g0
+eps.solve()
+print(json.dumps(dict(syncs=n.value - s0, steps=steps, passes=passes, nconv=eps.nconv, its=eps.its,
+                      lam=[eps.eigenvalue(i)[0] for i in range(eps.nconv)])))
+''' % (os.path.dirname(HERE), refine.upper())
+    res = {}
+    for one in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2K_BV_ONESYNC=one), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        res[one] = json.loads(r.stdout.strip().splitlines()[-1])
+    a, b = res["1"], res["0"]
+    assert a["passes"] == 2 * a["steps"]                       # every Lanczos column of this problem is refined
+    assert a["syncs"] <= a["steps"] + 20 * 3 + 5, a             # one per step (+ a few per restart), was two per step
+    assert b["syncs"] >= 2 * b["steps"], b
+    assert a["its"] == b["its"] and a["nconv"] == b["nconv"] and a["lam"] == b["lam"]     # same arithmetic, bit for bit
