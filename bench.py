@@ -343,7 +343,9 @@ def run_b200(args, wl):
     for cid, name in enumerate(KCLASS):
         n_, ms_, b_ = ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double()
         _b2k.check(lib.b2k_prof_get(ctx, cid, ctypes.byref(n_), ctypes.byref(ms_), ctypes.byref(b_)))
-        prof[name] = dict(launches=n_.value, ms=ms_.value, bytes=b_.value)
+        f_ = ctypes.c_double()
+        _b2k.check(lib.b2k_prof_get_flops(ctx, cid, ctypes.byref(f_)))
+        prof[name] = dict(launches=n_.value, ms=ms_.value, bytes=b_.value, flops=f_.value)
     _b2k.check(lib.b2k_prof_enable(ctx, 0))
     if done < args.steps:
         raise SystemExit(f"bench.py: the solve converged after {done} timed cycles (< --steps {args.steps}); lower --steps/--warmup")
@@ -355,6 +357,11 @@ def run_b200(args, wl):
             kernels[name] = dict(launches=p["launches"], ms_total=round(p["ms"], 3), avg_ms=p["ms"] / p["launches"],
                                  share_of_step=p["ms"] / ms.value, achieved_gbs=p["bytes"] / p["ms"] / 1e6,
                                  frac_of_peak=p["bytes"] / p["ms"] / 1e6 / peak, frac_of_nominal_8tbs=p["bytes"] / p["ms"] / 1e6 / 8000.0)
+            if p["flops"]:                       # level-3 (restart GEMM): at the FP64 ridge, so the FP64 pipe is the second roofline
+                tf = p["flops"] / p["ms"] / 1e9
+                clk = (clocks or {}).get("sm_mhz") or 1965.0
+                kernels[name].update(fp64_tflops=tf, frac_of_fp64_peak_at_sampled_clock=tf / (148 * 64 * 2 * clk * 1e6 / 1e12),
+                                     fp64_note="FP64 peak = 148 SMs x 64 FMA/clk x SM clock sampled under load (DMMA = DFMA rate, tools/dmma_probe.cu)")
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
     gs_bytes = sum(prof[k]["bytes"] for k in ("dotvec", "multvec", "gs_fused"))
     gs_ms = sum(prof[k]["ms"] for k in ("dotvec", "multvec", "gs_fused"))

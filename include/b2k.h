@@ -79,6 +79,7 @@ int  b2k_ctx_copy_bytes(b2k_ctx ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 #define B2K_PROF_NCLASS   6
 int  b2k_prof_enable(b2k_ctx ctx, int on);               /* on: start a fresh recording            */
 int  b2k_prof_get(b2k_ctx ctx, int cls, uint64_t *launches, double *ms, double *algorithmic_bytes);
+int  b2k_prof_get_flops(b2k_ctx ctx, int cls, double *flops);   /* level-3 classes: 2 n kin nout per launch (FP64 roofline next to the HBM one) */
 
 /* ---- BV level-1/2/3 (replace bvcuda.cu) ------------------------------------------------------ */
 /* q[0:k] = V(:,0:k)^T y                      — BVDotVec_BLAS_CUDA  bvcuda.cu:204-264 (gemv 'C')  */

@@ -223,6 +223,14 @@ PetscErrorCode BVNorm(BV bv, NormType type, PetscReal *val);                    
 PetscErrorCode BVNormVec(BV bv, Vec v, NormType type, PetscReal *val);                  /* bvglobal.c:590 */
 PetscErrorCode BVNormColumn(BV bv, PetscInt j, NormType type, PetscReal *val);          /* bvglobal.c:523 */
 PetscErrorCode BVNormalize(BV bv, PetscScalar *eigi);                                   /* bvglobal.c:836 */
+/* split-phase reductions: every Begin queues its local part, the first End performs ONE global reduction for all of them
+   (PetscSplitReduction; a BV type may take the pair over with the dotvec_begin/end, norm_begin/end slots, bvimpl.h:33-39) */
+PetscErrorCode BVDotVecBegin(BV X, Vec y, PetscScalar *m);                              /* bvglobal.c:188 */
+PetscErrorCode BVDotVecEnd(BV X, Vec y, PetscScalar *m);                                /* bvglobal.c:238 */
+PetscErrorCode BVDotColumnBegin(BV X, PetscInt j, PetscScalar *m);                      /* bvglobal.c:350 */
+PetscErrorCode BVDotColumnEnd(BV X, PetscInt j, PetscScalar *m);                        /* bvglobal.c:410 */
+PetscErrorCode BVNormColumnBegin(BV bv, PetscInt j, NormType type, PetscReal *val);     /* bvglobal.c:703 */
+PetscErrorCode BVNormColumnEnd(BV bv, PetscInt j, NormType type, PetscReal *val);       /* bvglobal.c:760 */
 PetscErrorCode BVMatMult(BV V, Mat A, BV Y);                                            /* bvops.c:767 */
 PetscErrorCode BVMatMultColumn(BV V, Mat A, PetscInt j);                                /* bvops.c:862 */
 PetscErrorCode BVOrthogonalizeVec(BV bv, Vec v, PetscScalar *H, PetscReal *norm, PetscBool *lindep);       /* bvorthog.c:249 */

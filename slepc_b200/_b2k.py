@@ -30,6 +30,7 @@ SIGNATURES = {
     "b2k_ctx_copy_bytes": [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)],
     "b2k_prof_enable": [c_vp, c_int],
     "b2k_prof_get": [c_vp, c_int, ctypes.POINTER(c_u64), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
+    "b2k_prof_get_flops": [c_vp, c_int, ctypes.POINTER(c_dbl)],
     "b2k_malloc": [c_vp, ctypes.POINTER(c_vp), c_sz],
     "b2k_free": [c_vp, c_vp],
     "b2k_memset0": [c_vp, c_vp, c_sz],

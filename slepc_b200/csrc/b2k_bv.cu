@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
  * all ranks get bit-identical sums.  One-shot, latency-bound (<= 1025 doubles): no ring, no NCCL launch.
  * Mailbox = [parity][source rank][column]; two parities suffice because a rank can only be one reduction ahead of the
  * slowest peer (it cannot finish reduction s+1 before every peer has started it, i.e. finished reading s). */
-__global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *__restrict__ part, int nblk, int pstride, int ncols,
-                                                            double *__restrict__ out, const b2k_xg_s xg, unsigned long long seq)
+__global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *part, int nblk, int pstride, int ncols,
+                                                            double *out, const b2k_xg_s xg, unsigned long long seq)   /* out may be part (in-place all-reduce) */
 {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -481,6 +481,16 @@ int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, do
   return B2K_OK;
 }
 
+/* in-place sum over the ranks of n <= B2K_XG_MAXC doubles through the NVLink mailboxes (one launch; the reduction kernel with a
+   single "CTA partial" = the buffer itself); returns -1 when the mailboxes are not open or n is too large → caller uses NCCL */
+int b2k_xg_allreduce_inplace(b2k_ctx ctx, double *buf, int n)
+{
+  if (!ctx->xg || n < 1 || n > B2K_XG_MAXC || (n + 7) / 8 > B2K_XG_MAXB) return -1;
+  k_reduce_partials_xg<<<(n + 7) / 8, 256, 0, ctx->stream>>>(buf, 1, n, n, buf, *ctx->xg, ++ctx->xg_seq);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
 static inline int grid_rows(b2k_ctx ctx, int64_t work_items, int per_sm)
 {
   int64_t need = (work_items + 255) / 256;
@@ -795,6 +805,7 @@ static int launch_gemm_ts(b2k_ctx ctx, double *Out, int64_t ldo, const double *I
     dim3 blk(RB / 4, 16);                                                                                       \
     const int64_t gx = (n + RB - 1) / RB;                                                                       \
     PROF_BEGIN(ctx, B2K_PROF_GEMM, 8.0 * (double)n * (kin + nout));                                             \
+    PROF_FLOPS(ctx, 2.0 * (double)n * kin * nout);                                                              \
     k_gemm_ts<RB><<<(unsigned)gx, blk, shm, ctx->stream>>>(Out, ldo, In, ldi, n, kin, nout, Q, ldq, qtrans, alpha, beta); \
     PROF_END(ctx);                                                                                              \
     CKLAUNCH(ctx);                                                                                              \

@@ -224,9 +224,15 @@ extern "C" int b2k_comm_rank(b2k_comm c, int *rank, int *size)
   return B2K_OK;
 }
 
+int b2k_xg_allreduce_inplace(b2k_ctx ctx, double *buf, int n);   /* b2k_bv.cu */
+
 extern "C" int b2k_comm_allreduce_sum(b2k_comm c, double *buf, int count)
 {
   if (!c || c->size == 1 || count == 0) return B2K_OK;
+  if (c->p2p_open) {                              /* short vectors: one-shot over the NVLink mailboxes, bit-identical on every rank */
+    const int rc = b2k_xg_allreduce_inplace(c->ctx, buf, count);
+    if (rc != -1) return rc;
+  }
   NK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, c->nccl, c->ctx->stream));
   return B2K_OK;
 }

@@ -60,7 +60,7 @@ extern "C" int b2k_ctx_destroy(b2k_ctx c)
   cudaStreamSynchronize(c->stream);
   cudaFree(c->partials);
   cudaFree(c->dscratch);
-  if (c->prof_ev) { for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]); free(c->prof_ev); free(c->prof_id); free(c->prof_bytes); }
+  if (c->prof_ev) { for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]); free(c->prof_ev); free(c->prof_id); free(c->prof_bytes); free(c->prof_flop); }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -91,6 +91,7 @@ static int prof_flush(b2k_ctx c)
     const int id = c->prof_id[i];
     c->prof_ms[id] += (double)f;
     c->prof_b[id] += c->prof_bytes[i];
+    c->prof_f[id] += c->prof_flop[i];
     c->prof_cnt[id]++;
   }
   c->prof_n = 0;
@@ -104,11 +105,12 @@ extern "C" int b2k_prof_enable(b2k_ctx c, int on)
       c->prof_ev = (cudaEvent_t *)calloc(2 * (size_t)c->prof_cap, sizeof(cudaEvent_t));
       c->prof_id = (int *)calloc((size_t)c->prof_cap, sizeof(int));
       c->prof_bytes = (double *)calloc((size_t)c->prof_cap, sizeof(double));
-      if (!c->prof_ev || !c->prof_id || !c->prof_bytes) return B2K_ERR_MEM;
+      c->prof_flop = (double *)calloc((size_t)c->prof_cap, sizeof(double));
+      if (!c->prof_ev || !c->prof_id || !c->prof_bytes || !c->prof_flop) return B2K_ERR_MEM;
       for (int i = 0; i < 2 * c->prof_cap; i++) CK(cudaEventCreate(&c->prof_ev[i]));
     }
     c->prof_n = 0;
-    for (int i = 0; i < B2K_PROF_NCLASS; i++) { c->prof_ms[i] = 0.0; c->prof_b[i] = 0.0; c->prof_cnt[i] = 0; }
+    for (int i = 0; i < B2K_PROF_NCLASS; i++) { c->prof_ms[i] = 0.0; c->prof_b[i] = 0.0; c->prof_f[i] = 0.0; c->prof_cnt[i] = 0; }
     c->prof_on = 1;
   } else {
     int rc = prof_flush(c);
@@ -125,6 +127,15 @@ extern "C" int b2k_prof_get(b2k_ctx c, int cls, uint64_t *launches, double *ms, 
   if (launches) *launches = c->prof_cnt[cls];
   if (ms) *ms = c->prof_ms[cls];
   if (bytes) *bytes = c->prof_b[cls];
+  return B2K_OK;
+}
+
+extern "C" int b2k_prof_get_flops(b2k_ctx c, int cls, double *flops)
+{
+  ARGCHK(cls >= 0 && cls < B2K_PROF_NCLASS, "kernel class out of range");
+  int rc = prof_flush(c);
+  if (rc) return rc;
+  *flops = c->prof_f[cls];
   return B2K_OK;
 }
 

@@ -37,7 +37,8 @@ struct b2k_ctx_s {
   cudaEvent_t *prof_ev;         /* 2 events per recorded launch */
   int         *prof_id;
   double      *prof_bytes;
-  double       prof_ms[B2K_PROF_NCLASS], prof_b[B2K_PROF_NCLASS];
+  double      *prof_flop;      /* floating-point operations of the recorded launch (level-3 kernels)  */
+  double       prof_ms[B2K_PROF_NCLASS], prof_b[B2K_PROF_NCLASS], prof_f[B2K_PROF_NCLASS];
   uint64_t     prof_cnt[B2K_PROF_NCLASS];
   /* when xg_on, every two-stage reduction launched through b2k_launch_reduce_partials also sums over the ranks */
   b2k_xg_s    *xg;
@@ -69,8 +70,10 @@ __device__ __forceinline__ bool b2k_gate_closed(const b2k_gate_s &g)
   if (prof_slot_ >= 0) {                                                                      \
     (ctx)->prof_id[prof_slot_] = (cls);                                                       \
     (ctx)->prof_bytes[prof_slot_] = (double)(bytes);                                          \
+    (ctx)->prof_flop[prof_slot_] = 0.0;                                                       \
     cudaEventRecord((ctx)->prof_ev[2 * prof_slot_], (ctx)->stream);                           \
   }
+#define PROF_FLOPS(ctx, f) do { if (prof_slot_ >= 0) (ctx)->prof_flop[prof_slot_] = (double)(f); } while (0)
 #define PROF_END(ctx)                                                                         \
   if (prof_slot_ >= 0) cudaEventRecord((ctx)->prof_ev[2 * prof_slot_ + 1], (ctx)->stream);
 

@@ -125,6 +125,7 @@ int b2k_vq_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, int64
   int grid = ctx->sm_count * 2;
   if ((int64_t)grid > ntiles) grid = (int)ntiles;
   PROF_BEGIN(ctx, B2K_PROF_GEMM, 8.0 * (double)n * (kin + nout));
+  PROF_FLOPS(ctx, 2.0 * (double)n * kin * nout);
 #define VQ_LAUNCH(CC)                                                                                              \
   do {                                                                                                             \
     CK(cudaFuncSetAttribute(k_vq<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));                     \

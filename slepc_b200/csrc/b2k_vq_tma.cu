@@ -53,7 +53,7 @@ __device__ __forceinline__ void vt_dmma(double &d0, double &d1, double a, double
 }
 
 /* KB = columns of a TMA box (= of a shared-memory stage), STAGES = depth of the ring.  <.,.,64,3> is the general shape;
-   <.,.,32,6> (opt-in, B2K_VQ_NARROW=1) halves the box for kin <= 32 so that twice as many tiles are in flight.
+   <.,.,32,6> (default for kin, nout <= 32) halves the box so that twice as many tiles are in flight.
    MT = m-tiles (8 rows each) per warp, NS = 8-column slabs per warp.  The 8 consumer warps tile the 128 x nout output as
    (16/MT row groups) x (MT/2 column groups): <8,1> nout <= 32, <4,3> nout <= 48, <8,2> nout <= 64 — the shape that wastes
    the fewest DMMAs on padding columns. */
@@ -200,8 +200,10 @@ int b2k_vq_tma_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, i
   if (kin < 1 || kin > 64 || nout < 1 || nout > 64 || n < 32 * VT_ROWS || n >= 2147483647LL - VT_ROWS) return -1;
   if (!b2k_is_aligned16(In) || !b2k_is_aligned16(Out) || (ldi & 1) || (ldo & 1)) return -1;
   /* in place is safe only when Out's rows are In's rows: same leading dimension, Out a column of In's block */
-  static int narrow = -1;             /* env B2K_VQ_NARROW=1: 32-column boxes, 6 stages, <4,1> tiling for kin <= 32 (not yet the default) */
-  if (narrow < 0) { const char *e = getenv("B2K_VQ_NARROW"); narrow = (e && e[0] == '1') ? 1 : 0; }
+  static int narrow = -1;             /* 32-column boxes, 6 stages, <4,1> tiling for kin <= 32: twice the tiles in flight.  Measured on B200 at
+                                         25 -> 13 columns (the C3 restart), n = 4.2 M: 5410 GB/s against 3189 GB/s with 64-column boxes
+                                         (profiles/r02_kernels.md); env B2K_VQ_NARROW=0 turns it off */
+  if (narrow < 0) { const char *e = getenv("B2K_VQ_NARROW"); narrow = (e && e[0] == '0') ? 0 : 1; }
   const bool use_narrow = narrow && kin <= 32 && nout <= 32;
   const int kb = use_narrow ? 32 : VT_KB, nst = use_narrow ? 6 : VT_STAGES;
   CUtensorMap mIn;
@@ -222,6 +224,7 @@ int b2k_vq_tma_launch(b2k_ctx ctx, double *Out, int64_t ldo, const double *In, i
     configured = 1;
   }
   PROF_BEGIN(ctx, B2K_PROF_GEMM, 8.0 * (double)n * (kin + nout));
+  PROF_FLOPS(ctx, 2.0 * (double)n * kin * nout);
   if (use_narrow && nout <= 16) k_vq_tma<4, 1, 32, 6><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
   else if (use_narrow) k_vq_tma<8, 1, 32, 6><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);
   else if (nout <= 32) k_vq_tma<8, 1, VT_KB, VT_STAGES><<<grid, VT_THREADS, shm, ctx->stream>>>(mIn, Out, ldo, n, kin, nout, Q, ldq, qtrans, alpha, beta);

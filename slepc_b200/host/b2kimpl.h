@@ -111,9 +111,13 @@ typedef struct _BVOps {
   PetscErrorCode (*dot)(BV, BV, Mat);
   PetscErrorCode (*dotvec)(BV, Vec, PetscScalar *);
   PetscErrorCode (*dotvec_local)(BV, Vec, PetscScalar *);
+  PetscErrorCode (*dotvec_begin)(BV, Vec, PetscScalar *);                    /* bvimpl.h:33 */
+  PetscErrorCode (*dotvec_end)(BV, Vec, PetscScalar *);                      /* bvimpl.h:34 */
   PetscErrorCode (*scale)(BV, PetscInt, PetscScalar);
   PetscErrorCode (*norm)(BV, PetscInt, NormType, PetscReal *);
   PetscErrorCode (*norm_local)(BV, PetscInt, NormType, PetscReal *);
+  PetscErrorCode (*norm_begin)(BV, PetscInt, NormType, PetscReal *);         /* bvimpl.h:38 */
+  PetscErrorCode (*norm_end)(BV, PetscInt, NormType, PetscReal *);           /* bvimpl.h:39 */
   PetscErrorCode (*normalize)(BV, PetscScalar *);
   PetscErrorCode (*matmult)(BV, Mat, BV);
   PetscErrorCode (*copy)(BV, BV);

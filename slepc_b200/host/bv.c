@@ -497,6 +497,132 @@ PetscErrorCode BVDotColumn(BV X, PetscInt j, PetscScalar *q)
   return PETSC_SUCCESS;
 }
 
+/* ---- split-phase reductions: bvglobal.c:188-260, 350-440, 703-800 ------------------------------------------------
+   PetscSplitReduction stand-in for BV types WITHOUT the *_begin/_end slots: local parts (dotvec_local / norm_local) are
+   queued in host memory, the first End reduces all of them in one collective per reduction type. */
+#define B2K_SR_MAX 4096
+static struct {
+  double lv[B2K_SR_MAX], gv[B2K_SR_MAX];
+  char   ismax[B2K_SR_MAX];
+  void  *owner[B2K_SR_MAX];
+  int    nbegin, nend, reduced;
+} g_sr;
+
+static PetscErrorCode BVSplitReductionEnd_Private(BV bv)
+{
+  if (g_sr.reduced) return PETSC_SUCCESS;
+  int nmax = 0;
+  for (int i = 0; i < g_sr.nbegin; i++) nmax += g_sr.ismax[i];
+  if (!nmax) {
+    memcpy(g_sr.gv, g_sr.lv, sizeof(double) * (size_t)g_sr.nbegin);
+    PetscCall(B2KCommAllreduce(bv->comm, g_sr.gv, g_sr.nbegin, 0, B2K_MEM_HOST));
+  } else {                                        /* mixed SUM / MAX: one collective per type */
+    static double tmp[B2K_SR_MAX];
+    for (int op = 0; op < 2; op++) {
+      int n = 0;
+      for (int i = 0; i < g_sr.nbegin; i++) if (g_sr.ismax[i] == op) tmp[n++] = g_sr.lv[i];
+      if (n) PetscCall(B2KCommAllreduce(bv->comm, tmp, n, op, B2K_MEM_HOST));
+      n = 0;
+      for (int i = 0; i < g_sr.nbegin; i++) if (g_sr.ismax[i] == op) g_sr.gv[i] = tmp[n++];
+    }
+  }
+  g_sr.reduced = 1;
+  return PETSC_SUCCESS;
+}
+static void BVSplitReductionPop_Private(int n)
+{
+  g_sr.nend += n;
+  if (g_sr.nend == g_sr.nbegin) g_sr.nbegin = g_sr.nend = g_sr.reduced = 0;   /* all results handed out: ready for the next batch */
+}
+
+PetscErrorCode BVDotVecBegin(BV X, Vec y, PetscScalar *m)
+{
+  BVCheckSizes(X);
+  PetscCheck(y, PETSC_ERR_ARG_NULL, "null vector");
+  PetscCheck(X->n == y->n, PETSC_ERR_ARG_INCOMP, "Mismatching local dimension X %d, y %d", X->n, y->n);
+  if (X->ops.dotvec_begin) { PetscCall(X->ops.dotvec_begin(X, y, m)); return PETSC_SUCCESS; }
+  BVCheckOp(X, dotvec_local);
+  const PetscInt nv = X->k - X->l;
+  PetscCheck(!g_sr.reduced, PETSC_ERR_ORDER, "Called before all BVxxxEnd() called");
+  PetscCheck(g_sr.nbegin + nv <= B2K_SR_MAX, PETSC_ERR_ARG_SIZ, "too many outstanding split reductions");
+  for (PetscInt i = 0; i < nv; i++) { g_sr.ismax[g_sr.nbegin + i] = 0; g_sr.owner[g_sr.nbegin + i] = (void *)X; }
+  PetscCall(X->ops.dotvec_local(X, y, g_sr.lv + g_sr.nbegin));
+  g_sr.nbegin += nv;
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVDotVecEnd(BV X, Vec y, PetscScalar *m)
+{
+  BVCheckSizes(X);
+  if (X->ops.dotvec_end) { PetscCall(X->ops.dotvec_end(X, y, m)); return PETSC_SUCCESS; }
+  const PetscInt nv = X->k - X->l;
+  PetscCall(BVSplitReductionEnd_Private(X));
+  PetscCheck(g_sr.nend + nv <= g_sr.nbegin, PETSC_ERR_ARG_WRONGSTATE, "Called BVxxxEnd() more times than BVxxxBegin()");
+  PetscCheck(nv == 0 || (void *)X == g_sr.owner[g_sr.nend], PETSC_ERR_ARG_WRONGSTATE, "Called BVxxxEnd() in a different order or with a different BV than BVxxxBegin()");
+  PetscScalar *mm = m ? m : X->buffer;
+  for (PetscInt i = 0; i < nv; i++) mm[i] = g_sr.gv[g_sr.nend + i];
+  BVSplitReductionPop_Private(nv);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVDotColumnBegin(BV X, PetscInt j, PetscScalar *m)
+{
+  BVCheckSizes(X);
+  PetscCheck(j >= 0, PETSC_ERR_ARG_OUTOFRANGE, "Index j must be non-negative");
+  PetscCheck(j < X->m, PETSC_ERR_ARG_OUTOFRANGE, "Index j=%d but BV only has %d columns", j, X->m);
+  const PetscInt ksave = X->k;
+  X->k = j;
+  Vec y;
+  PetscCall(BVGetColumn(X, j, &y));
+  PetscErrorCode ierr = BVDotVecBegin(X, y, m);
+  PetscCall(BVRestoreColumn(X, j, &y));
+  X->k = ksave;
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVDotColumnEnd(BV X, PetscInt j, PetscScalar *m)
+{
+  BVCheckSizes(X);
+  PetscCheck(j >= 0 && j < X->m, PETSC_ERR_ARG_OUTOFRANGE, "Index j=%d out of range", j);
+  const PetscInt ksave = X->k;
+  X->k = j;
+  PetscErrorCode ierr = BVDotVecEnd(X, NULL, m);
+  X->k = ksave;
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVNormColumnBegin(BV bv, PetscInt j, NormType type, PetscReal *val)
+{
+  BVCheckSizes(bv);
+  PetscCheck(j >= 0 && j < bv->m, PETSC_ERR_ARG_OUTOFRANGE, "Argument j has wrong value %d, the number of columns is %d", j, bv->m);
+  if (bv->ops.norm_begin) { PetscCall(bv->ops.norm_begin(bv, j, type, val)); return PETSC_SUCCESS; }
+  BVCheckOp(bv, norm_local);
+  PetscCheck(!g_sr.reduced, PETSC_ERR_ORDER, "Called before all BVxxxEnd() called");
+  PetscCheck(g_sr.nbegin < B2K_SR_MAX, PETSC_ERR_ARG_SIZ, "too many outstanding split reductions");
+  PetscReal lres;
+  PetscCall(bv->ops.norm_local(bv, j, type, &lres));
+  if (type == NORM_2 || type == NORM_FROBENIUS) lres = lres * lres;
+  g_sr.ismax[g_sr.nbegin] = (type == NORM_INFINITY) ? 1 : 0;
+  g_sr.owner[g_sr.nbegin] = (void *)bv;
+  g_sr.lv[g_sr.nbegin++] = lres;
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode BVNormColumnEnd(BV bv, PetscInt j, NormType type, PetscReal *val)
+{
+  BVCheckSizes(bv);
+  if (bv->ops.norm_end) { PetscCall(bv->ops.norm_end(bv, j, type, val)); return PETSC_SUCCESS; }
+  PetscCall(BVSplitReductionEnd_Private(bv));
+  PetscCheck(g_sr.nend < g_sr.nbegin, PETSC_ERR_ARG_WRONGSTATE, "Called BVxxxEnd() more times than BVxxxBegin()");
+  PetscCheck((void *)bv == g_sr.owner[g_sr.nend], PETSC_ERR_ARG_WRONGSTATE, "Called BVxxxEnd() in a different order or with a different BV than BVxxxBegin()");
+  const PetscReal g = g_sr.gv[g_sr.nend];
+  *val = (type == NORM_2 || type == NORM_FROBENIUS) ? sqrt(g) : g;
+  BVSplitReductionPop_Private(1);
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode BVNorm(BV bv, NormType type, PetscReal *val)
 {
   BVCheckSizes(bv);

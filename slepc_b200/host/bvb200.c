@@ -239,6 +239,94 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
   return PETSC_SUCCESS;
 }
 
+/* ---- split-phase reductions: the dotvec_begin/end, norm_begin/end slots (bvimpl.h:33-34,38-39) -------------------------
+   What the reference's one-sided Lanczos merges with BVNormColumnBegin + BVDotVecBegin … End (trlanczos.c:383-396): every Begin
+   launches its sweep with a LOCAL reduction into one shared device queue (any BV of type b200 of this process: U and V of
+   the SVD share it); the first End sums the whole queue over the GPUs in ONE short all-reduce (NVLink mailboxes, else
+   ncclAllReduce), copies it to pinned memory once and synchronises once; the other Ends only pick their numbers up. */
+#define SRQ_MAX 2048
+static struct {
+  double *d, *h;
+  int     n, nent, next;
+  struct { int off, cnt; void *owner; } e[64];
+  PetscBool reduced;
+} g_srq;
+
+static PetscErrorCode BVSplitQueuePush_B200(BV bv, PetscInt cnt, double **slot)
+{
+  if (!g_srq.d) {
+    B2KCall(b2k_malloc(CTX(), (void **)&g_srq.d, sizeof(double) * SRQ_MAX));
+    B2KCall(b2k_host_alloc((void **)&g_srq.h, sizeof(double) * SRQ_MAX));
+  }
+  PetscCheck(!g_srq.reduced, PETSC_ERR_ORDER, "Called before all BVxxxEnd() called");
+  PetscCheck(g_srq.nent < 64 && g_srq.n + cnt <= SRQ_MAX, PETSC_ERR_ARG_SIZ, "too many outstanding split reductions");
+  g_srq.e[g_srq.nent].off = g_srq.n; g_srq.e[g_srq.nent].cnt = (int)cnt; g_srq.e[g_srq.nent].owner = (void *)bv;
+  *slot = g_srq.d + g_srq.n;
+  g_srq.n += (int)((cnt + 1) & ~1);               /* even offsets: 16-byte aligned outputs */
+  g_srq.nent++;
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVSplitQueuePop_B200(BV bv, PetscInt cnt, const double **vals)
+{
+  b2k_ctx ctx = CTX();
+  if (!g_srq.reduced) {
+    PetscCall(B2KCommAllreduce(bv->comm, g_srq.d, g_srq.n, 0, B2K_MEM_DEVICE));
+    B2KCall(b2k_d2h_async(ctx, g_srq.h, g_srq.d, sizeof(double) * (size_t)g_srq.n));
+    B2KCall(b2k_ctx_sync(ctx));
+    g_srq.reduced = PETSC_TRUE;
+    g_srq.next = 0;
+  }
+  PetscCheck(g_srq.next < g_srq.nent, PETSC_ERR_ARG_WRONGSTATE, "Called BVxxxEnd() more times than BVxxxBegin()");
+  PetscCheck(g_srq.e[g_srq.next].owner == (void *)bv && g_srq.e[g_srq.next].cnt == (int)cnt, PETSC_ERR_ARG_WRONGSTATE,
+             "Called BVxxxEnd() in a different order or with a different BV than BVxxxBegin()");
+  *vals = g_srq.h + g_srq.e[g_srq.next].off;
+  if (++g_srq.next == g_srq.nent) { g_srq.n = g_srq.nent = g_srq.next = 0; g_srq.reduced = PETSC_FALSE; }
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode BVDotVecBegin_B200(BV X, Vec y, PetscScalar *m)
+{
+  (void)m;
+  BV_B200 *d = (BV_B200 *)X->data;
+  const PetscInt k = X->k - X->l;
+  PetscCheck(y->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "BV type b200 needs device vectors");
+  double *slot;
+  PetscCall(BVSplitQueuePush_B200(X, k, &slot));
+  if (k > 0) B2KCall(b2k_dotvec(CTX(), COL(X, d, X->l), X->ld, X->n, k, y->array, slot));     /* reduce scope closed: local sums */
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVDotVecEnd_B200(BV X, Vec y, PetscScalar *m)
+{
+  (void)y;
+  const PetscInt k = X->k - X->l;
+  const double *v;
+  PetscCall(BVSplitQueuePop_B200(X, k, &v));
+  PetscScalar *mm = m ? m : X->buffer;
+  if (k > 0) memcpy(mm, v, sizeof(double) * (size_t)k);
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVNormBegin_B200(BV bv, PetscInt j, NormType type, PetscReal *val)
+{
+  (void)val;
+  BV_B200 *d = (BV_B200 *)bv->data;
+  PetscCheck(type == NORM_2 || type == NORM_FROBENIUS, PETSC_ERR_SUP, "split-phase norms of type b200 are 2-norms");
+  const double *X = (j < 0) ? COL(bv, d, bv->l) : COL(bv, d, j);
+  const PetscInt k = (j < 0) ? bv->k - bv->l : 1;
+  double *slot;
+  PetscCall(BVSplitQueuePush_B200(bv, 1, &slot));
+  B2KCall(b2k_sumsq(CTX(), X, bv->ld, bv->n, k > 0 ? k : 1, slot));
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVNormEnd_B200(BV bv, PetscInt j, NormType type, PetscReal *val)
+{
+  (void)j; (void)type;
+  const double *v;
+  PetscCall(BVSplitQueuePop_B200(bv, 1, &v));
+  *val = sqrt(v[0]);
+  return PETSC_SUCCESS;
+}
+
 /* ---- scale / norm / normalize: svec.c:150-175, sveccuda.cu:164-214, bvglobal.c:836 ----------------- */
 static PetscErrorCode BVScale_B200(BV bv, PetscInt j, PetscScalar alpha)
 {
@@ -474,9 +562,13 @@ PetscErrorCode BVCreate_B200(BV bv)
   bv->ops.dot = BVDot_B200;
   bv->ops.dotvec = BVDotVec_B200;
   bv->ops.dotvec_local = BVDotVec_Local_B200;
+  bv->ops.dotvec_begin = BVDotVecBegin_B200;
+  bv->ops.dotvec_end = BVDotVecEnd_B200;
   bv->ops.scale = BVScale_B200;
   bv->ops.norm = BVNorm_B200;
   bv->ops.norm_local = BVNorm_Local_B200;
+  bv->ops.norm_begin = BVNormBegin_B200;
+  bv->ops.norm_end = BVNormEnd_B200;
   bv->ops.normalize = BVNormalize_B200;
   bv->ops.matmult = BVMatMult_B200;
   bv->ops.copy = BVCopy_B200;

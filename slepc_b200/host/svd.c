@@ -276,26 +276,29 @@ static PetscErrorCode SVDOrthogonalizeCGS_Private(BV V, PetscInt i, PetscScalar 
   return PETSC_SUCCESS;
 }
 
-/* ||u_{i-1}|| together with the first CGS pass of v_i (the reference merges both reductions into one MPI_Allreduce with
-   the Begin/End split calls, trlanczos.c:385-400; here they are two device reductions on the same stream), then the
+/* ||u_{i-1}|| together with the first CGS pass of v_i, merged into ONE reduction with the split-phase calls exactly as
+   trlanczos.c:383-396 does (BVNormColumnBegin + BVDotVecBegin … End: one all-reduce, one host synchronisation), then the
    scaled update v_i <- v_i/a - V (h/a) and the refinement decision */
 static PetscErrorCode SVDOneSideStep_Private(SVD svd, PetscInt i, PetscScalar *work, BVOrthogRefineType refine, PetscReal eta, PetscReal *pa, PetscReal *pb)
 {
   BV V = svd->V, U = svd->U;
   PetscReal a, b;
-  PetscCall(BVNormColumn(U, i - 1, NORM_2, &a));
+  Vec vi = NULL;
+  PetscCall(BVNormColumnBegin(U, i - 1, NORM_2, &a));
   if (refine == BV_ORTHOG_REFINE_IFNEEDED) {
-    Vec vi;
     PetscCall(BVSetActiveColumns(V, 0, i + 1));
     PetscCall(BVGetColumn(V, i, &vi));
-    PetscErrorCode ierr = BVDotVec(V, vi, work);        /* work[i] = v_i^T v_i comes with the same sweep */
-    PetscCall(BVRestoreColumn(V, i, &vi));
-    PetscCall(ierr);
-    PetscCall(BVSetActiveColumns(V, 0, i));
+    PetscCall(BVDotVecBegin(V, vi, work));               /* work[i] = v_i^T v_i comes with the same sweep */
   } else {
     PetscCall(BVSetActiveColumns(V, 0, i));
-    PetscCall(BVDotColumn(V, i, work));
+    PetscCall(BVDotColumnBegin(V, i, work));
   }
+  PetscCall(BVNormColumnEnd(U, i - 1, NORM_2, &a));
+  if (refine == BV_ORTHOG_REFINE_IFNEEDED) {
+    PetscCall(BVDotVecEnd(V, vi, work));
+    PetscCall(BVRestoreColumn(V, i, &vi));
+    PetscCall(BVSetActiveColumns(V, 0, i));
+  } else PetscCall(BVDotColumnEnd(V, i, work));
   PetscCall(BVScaleColumn(U, i - 1, 1.0 / a));
   for (PetscInt j = 0; j < i; j++) work[j] = work[j] / a;
   PetscCall(BVMultColumn(V, -1.0, 1.0 / a, i, work));
