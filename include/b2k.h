@@ -166,12 +166,16 @@ int  b2k_csr_bytes(b2k_csr A, int64_t *bytes);
 #define B2K_SPMV_KERNEL_SELL            2   /* k_spmv_sell                            */
 #define B2K_SPMV_KERNEL_SELL_PIPE       3   /* k_spmv_sell_pipe<false> (no ghosts)    */
 #define B2K_SPMV_KERNEL_SELL_PIPE_GHOST 4   /* k_spmv_sell_pipe<true>  (halo columns) */
+#define B2K_SPMV_KERNEL_SPMM            5   /* k_spmm_sell (block of vectors)         */
 int  b2k_csr_last_kernel(b2k_csr A, int *which);
 /* the bulk-copy pipeline kernel runs when the SELL copy has at least this many chunks (default 4 per SM, i.e. about 6e5 rows;
    env B2K_SPMV_PIPE_MIN_CHUNKS); < 0 restores the default.  Tests lower it to push small matrices through the pipeline. */
 int  b2k_spmv_set_pipe_min_chunks(int min_chunks);
 /* y = A [x ; xghost]                                                                               */
 int  b2k_csr_spmv(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y);
+/* Y(:,0:k) = A [X ; XG](:,0:k): sparse matrix times a block of k vectors (column-major, leading dimensions ldx / ldg / ldy),
+   the matrix read once per 16 columns — BVMatMult in BV_MATMULT_MAT mode (svec.c:203-231, PETSc MatMatMult)            */
+int  b2k_csr_spmm(b2k_ctx ctx, b2k_csr A, const double *X, int64_t ldx, const double *XG, int64_t ldg, double *Y, int64_t ldy, int k);
 /* y = A x - sigma*xdiag   (shifted operator of STSHIFT, shift.c:79; xdiag = x rows owned here)    */
 int  b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y, double sigma);
 /* storage used by b2k_csr_spmv: 0 CSR-stream only, 1 (default) SELL-32 copy when its padding is <= 25 %, 2 SELL-32 always;

@@ -74,6 +74,7 @@ SIGNATURES = {
     "b2k_csr_bytes": [c_vp, ctypes.POINTER(c_i64)],
     "b2k_csr_last_kernel": [c_vp, ctypes.POINTER(c_int)],
     "b2k_spmv_set_pipe_min_chunks": [c_int],
+    "b2k_csr_spmm": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int],
     "b2k_csr_spmv": [c_vp, c_vp, c_vp, c_vp, c_vp],
     "b2k_csr_spmv_shift": [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl],
     "b2k_csr_laplacian": [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),

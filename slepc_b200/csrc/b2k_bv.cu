@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *part, 
         reinterpret_cast<unsigned long long *>(xg.box[xg.rank] + B2K_XG_DATA_ELEMS) + (par * B2K_XG_MAXR + p) * B2K_XG_MAXB + blockIdx.x;
     const long long t0 = clock64();
     while (*mine < seq) {
-      if (clock64() - t0 > 120000000000LL) { *((volatile int *)xg.err) = 1; break; }   /* ~60 s: a peer is missing; fail, do not hang */
+      if (clock64() - t0 > xg.spin_limit) { *((volatile int *)xg.err) = 1; break; }   /* ~60 s: a peer is missing; fail, do not hang */
     }
     __threadfence_system();
   }
@@ -833,10 +833,32 @@ extern "C" int b2k_mult_inplace(b2k_ctx ctx, double *V, int64_t ld, int64_t n, i
   return launch_gemm_ts(ctx, V + (int64_t)s * ld, ld, V, ld, n, k, e - s, Qb, ldq, trans, 1.0, 0.0);
 }
 
+int b2k_gram_tma_launch(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx, double *M,
+                        int ldm);   /* b2k_gram_tma.cu (one sweep, FP64 tensor cores) */
+
 extern "C" int b2k_dot(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t ldx, int64_t n, int ky, int kx, double *M,
                        int ldm)
 {
-  /* M(:,j) = Y^T X(:,j): kx fused-reduction sweeps (not on the Krylov hot path; tests + block GS) */
+  /* one sweep of Y and X per 64 x 64 block of M (k_gram_tma); blocks that do not start at M(0,0) with ldm == ky go through
+     the context's scratch and a strided copy */
+  if (ky > 0 && kx > 0 && n > 0) {
+    bool ok = true;
+    for (int y0 = 0; ok && y0 < ky; y0 += 64) {
+      for (int x0 = 0; ok && x0 < kx; x0 += 64) {
+        const int by = ky - y0 < 64 ? ky - y0 : 64, bx = kx - x0 < 64 ? kx - x0 : 64;
+        const bool direct = (ky <= 64 && kx <= 64 && ldm == ky);
+        double *dst = direct ? M : ctx->dscratch;
+        const int rc = b2k_gram_tma_launch(ctx, Y + (int64_t)y0 * ldy, ldy, X + (int64_t)x0 * ldx, ldx, n, by, bx, dst, by);
+        if (rc == -1) { ok = false; break; }
+        if (rc) return rc;
+        if (!direct)
+          CK(cudaMemcpy2DAsync(M + (int64_t)x0 * ldm + y0, sizeof(double) * (size_t)ldm, ctx->dscratch, sizeof(double) * (size_t)by,
+                               sizeof(double) * (size_t)by, (size_t)bx, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    }
+    if (ok) return B2K_OK;
+  }
+  /* shapes the tensor-map kernel does not take (short or unaligned blocks): M(:,j) = Y^T X(:,j), kx fused-reduction sweeps */
   for (int j = 0; j < kx; j++) {
     int rc = launch_dotvec(ctx, Y, ldy, n, ky, X + (int64_t)j * ldx, M + (int64_t)j * ldm, 0);
     if (rc) return rc;

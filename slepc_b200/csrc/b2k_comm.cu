@@ -154,6 +154,7 @@ extern "C" int b2k_comm_p2p_open(b2k_comm c, const void *all_handles)
   int *derr = NULL;
   CK(cudaHostGetDevicePointer((void **)&derr, c->err_host, 0));
   c->xg.err = derr;
+  c->xg.spin_limit = b2k_spin_limit();
   c->p2p_open = 1;
   c->ctx->xg = &c->xg;
   c->ctx->xg_on = 0;

@@ -41,6 +41,7 @@ struct hl_args {
   u64     *peer_ack[HL_MAXP];          /* sender p's ack[my send slot there]                          */
   const u64 *my_arrived;               /* my arrived[0..nrecv)                                        */
   int     *err;
+  long long spin_limit;
 };
 
 struct b2k_halo_s {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ x,
     const long long t0 = clock64();
     go = 1;
     while (*((volatile const u64 *)d.my_ack) + 2 < seq) {
-      if (clock64() - t0 > 120000000000LL) { *((volatile int *)a.err) = 2; go = 0; break; }
+      if (clock64() - t0 > a.spin_limit) { *((volatile int *)a.err) = 2; go = 0; break; }
     }
     __threadfence_system();
   }
@@ -113,7 +114,7 @@ __global__ void k_halo_wait(const hl_args a, u64 seq)
   if (threadIdx.x < a.nrecv) {
     const long long t0 = clock64();
     while (*((volatile const u64 *)(a.my_arrived + threadIdx.x)) < seq) {
-      if (clock64() - t0 > 120000000000LL) { *((volatile int *)a.err) = 3; break; }
+      if (clock64() - t0 > a.spin_limit) { *((volatile int *)a.err) = 3; break; }
     }
     __threadfence_system();
   }
@@ -195,6 +196,7 @@ extern "C" int b2k_halo_create(b2k_comm comm, int nrecv, const int *recvrank, co
   int *derr = NULL;
   CK(cudaHostGetDevicePointer((void **)&derr, h->err_host, 0));
   a->err = derr;
+  a->spin_limit = b2k_spin_limit();
   a->my_arrived = hl_arrived(h->block, dbytes);
   unsigned int *done = (unsigned int *)(hl_ack(h->block, dbytes) + HL_MAXP);
   long long soff = 0;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "b2k.h"
 
 /* cross-GPU one-shot reduction over NVLink peer memory (b2k_comm.cu, k_reduce_partials_xg in b2k_bv.cu): every rank owns
@@ -18,7 +19,15 @@ struct b2k_xg_s {
   int     rank, size;
   double *box[B2K_XG_MAXR];           /* box[p] = mailbox of rank p as mapped in THIS process (box[rank] is local) */
   int    *err;                        /* mapped pinned host flag: set when a peer did not show up in time  */
+  long long spin_limit;               /* clock64 ticks a kernel waits for a peer before it raises err (env B2K_SPIN_TIMEOUT_S, default 60 s) */
 };
+static inline long long b2k_spin_limit(void)
+{
+  const char *e = getenv("B2K_SPIN_TIMEOUT_S");
+  double s = e ? atof(e) : 60.0;
+  if (!(s > 0.0)) s = 60.0;
+  return (long long)(s * 2.0e9);
+}
 
 struct b2k_ctx_s {
   int          device;

@@ -85,6 +85,9 @@ typedef struct _MatOps {
   PetscErrorCode (*mult)(Mat, Vec, Vec);
   PetscErrorCode (*multtranspose)(Mat, Vec, Vec);
   PetscErrorCode (*destroy)(Mat);
+  /* optional: Y(:,0:k) = A X(:,0:k) on column-major blocks in the Mat's own memory space (MatMatMult on a dense block, what
+     BVMatMult uses in BV_MATMULT_MAT mode, svec.c:203-231); NULL = the caller loops over the columns with mult */
+  PetscErrorCode (*multblock)(Mat, const PetscScalar *, PetscInt, PetscScalar *, PetscInt, PetscInt);
 } MatOps;
 
 struct _p_Mat {

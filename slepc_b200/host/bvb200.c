@@ -444,16 +444,22 @@ static PetscErrorCode BVDot_B200(BV X, BV Y, Mat M)
   return PETSC_SUCCESS;
 }
 
-/* column loop of sveccuda.cu:269-303 */
+/* BVMatMult: the whole active block at once when the Mat can (BV_MATMULT_MAT, svec.c:203-231: the matrix is read once per 16
+   columns by b2k_csr_spmm), the column loop of sveccuda.cu:269-303 otherwise (MatShell operators) */
 static PetscErrorCode BVMatMult_B200(BV V, Mat A, BV W)
 {
   BV_B200 *v = (BV_B200 *)V->data, *w = (BV_B200 *)W->data;
+  const PetscInt k = V->k - V->l;
+  if (A->ops.multblock && A->mem == B2K_MEM_DEVICE && k > 1) {
+    PetscCall(A->ops.multblock(A, COL(V, v, V->l), V->ld, COL(W, w, W->l), W->ld, k));
+    return PETSC_SUCCESS;
+  }
   Vec x, y;
   PetscCall(VecCreateWithArray(B2K_MEM_DEVICE, V->n, V->N, NULL, &x));
   PetscCall(VecCreateWithArray(B2K_MEM_DEVICE, W->n, W->N, NULL, &y));
   x->rstart = V->row0; y->rstart = W->row0;
   PetscErrorCode ierr = PETSC_SUCCESS;
-  for (PetscInt j = 0; j < V->k - V->l && !ierr; j++) {
+  for (PetscInt j = 0; j < k && !ierr; j++) {
     x->array = COL(V, v, V->l + j);
     y->array = COL(W, w, W->l + j);
     ierr = MatMult(A, x, y);

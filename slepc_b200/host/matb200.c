@@ -30,6 +30,8 @@ typedef struct {
   double   *zghost, *rbuf;
   /* default on one NVSwitch box (B2K_HALO_P2P=0 turns it off): the forward halo pushed over NVLink peer memory instead of ncclSend/ncclRecv */
   b2k_halo  halo;
+  double   *gblock;          /* device: ghost values of a block of vectors, nghost x gblock_cols (MatMultBlock) */
+  PetscInt  gblock_cols;
 } Mat_B200CSR;
 
 #define CTX() B2KGetContext()
@@ -94,6 +96,33 @@ static PetscErrorCode MatMult_B200CSR(Mat A, Vec x, Vec y)
   const double *ghost;
   PetscCall(MatHaloExchange_B200CSR(A, x->array, &ghost));
   B2KCall(b2k_csr_spmv(CTX(), a->A, x->array, ghost, y->array));
+  return PETSC_SUCCESS;
+}
+
+/* Y(:,0:k) = A X(:,0:k): one halo exchange per column into a ghost block, then ONE block product that reads the matrix once
+   per 16 columns (b2k_csr_spmm) — BVMatMult in BV_MATMULT_MAT mode (svec.c:203-231) */
+static PetscErrorCode MatMultBlock_B200CSR(Mat A, const PetscScalar *X, PetscInt ldx, PetscScalar *Y, PetscInt ldy, PetscInt k)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  b2k_ctx ctx = CTX();
+  int size = 1;
+  PetscCall(B2KCommGetRank(B2KCommWorld(), NULL, &size));
+  if (size == 1 || (a->nghost == 0 && a->nsend == 0)) {
+    B2KCall(b2k_csr_spmm(ctx, a->A, X, ldx, NULL, 0, Y, ldy, k));
+    return PETSC_SUCCESS;
+  }
+  if (a->nghost && a->gblock_cols < k) {
+    if (a->gblock) B2KCall(b2k_free(ctx, a->gblock));
+    a->gblock = NULL;
+    B2KCall(b2k_malloc(ctx, (void **)&a->gblock, sizeof(double) * (size_t)a->nghost * (size_t)k));
+    a->gblock_cols = k;
+  }
+  for (PetscInt j = 0; j < k; j++) {              /* collective per column, also on a rank that only sends */
+    const double *ghost;
+    PetscCall(MatHaloExchange_B200CSR(A, X + (size_t)j * (size_t)ldx, &ghost));
+    if (a->nghost) B2KCall(b2k_d2d(ctx, a->gblock + (size_t)j * (size_t)a->nghost, ghost, sizeof(double) * (size_t)a->nghost));
+  }
+  B2KCall(b2k_csr_spmm(ctx, a->A, X, ldx, a->gblock, a->nghost, Y, ldy, k));
   return PETSC_SUCCESS;
 }
 
@@ -185,7 +214,7 @@ static PetscErrorCode MatDestroy_B200CSR(Mat A)
   if (ctx) {
     if (a->halo) b2k_halo_destroy(a->halo);         /* collective */
     b2k_csr_destroy(ctx, a->ATown); b2k_csr_destroy(ctx, a->ATgh);
-    b2k_free(ctx, a->zghost); b2k_free(ctx, a->rbuf);
+    b2k_free(ctx, a->zghost); b2k_free(ctx, a->rbuf); b2k_free(ctx, a->gblock);
     b2k_csr_destroy(ctx, a->A);
     b2k_free(ctx, a->xghost); b2k_free(ctx, a->d_sendidx); b2k_free(ctx, a->sendbuf);
   }
@@ -206,6 +235,7 @@ static PetscErrorCode MatSetUp_B200CSR(Mat A, PetscInt M, PetscInt N, PetscInt r
   A->data = a;
   A->ops.mult = MatMult_B200CSR;
   A->ops.multtranspose = MatMultTranspose_B200CSR;
+  A->ops.multblock = MatMultBlock_B200CSR;
   A->ops.destroy = MatDestroy_B200CSR;
   *out = a;
   return PETSC_SUCCESS;

@@ -139,6 +139,7 @@ EPS_HEP, EPS_NHEP = 1, 3
 EPS_LARGEST_MAGNITUDE, EPS_SMALLEST_MAGNITUDE, EPS_LARGEST_REAL, EPS_SMALLEST_REAL = 1, 2, 3, 4
 EPS_LARGEST_IMAGINARY, EPS_SMALLEST_IMAGINARY, EPS_TARGET_MAGNITUDE, EPS_TARGET_REAL = 5, 6, 7, 8
 EPS_ERROR_ABSOLUTE, EPS_ERROR_RELATIVE = 0, 1
+EPS_CONVERGED_TOL, EPS_CONVERGED_USER, EPS_DIVERGED_ITS, EPS_DIVERGED_BREAKDOWN, EPS_CONVERGED_ITERATING = 1, 2, -1, -2, 0
 SVD_LARGEST, SVD_SMALLEST = 0, 1
 SVD_ERROR_ABSOLUTE, SVD_ERROR_RELATIVE = 0, 1
 DS_MAT_A, DS_MAT_T, DS_MAT_Q, DS_MAT_X, DS_MAT_U, DS_MAT_V = 0, 3, 5, 7, 9, 10

@@ -16,6 +16,13 @@ from slepc_b200.slepc import S
 pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
 
 
+def stage(msg):
+    """progress line per rank (stderr, flushed): tells where a hung run stopped"""
+    import sys
+    import time
+    print(f"[mgpu rank {dist.get_rank()} t={time.time() % 1000:.2f}] {msg}", file=sys.stderr, flush=True)
+
+
 def gather(x):
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, x)
@@ -102,6 +109,7 @@ def case_markov(rank, world, m=40):
 
 
 def case_svd(rank, world, Mr=3000, Nc=1100):
+    stage("svd: build A")
     A = csr_mat(lambda a, b: matgen.random_sparse_rows(Mr, Nc, 6, seed=3, r0=a, r1=b), Mr, Nc, rank, world)
     import scipy.sparse as sp
     rp, ci, v = matgen.random_sparse_rows(Mr, Nc, 6, seed=3)
@@ -111,7 +119,9 @@ def case_svd(rank, world, Mr=3000, Nc=1100):
     def at_rows(a, b):
         loc = AT[a:b]
         return loc.indptr.astype(np.int32), loc.indices.astype(np.int32), loc.data.astype(np.float64)
+    stage("svd: build At")
     At = csr_mat(at_rows, Nc, Mr, rank, world)
+    stage("svd: two-sided solve, explicit transpose")
     svd = SL.SVD(A, At)
     S.SVDSetDimensions(svd.h, 5, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
     svd.solve()
@@ -119,19 +129,23 @@ def case_svd(rank, world, Mr=3000, Nc=1100):
     res = dict(nconv=svd.nconv, sigma=[svd.triplet(i) for i in range(svd.nconv)], errs=[svd.error(i) for i in range(svd.nconv)],
                ref=list(sref[:5]))
     # the same solve without an explicit A^T: MatMultTranspose = local transpose products + reverse halo (scatter-add)
+    stage("svd: two-sided solve, implicit transpose")
     svd2 = SL.SVD(A)
     S.SVDSetDimensions(svd2.h, 5, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
     svd2.solve()
     res.update(nconv_impl=svd2.nconv, sigma_impl=[svd2.triplet(i) for i in range(svd2.nconv)],
                errs_impl=[svd2.error(i) for i in range(svd2.nconv)])
     # one-sided recurrence (fused split reduction) on the same matrix
+    stage("svd: one-sided solve")
     svd3 = SL.SVD(A, At)
     S.SVDSetDimensions(svd3.h, 5, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
     S.SVDTRLanczosSetOneSide(svd3.h, 1)
     svd3.solve()
     res.update(nconv_one=svd3.nconv, sigma_one=[svd3.triplet(i) for i in range(svd3.nconv)], errs_one=[svd3.error(i) for i in range(svd3.nconv)])
+    stage("svd: destroy")
     for o in (svd, svd2, svd3, At, A):
         o.destroy()
+    stage("svd: done")
     return res
 
 

@@ -272,3 +272,39 @@ def test_svd_wide_matrix_swaps():
         uu, vv = u.get_values(), v.get_values()
         assert np.linalg.norm(A @ vv - s * uu) < 1e-7 * s
         assert svd.error(i) < 5e-8
+
+
+def test_bv_split_phase_reductions():
+    """BVNormColumnBegin/End, BVDotVecBegin/End, BVDotColumnBegin/End (bvglobal.c:188-260,350-440,703-800): queued local parts,
+    ONE reduction at the first End, results equal to the blocking calls; Ends out of order are an error (the PetscSplitReduction
+    fallback of a BV type without the *_begin/_end slots, which is what the CPU plug-in is)."""
+    rng = np.random.default_rng(21)
+    X, U = make_bv(60, 6), make_bv(35, 3)
+    X.from_numpy(rng.standard_normal((60, 6)))
+    U.from_numpy(rng.standard_normal((35, 3)))
+    Xh, Uh = X.to_numpy(), U.to_numpy()
+    a, b = c_dbl(), c_dbl()
+    m1, m2 = np.zeros(5), np.zeros(4)
+    X.set_active(0, 5)
+    S.BVNormColumnBegin(U.h, 1, SL.NORM_2, ctypes.byref(a))
+    v5 = SC.with_column(X, 5, lambda v: S.BVDotVecBegin(X.h, v, m1.ctypes.data_as(ctypes.c_void_p)))
+    S.BVDotColumnBegin(X.h, 4, m2.ctypes.data_as(ctypes.c_void_p))
+    S.BVNormColumnBegin(U.h, 2, SL.NORM_2, ctypes.byref(b))
+    S.BVNormColumnEnd(U.h, 1, SL.NORM_2, ctypes.byref(a))
+    S.BVDotVecEnd(X.h, None, m1.ctypes.data_as(ctypes.c_void_p))
+    S.BVDotColumnEnd(X.h, 4, m2.ctypes.data_as(ctypes.c_void_p))
+    S.BVNormColumnEnd(U.h, 2, SL.NORM_2, ctypes.byref(b))
+    assert np.isclose(a.value, np.linalg.norm(Uh[:, 1]), rtol=1e-14) and np.isclose(b.value, np.linalg.norm(Uh[:, 2]), rtol=1e-14)
+    assert np.allclose(m1, Xh[:, :5].T @ Xh[:, 5], rtol=1e-13, atol=1e-13)
+    assert np.allclose(m2, Xh[:, :4].T @ Xh[:, 4], rtol=1e-13, atol=1e-13)
+    # a second batch works after the first was fully collected, and a wrong order is refused
+    S.BVNormColumnBegin(U.h, 0, SL.NORM_2, ctypes.byref(a))
+    S.BVDotColumnBegin(X.h, 3, m2.ctypes.data_as(ctypes.c_void_p))
+    with pytest.raises(SL.SlepcError):
+        S.BVDotColumnEnd(X.h, 3, m2.ctypes.data_as(ctypes.c_void_p))
+    SL.S.B2KClearError() if hasattr(SL.S, "B2KClearError") else None
+    S.BVNormColumnEnd(U.h, 0, SL.NORM_2, ctypes.byref(a))
+    S.BVDotColumnEnd(X.h, 3, m2.ctypes.data_as(ctypes.c_void_p))
+    assert np.isclose(a.value, np.linalg.norm(Uh[:, 0]), rtol=1e-14)
+    assert np.allclose(m2[:3], Xh[:, :3].T @ Xh[:, 3], rtol=1e-13, atol=1e-13)
+    X.destroy(); U.destroy()

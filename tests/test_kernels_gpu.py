@@ -256,6 +256,40 @@ def test_dot(ctx):
     assert np.allclose(got[:ky], Y[:n].T @ X[:n], rtol=1e-12, atol=1e-10)
 
 
+@pytest.mark.parametrize("n,ky,kx,same", [(4099, 5, 7, False), (50002, 64, 64, False), (50002, 64, 64, True), (131072, 33, 17, False),
+                                          (70001, 24, 24, True), (20000, 40, 9, True), (30000, 100, 70, False), (30000, 130, 130, True),
+                                          (1 << 20, 32, 32, True), (3000, 8, 8, True)])
+def test_dot_one_sweep_tensor_core_gram(ctx, n, ky, kx, same):
+    """b2k_dot = k_gram_tma (one sweep of Y and X, DMMA) against numpy and against the column-by-column sweeps it replaces
+    (B2K_GRAM_TMA=0 is a process-wide switch, so the reference here is b2k_dotvec per column): odd n (zero-filled tail rows),
+    column counts that are not multiples of 8, more than 64 columns (64 x 64 blocks through the scratch area), X == Y (the Gram
+    matrix of BVOrthogonalize CHOL / SVQB, read once), leading dimension of M larger than ky."""
+    from slepc_b200._b2k import check
+    ld = n + (n % 2) + 2
+    Y, dY, pY = _mk(ctx, n, ky, ld, 51)
+    if same:
+        X, pX, kx = Y, pY, min(kx, ky)
+    else:
+        X, dX, pX = _mk(ctx, n, kx, ld, 52)
+    for ldm in (ky, ky + 3):
+        M = ctx.empty(ldm * kx)
+        check(ctx.lib.b2k_memset0(ctx.h, M.ptr, 8 * ldm * kx))
+        check(ctx.lib.b2k_dot(ctx.h, pY, ld, pX, ld, n, ky, kx, M.ptr, ldm))
+        got = M.to_host((ldm, kx))
+        ref = Y[:n, :ky].T @ X[:n, :kx]
+        assert np.allclose(got[:ky], ref, rtol=1e-12, atol=1e-11 * np.sqrt(n))
+        assert np.array_equal(got[ky:], np.zeros((ldm - ky, kx)))
+        M2 = ctx.empty(ldm * kx)
+        check(ctx.lib.b2k_dot(ctx.h, pY, ld, pX, ld, n, ky, kx, M2.ptr, ldm))          # bit-reproducible run to run
+        assert np.array_equal(M2.to_host((ldm, kx))[:ky], got[:ky])
+        col = ctx.empty(ky)
+        for j in (0, kx - 1):
+            check(ctx.lib.b2k_dotvec(ctx.h, pY, ld, n, ky, pX + 8 * j * ld, col.ptr))
+            assert np.allclose(col.to_host(), got[:ky, j], rtol=1e-12, atol=1e-11 * np.sqrt(n))
+        for a in (M, M2, col):
+            a.free()
+
+
 def _spmv(ctx, A, x, xg=None, sell=1, sigma=None):
     from slepc_b200._b2k import check
     check(ctx.lib.b2k_spmv_set_sell(sell))

@@ -36,11 +36,17 @@ def run_case(case, world, tmp_path, extra_env=None, tag=""):
     logs = []
     for p in procs:
         try:
-            o, _ = p.communicate(timeout=300)
+            o, _ = p.communicate(timeout=240)
         except subprocess.TimeoutExpired:
             for q in procs:
                 q.kill()
-            raise
+            tails = []
+            for q in procs:
+                try:
+                    tails.append((q.communicate(timeout=10)[0] or "")[-2000:])
+                except Exception:                      # noqa: BLE001
+                    tails.append("<no output>")
+            pytest.fail(f"{case} on {world} ranks hung (240 s); output of the ranks:\n" + "\n----\n".join(tails))
         logs.append(o)
     assert all(p.returncode == 0 for p in procs), "\n".join(l[-3000:] for l in logs)
     return json.load(open(out))

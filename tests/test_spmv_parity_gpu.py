@@ -281,3 +281,47 @@ def test_csr_arrays_come_back_after_the_drop(ctx):
     _check(ctx.lib.b2k_csr_bytes(h, ctypes.byref(b1)))
     assert b1.value == b0.value
     _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+
+
+@pytest.mark.parametrize("k", [1, 5, 8, 16, 23, 40])
+@pytest.mark.parametrize("kind", ["lap3", "random_ghost", "empty_rows"])
+def test_spmm_block_of_vectors(ctx, kind, k):
+    """b2k_csr_spmm (k_spmm_sell: Y = A X for k vectors, the matrix read once per 16 columns — BVMatMult in BV_MATMULT_MAT mode,
+    svec.c:203-231) against scipy, leading dimensions larger than the row counts, ghost block included"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(17 + k)
+    if kind == "lap3":
+        A = O.laplacian_3d(23, 17, 19).tocsr()
+        ncl = A.shape[1]
+    elif kind == "random_ghost":
+        A = sp.random(30011, 26003, density=12 / 26003, random_state=5, format="csr")
+        ncl = 20000
+    else:
+        A = _irregular("empty_rows", rng)
+        ncl = A.shape[1]
+    A.sort_indices()
+    n, nc = A.shape
+    ng = nc - ncl
+    ldx, ldg, ldy = ncl + 2, ng + 4, n + 6
+    X = np.zeros((ldx, k), order="F"); X[:ncl] = rng.standard_normal((ncl, k))
+    G = np.zeros((max(ldg, 1), k), order="F"); G[:ng] = rng.standard_normal((ng, k))
+    h = ctypes.c_void_p()
+    rp = A.indptr.astype(np.int32); ci = A.indices.astype(np.int32); va = A.data.astype(np.float64)
+    _check(ctx.lib.b2k_spmv_set_sell(2))
+    try:
+        _check(ctx.lib.b2k_csr_create(ctx.h, n, ncl, ng, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h)))
+    finally:
+        _check(ctx.lib.b2k_spmv_set_sell(1))
+    dX, dG = ctx.to_device(X), ctx.to_device(G)
+    dY = ctx.to_device(np.full((ldy, k), 7.0, order="F"))
+    _check(ctx.lib.b2k_csr_spmm(ctx.h, h, dX.ptr, ldx, dG.ptr if ng else None, ldg, dY.ptr, ldy, k))
+    ctx.sync()
+    assert _last_kernel(ctx, h) == 5
+    Y = dY.to_host((ldy, k))
+    ref = A @ np.vstack([X[:ncl], G[:ng]])
+    tol = 1e-13 * max(int(np.diff(A.indptr).max()), 1) * max(np.abs(A.data).max(), 1.0) * 6
+    assert np.abs(Y[:n] - ref).max() <= tol
+    assert np.array_equal(Y[n:], np.full((ldy - n, k), 7.0))                 # rows past n untouched
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    for d in (dX, dG, dY):
+        d.free()
