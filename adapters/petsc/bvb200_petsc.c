@@ -7,7 +7,7 @@
  * BVSetType(bv,"b200").  It is the PETSc-typed twin of slepc_b200/host/bvb200.c: the same sm_100a kernels behind the same C ABI
  * (include/b2k.h), with Vec / Mat / MPI_Comm where the stand-alone host layer has its own look-alikes.
  *
- * Every one of the 36 slots of struct _BVOps (include/slepc/private/bvimpl.h:24-61) is decided at the end of this file:
+ * Every one of the 35 slots of struct _BVOps (include/slepc/private/bvimpl.h:24-61) is decided at the end of this file:
  * implemented here, or NULL where the reference's front-end has a generic path that is correct for this type.
  *
  * This file cannot be linked in this repository (no PETSc in the image): it is type-checked against the reference's OWN headers
@@ -574,7 +574,7 @@ PETSC_EXTERN PetscErrorCode BVCreate_B200(BV bv)
   PetscCall(BVCreateVecEmpty(bv, &bv->cv[0]));                  /* svec.c:486-487 */
   PetscCall(BVCreateVecEmpty(bv, &bv->cv[1]));
 
-  /* all 36 slots of struct _BVOps (bvimpl.h:24-61) */
+  /* all 35 slots of struct _BVOps (bvimpl.h:24-61) */
   bv->ops->mult             = BVMult_B200;
   bv->ops->multvec          = BVMultVec_B200;
   bv->ops->multinplace      = BVMultInPlace_B200;

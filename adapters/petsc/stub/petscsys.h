@@ -75,6 +75,7 @@ typedef int MPI_Datatype;
 #define MPIU_REAL 0
 #define MPIU_SUM 0
 #define MPIU_MAX 0
+#define MPIU_MIN 0
 #define MPI_IN_PLACE ((void *)1)
 #define PETSC_SUCCESS 0
 #define PETSC_ERR_MEM 55
@@ -245,3 +246,11 @@ int MPI_Allreduce(const void *, void *, int, MPI_Datatype, MPI_Op, MPI_Comm);
 #define PETSC_VIEWER_ASCII_INFO 1
 #define PETSC_VIEWER_ASCII_INFO_DETAIL 2
 #define PETSC_CUDA 1
+/* the MPI calls the adapter makes (real signatures) */
+#define MPIU_INT 0
+#define MPI_BYTE 0
+#define MPI_STATUS_IGNORE NULL
+typedef struct { int dummy; } MPI_Status;
+int MPI_Allgather(const void *, int, MPI_Datatype, void *, int, MPI_Datatype, MPI_Comm);
+int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm);
+int MPI_Sendrecv(const void *, int, MPI_Datatype, int, int, void *, int, MPI_Datatype, int, int, MPI_Comm, MPI_Status *);

@@ -451,14 +451,6 @@ def run_b200(args, wl):
         et.destroy()
         Mt.destroy()
 
-    # ---------------- multi-GPU correctness inside the scaling run -----------------------------------------------
-    parity = None
-    if world > 1 and not args.no_parity:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import mgpu_cases
-        parity = mgpu_cases.run_all(rank, world)
-        parity["transport"] = "reductions: NVLink mailboxes" if D.P2P else "reductions: ncclAllReduce"
-
     # ---------------- time-to-solution of the north-star problem, strong-scaled, checked before printing ----------------
     tts = None
     if args.tts != "none":
@@ -533,7 +525,11 @@ def run_b200(args, wl):
         except Exception as e:                                   # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
-    if rank == 0:
+    parity = None
+
+    def emit():
+        if rank != 0:
+            return
         halo = "none (1 GPU)"
         if world > 1:
             halo = ("k-vector reductions fused into the reduction kernel over NVLink peer memory (k_reduce_partials_xg); " if D.P2P
@@ -554,6 +550,25 @@ def run_b200(args, wl):
             "latency_leg": lat, "multi_gpu_parity": parity, "gpu_launches": nl, "clocks": clocks, "collectives": halo,
         }
         print(json.dumps(line), flush=True)
+
+    # ---------------- multi-GPU correctness inside the scaling run (last: a watchdog prints the line if a case hangs) ----------
+    if world > 1 and not args.no_parity:
+        import threading
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import mgpu_cases
+
+        def watchdog():
+            nonlocal parity
+            parity = {"cases": len(mgpu_cases.CASES), "passed": 0, "failed": ["a row-partitioned correctness case did not finish within 300 s"], "ranks": world}
+            emit()
+            os._exit(3)
+        timer = threading.Timer(300.0, watchdog)
+        timer.daemon = True
+        timer.start()
+        parity = mgpu_cases.run_all(rank, world)
+        timer.cancel()
+        parity["transport"] = "reductions: NVLink mailboxes" if D.P2P else "reductions: ncclAllReduce"
+    emit()
     D.finalize()
     if parity is not None and parity["passed"] != parity["cases"]:
         raise SystemExit(f"bench.py: multi-GPU parity failed: {parity['failed']}")

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256, 2) k_dotvec(const double *__restrict__ V,
                                                  const double *__restrict__ w, double *__restrict__ part, int pstride,
                                                  int with_ww)
 {
+  b2k_pdl_enter();
   const int tile = blockIdx.y;
   const int c0 = tile * ctile;
   const int nc = min(ctile, k - c0);
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256, 2) k_dotvec(const double *__restrict__ V,
 __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ part, int nblk, int pstride, int ncols,
                                                          double *__restrict__ out)
 {
+  b2k_pdl_enter();
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= ncols) return;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
 __global__ void __launch_bounds__(256) k_reduce_partials_xg(const double *part, int nblk, int pstride, int ncols,
                                                             double *out, const b2k_xg_s xg, unsigned long long seq)   /* out may be part (in-place all-reduce) */
 {
+  b2k_pdl_enter();
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const size_t par = (size_t)(seq & 1ull);
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(256) k_multvec(const double *__restrict__ V, i
                                                   double beta, double *__restrict__ y, const double *__restrict__ q,
                                                   double *__restrict__ part, int pstride, int pcol, const b2k_gate_s gate)
 {
+  b2k_pdl_enter();
   if (b2k_gate_closed(gate)) return;
   extern __shared__ double qs[];
   for (int i = threadIdx.x; i < k; i += blockDim.x) qs[i] = q[i];
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(256) k_multvec(const double *__restrict__ V, i
 /* ---- elementwise n x k block kernels (blockIdx.y = column) ------------------------------------ */
 __global__ void __launch_bounds__(256) k_scale(double *__restrict__ X, int64_t ld, int64_t n, double alpha)
 {
+  b2k_pdl_enter();
   double *x = X + (int64_t)blockIdx.y * ld;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] *= alpha;
@@ -472,10 +477,10 @@ __global__ void __launch_bounds__((RB / 4) * 16) k_gemm_ts(double *Out, int64_t 
 int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, double *out)
 {
   if (ctx->xg && ctx->xg_on && ncols <= B2K_XG_MAXC && (ncols + 7) / 8 <= B2K_XG_MAXB)
-    k_reduce_partials_xg<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out, *ctx->xg, ++ctx->xg_seq);
+    b2k_launch_pdl(k_reduce_partials_xg, dim3((ncols + 7) / 8), dim3(256), 0, ctx->stream, ctx->partials, nblk, pstride, ncols, out, *ctx->xg, ++ctx->xg_seq);
   else {
     ARGCHK(!(ctx->xg && ctx->xg_on), "reduction too wide for the peer-memory mailbox");
-    k_reduce_partials<<<(ncols + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nblk, pstride, ncols, out);
+    b2k_launch_pdl(k_reduce_partials, dim3((ncols + 7) / 8), dim3(256), 0, ctx->stream, ctx->partials, nblk, pstride, ncols, out);
   }
   CKLAUNCH(ctx);
   return B2K_OK;
@@ -486,7 +491,7 @@ int b2k_launch_reduce_partials(b2k_ctx ctx, int nblk, int pstride, int ncols, do
 int b2k_xg_allreduce_inplace(b2k_ctx ctx, double *buf, int n)
 {
   if (!ctx->xg || n < 1 || n > B2K_XG_MAXC || (n + 7) / 8 > B2K_XG_MAXB) return -1;
-  k_reduce_partials_xg<<<(n + 7) / 8, 256, 0, ctx->stream>>>(buf, 1, n, n, buf, *ctx->xg, ++ctx->xg_seq);
+  b2k_launch_pdl(k_reduce_partials_xg, dim3((n + 7) / 8), dim3(256), 0, ctx->stream, buf, 1, n, n, buf, *ctx->xg, ++ctx->xg_seq);
   CKLAUNCH(ctx);
   return B2K_OK;
 }
@@ -525,8 +530,8 @@ static int launch_dotvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, in
   const int pstride = ncols;
   dim3 grid(gx, ntiles);
   PROF_BEGIN(ctx, B2K_PROF_DOTVEC, 8.0 * (double)n * (k + 1));
-  if (vec2) k_dotvec<16, true><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
-  else      k_dotvec<16, false><<<grid, 256, 0, ctx->stream>>>(V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
+  if (vec2) b2k_launch_pdl(k_dotvec<16, true>, grid, dim3(256), 0, ctx->stream, V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
+  else      b2k_launch_pdl(k_dotvec<16, false>, grid, dim3(256), 0, ctx->stream, V, ld, n, k, ctile, w, ctx->partials, pstride, with_ww);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return b2k_launch_reduce_partials(ctx, gx, pstride, ncols, out);
@@ -558,14 +563,14 @@ static int launch_multvec(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, i
   const size_t shm = sizeof(double) * (size_t)(k > 0 ? k : 1);
   PROF_BEGIN(ctx, B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
   if (nrm_out) {
-    if (vec2) k_multvec<true, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
-    else      k_multvec<false, true><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
+    if (vec2) b2k_launch_pdl(k_multvec<true, true>, dim3(gx), dim3(256), shm, ctx->stream, V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
+    else      b2k_launch_pdl(k_multvec<false, true>, dim3(gx), dim3(256), shm, ctx->stream, V, ld, n, k, alpha, beta, y, q, ctx->partials, 1, 0, gate);
     PROF_END(ctx);
     CKLAUNCH(ctx);
     { const int rc_ = b2k_launch_reduce_partials(ctx, gx, 1, 1, nrm_out); if (rc_) return rc_; }
   } else {
-    if (vec2) k_multvec<true, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0, gate);
-    else      k_multvec<false, false><<<gx, 256, shm, ctx->stream>>>(V, ld, n, k, alpha, beta, y, q, nullptr, 0, 0, gate);
+    if (vec2) b2k_launch_pdl(k_multvec<true, false>, dim3(gx), dim3(256), shm, ctx->stream, V, ld, n, k, alpha, beta, y, q, (double *)nullptr, 0, 0, gate);
+    else      b2k_launch_pdl(k_multvec<false, false>, dim3(gx), dim3(256), shm, ctx->stream, V, ld, n, k, alpha, beta, y, q, (double *)nullptr, 0, 0, gate);
     PROF_END(ctx);
     CKLAUNCH(ctx);
   }
@@ -729,7 +734,7 @@ extern "C" int b2k_scale(b2k_ctx ctx, double *X, int64_t ld, int64_t n, int k, d
     return B2K_OK;
   }
   PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n * k);
-  k_scale<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(X, ld, n, alpha);
+  b2k_launch_pdl(k_scale, grid2d(ctx, n, k), dim3(256), 0, ctx->stream, X, ld, n, alpha);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;

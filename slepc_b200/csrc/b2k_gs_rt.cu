@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(RT_THREADS, (CPT >= 16 ? 4 : (CPT >= 8 ? 5 : 6
 k_gs_rt(const double *__restrict__ V, int64_t ld, int64_t n, int k, double alpha, double beta, double *__restrict__ w,
         const double *__restrict__ q, double *__restrict__ part, int pstride, const b2k_gate_s gate)
 {
+  b2k_pdl_enter();
   if (b2k_gate_closed(gate)) return;              /* DGKS does not refine: the whole grid leaves (uniform) */
   __shared__ double  qs[4 * CPT];
   __shared__ double2 psum[2][4][32];
@@ -139,9 +140,9 @@ int b2k_gs_rt_launch(b2k_ctx ctx, const double *V, int64_t ld, int64_t n, int k,
   PROF_BEGIN(ctx, dot ? B2K_PROF_GSFUSED : B2K_PROF_MULTVEC, 8.0 * (double)n * (k + (beta == 0.0 ? 1 : 2)));
 #define RT_LAUNCH(CPT)                                                                                                          \
   do {                                                                                                                          \
-    if (dot) k_gs_rt<CPT, true, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
-    else if (nrm) k_gs_rt<CPT, false, true><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
-    else k_gs_rt<CPT, false, false><<<grid, RT_THREADS, 0, ctx->stream>>>(V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
+    if (dot) b2k_launch_pdl(k_gs_rt<CPT, true, true>, dim3(grid), dim3(RT_THREADS), 0, ctx->stream, V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
+    else if (nrm) b2k_launch_pdl(k_gs_rt<CPT, false, true>, dim3(grid), dim3(RT_THREADS), 0, ctx->stream, V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
+    else b2k_launch_pdl(k_gs_rt<CPT, false, false>, dim3(grid), dim3(RT_THREADS), 0, ctx->stream, V, ld, n, k, alpha, beta, w, q, ctx->partials, pstride, gate); \
   } while (0)
   if (kq <= 4) RT_LAUNCH(4);
   else if (kq <= 8) RT_LAUNCH(8);

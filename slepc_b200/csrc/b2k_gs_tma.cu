@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
 k_gs_tma(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmW, int64_t n, int k, double alpha, double beta,
          double *__restrict__ w, const double *__restrict__ q, double *__restrict__ part, int pstride, int nstages, const b2k_gate_s gate)
 {
+  b2k_pdl_enter();
   if (b2k_gate_closed(gate)) return;                            /* DGKS does not refine: the whole grid leaves (uniform) */
   constexpr int KB = 4 * CPT;                                   /* columns per stage (box width)   */
   constexpr int STAGE_DOUBLES = (KB + 1) * TM_ROWS;            /* V box + w box                   */
@@ -242,7 +243,7 @@ static int tm_launch(b2k_ctx ctx, const CUtensorMap &mV, const CUtensorMap &mW, 
       CK(cudaFuncSetAttribute(k_gs_tma<CPT, D, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));                  \
       configured = 1;                                                                                                           \
     }                                                                                                                           \
-    k_gs_tma<CPT, D, N><<<grid, TM_THREADS, shm, ctx->stream>>>(mV, mW, n, k, alpha, beta, w, q, ctx->partials, pstride, nstages, gate); \
+    b2k_launch_pdl(k_gs_tma<CPT, D, N>, dim3(grid), dim3(TM_THREADS), shm, ctx->stream, mV, mW, n, k, alpha, beta, w, q, ctx->partials, pstride, nstages, gate); \
   } while (0)
   if (dot) TM_GO(true, true);
   else if (nrm) TM_GO(false, true);

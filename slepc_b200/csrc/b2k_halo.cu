@@ -68,6 +68,7 @@ __host__ __device__ static inline u64 *hl_ack(void *block, size_t data_bytes) { 
 
 __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ x, const hl_args a, u64 seq)
 {
+  b2k_pdl_enter();
   /* acknowledgements first: this kernel runs after the SpMV of seq-1, so its ghost buffer is free again */
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.nrecv) {
     __threadfence_system();
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ x,
 
 __global__ void k_halo_wait(const hl_args a, u64 seq)
 {
+  b2k_pdl_enter();
   if (threadIdx.x < a.nrecv) {
     const long long t0 = clock64();
     while (*((volatile const u64 *)(a.my_arrived + threadIdx.x)) < seq) {
@@ -239,11 +241,11 @@ extern "C" int b2k_halo_exchange(b2k_halo h, const double *x, const double **gho
   const u64 seq = ++h->seq;
   if (h->args.nsend > 0 || h->args.nrecv > 0) {
     dim3 grid(HL_CTAS, h->args.nsend > 0 ? h->args.nsend : 1);
-    k_halo_push<<<grid, 256, 0, ctx->stream>>>(x, h->args, seq);
+    b2k_launch_pdl(k_halo_push, grid, dim3(256), 0, ctx->stream, x, h->args, seq);
     CKLAUNCH(ctx);
   }
   if (h->args.nrecv > 0) {
-    k_halo_wait<<<1, 32, 0, ctx->stream>>>(h->args, seq);
+    b2k_launch_pdl(k_halo_wait, dim3(1), dim3(32), 0, ctx->stream, h->args, seq);
     CKLAUNCH(ctx);
   }
   if (ghost_out) *ghost_out = (const double *)h->block + (seq & 1ull) * hl_stride(h->nghost);

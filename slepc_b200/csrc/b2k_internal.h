@@ -118,6 +118,37 @@ void b2k_set_error(const char *fmt, ...);
     }                                                                                         \
   } while (0)
 
+/* Programmatic dependent launch (sm_90+): the kernels of the Lanczos-step chain (sweeps, their reductions, scale, SpMV, halo)
+   are launched with the programmatic-stream-serialization attribute and open with b2k_pdl_enter(): `launch_dependents` lets the
+   NEXT kernel of the stream be scheduled while this one runs (its CTAs become resident as resources allow), `wait` blocks until
+   the PREVIOUS kernel has completed and its writes are visible.  Data dependences are untouched (every chain kernel waits before
+   its first global access); what disappears is the launch / drain gap between the 8-10 short kernels of a step in the
+   latency-bound regime.  env B2K_PDL=0: plain stream order. */
+#ifdef __CUDACC__
+__device__ __forceinline__ void b2k_pdl_enter(void)
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+static inline int b2k_pdl_enabled(void)
+{
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("B2K_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static inline void b2k_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t shm, cudaStream_t st, Args &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = shm; cfg.stream = st;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = b2k_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);       /* errors surface through cudaGetLastError (CKLAUNCH) */
+}
+#endif
+
 static inline int b2k_is_aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
 #endif

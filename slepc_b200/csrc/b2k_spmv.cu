@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) k_spmv_sell(const int64_t *__restrict__ s
                                                     const double *__restrict__ xg, int ncl, double *__restrict__ y, int64_t nrows,
                                                     int64_t nslices, double sigma)
 {
+  b2k_pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s0 < nslices; s0 += 2 * nwarps) {
@@ -183,6 +184,7 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
                  const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int ncl,
                  double *__restrict__ y, int64_t nrows, double sigma, int cap, int nstages)
 {
+  b2k_pdl_enter();
   extern __shared__ __align__(128) unsigned char sp_raw[];
   const size_t stage_bytes = SP_STAGE_BYTES((size_t)cap);
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sp_raw);
@@ -666,15 +668,15 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
   A->last_kernel = (sp_stages >= 2) ? (A->nghost > 0 ? B2K_SPMV_KERNEL_SELL_PIPE_GHOST : B2K_SPMV_KERNEL_SELL_PIPE)
                                      : ((A->nslices > 0 && sell_mode()) ? B2K_SPMV_KERNEL_SELL : B2K_SPMV_KERNEL_CSR_STREAM);
   if (sp_stages >= 2 && A->nghost > 0)
-    k_spmv_sell_pipe<true><<<ctx->sm_count, SP_THREADS, sp_shm, ctx->stream>>>(
-        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma,
-        A->sp_cap, sp_stages);
+    b2k_launch_pdl(k_spmv_sell_pipe<true>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
+                   A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma,
+                   A->sp_cap, sp_stages);
   else if (sp_stages >= 2)
-    k_spmv_sell_pipe<false><<<ctx->sm_count, SP_THREADS, sp_shm, ctx->stream>>>(
-        A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, x, (int)A->ncols_local, y, A->nrows, sigma, A->sp_cap, sp_stages);
+    b2k_launch_pdl(k_spmv_sell_pipe<false>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
+                   A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, x, (int)A->ncols_local, y, A->nrows, sigma, A->sp_cap, sp_stages);
   else if (A->nslices > 0 && sell_mode())
-    k_spmv_sell<<<(unsigned)std::min<int64_t>((A->nslices + 15) / 16, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x,
-                                                                            (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
+    b2k_launch_pdl(k_spmv_sell, dim3((unsigned)std::min<int64_t>((A->nslices + 15) / 16, (int64_t)ctx->sm_count * 8)), dim3(256), 0, ctx->stream,
+                   A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
   else
     k_spmv_csr_stream<<<A->nblk, SPMV_THREADS, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->blkrow, x,
                                                                    xghost ? xghost : x, (int)A->ncols_local, y, sigma);
