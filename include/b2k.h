@@ -117,6 +117,8 @@ int  b2k_dot(b2k_ctx ctx, const double *Y, int64_t ldy, const double *X, int64_t
    (bvops.c:482, PetscRandom) shared bit-for-bit with the oracle and the host code              */
 int  b2k_set_random(b2k_ctx ctx, double *x, int64_t n, int64_t row0, uint64_t seed);
 int  b2k_fill(b2k_ctx ctx, double *x, int64_t n, double value);
+/* w = x .* y (VecPointwiseMult: Jacobi preconditioner of the CG behind the shift-and-invert ST)            */
+int  b2k_pointwise_mult(b2k_ctx ctx, double *w, const double *x, const double *y, int64_t n);
 
 /* ---- fused classical Gram-Schmidt sweeps (replace bvorthog.c:91-132 + bvcuda.cu:345-548) ---- */
 /* c[0:k] = V(:,0:k)^T w, c[k] = w^T w        — BVDotColumnInc bvorthog.c:32-47: one sweep, one
@@ -158,6 +160,9 @@ int  b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncols_local, int64_t *ngho
    rebuilds them from the SELL copy on A's stream, b2k_csr_release_arrays drops them again.  env B2K_CSR_KEEP=1 keeps both. */
 int  b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val);
 int  b2k_csr_release_arrays(b2k_csr A);
+/* diag[r] = A(r, r + diag_col_offset) of the local rows, 0 where not stored (MatGetDiagonal; offset = position of the diagonal
+   block in the local column numbering, 0 for a square matrix whose owned columns are its owned rows)          */
+int  b2k_csr_get_diagonal(b2k_ctx ctx, b2k_csr A, int64_t diag_col_offset, double *diag);
 /* HBM bytes held by the matrix, all copies (bench: footprint)                                      */
 int  b2k_csr_bytes(b2k_csr A, int64_t *bytes);
 /* which kernel the most recent product of A ran (tests assert the dispatch they mean to cover)     */

@@ -130,6 +130,9 @@ PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *val);                    /* col
 PetscErrorCode VecAXPY(Vec y, PetscScalar alpha, Vec x);
 PetscErrorCode VecScale(Vec v, PetscScalar alpha);
 PetscErrorCode VecCopy(Vec x, Vec y);
+PetscErrorCode VecAYPX(Vec y, PetscScalar beta, Vec x);                   /* y = x + beta y */
+PetscErrorCode VecPointwiseMult(Vec w, Vec x, Vec y);                     /* w = x .* y     */
+PetscErrorCode VecReciprocal(Vec v);                                      /* v = 1 ./ v (zeros stay zero), set-up only: goes through the host */
 
 /* ---- Mat (dense sequential host matrices for Q/H/T/M arguments; operator matrices) ----------- */
 PetscErrorCode MatCreateSeqDense(PetscInt m, PetscInt n, PetscScalar *data /* or NULL */, Mat *A);
@@ -147,12 +150,15 @@ PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y);
 PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left);
 PetscErrorCode MatCreateHermitianTranspose(Mat A, Mat *At);          /* virtual: MatMult(At) = MatMultTranspose(A) */
 PetscErrorCode MatGetType(Mat A, const char **type);
+PetscErrorCode MatGetDiagonal(Mat A, Vec d);                         /* Jacobi preconditioner of the ST's linear solves */
 /* operator plug-in, the MatShell route (cf. src/eps/tutorials/ex3.c:46-49,140-168) */
 typedef PetscErrorCode (*MatMultFn)(Mat A, Vec x, Vec y);
 PetscErrorCode MatCreateShell(PetscInt m, PetscInt n, PetscInt M, PetscInt N, B2KMemType mem, void *ctx, Mat *A);
 PetscErrorCode MatShellGetContext(Mat A, void **ctx);
 PetscErrorCode MatShellSetMult(Mat A, MatMultFn mult);
 PetscErrorCode MatShellSetMultTranspose(Mat A, MatMultFn multtranspose);
+typedef PetscErrorCode (*MatGetDiagonalFn)(Mat A, Vec d);
+PetscErrorCode MatShellSetGetDiagonal(Mat A, MatGetDiagonalFn getdiagonal);
 /* Mat type "b200csr": CSR rows [rstart,rend) of a global M x N matrix resident in HBM.
    colidx holds GLOBAL column indices.  The column space is partitioned by `colstarts`
    (size+1 entries; NULL = same as the row partition for square matrices / single rank).
@@ -223,6 +229,10 @@ PetscErrorCode BVNorm(BV bv, NormType type, PetscReal *val);                    
 PetscErrorCode BVNormVec(BV bv, Vec v, NormType type, PetscReal *val);                  /* bvglobal.c:590 */
 PetscErrorCode BVNormColumn(BV bv, PetscInt j, NormType type, PetscReal *val);          /* bvglobal.c:523 */
 PetscErrorCode BVNormalize(BV bv, PetscScalar *eigi);                                   /* bvglobal.c:836 */
+/* non-standard inner product <x,y> = y^T B x (B symmetric positive definite): BVDot*, BVNorm*, the orthogonalisations and
+   BVNormalize use it (bvbasic.c:497, BV_IPMatMult bvimpl.h:147-157) */
+PetscErrorCode BVSetMatrix(BV bv, Mat B, PetscBool indef);                              /* bvbasic.c:497 */
+PetscErrorCode BVGetMatrix(BV bv, Mat *B, PetscBool *indef);                            /* bvbasic.c:565 */
 /* split-phase reductions: every Begin queues its local part, the first End performs ONE global reduction for all of them
    (PetscSplitReduction; a BV type may take the pair over with the dotvec_begin/end, norm_begin/end slots, bvimpl.h:33-39) */
 PetscErrorCode BVDotVecBegin(BV X, Vec y, PetscScalar *m);                              /* bvglobal.c:188 */
@@ -287,10 +297,30 @@ PetscErrorCode DSVectors(DS ds, DSMatType mat, PetscInt *j, PetscReal *rnorm);
 PetscErrorCode DSTruncate(DS ds, PetscInt n, PetscBool trim);                      /* dsops.c:232 */
 PetscErrorCode DSGetTruncateSize(DS ds, PetscInt l, PetscInt n, PetscInt *k);      /* dsops.c:368 */
 
-/* ---- ST (include/slepcst.h): shift only ---------------------------------------------------------- */
-#define STSHIFT "shift"
+/* ---- KSP: the linear solves behind ST for generalized problems and shift-and-invert.  The reference defaults to a direct
+        solve (preonly + LU, stsles.c); a sparse factorisation is outside this path, so the solver here is Jacobi-preconditioned
+        conjugate gradients on the device vectors (symmetric positive definite coefficient matrices: B of a GHEP, A - sigma B
+        below the spectrum), tolerance SLEPC_DEFAULT_TOL * 1e-2 like STSetDefaultKSP (stsles.c:104-131) -------------------- */
+typedef struct _p_KSP *KSP;
+#define KSPCG "cg"
+PetscErrorCode KSPCreate(KSP *ksp);
+PetscErrorCode KSPDestroy(KSP *ksp);
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P /* ignored: the Jacobi preconditioner is taken from A */);
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt maxits);
+PetscErrorCode KSPSetUp(KSP ksp);
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x);
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its);
+PetscErrorCode KSPGetTotalIterations(KSP ksp, PetscInt *its);
+
+/* ---- ST (include/slepcst.h): shift and shift-and-invert ---------------------------------------------- */
+#define STSHIFT   "shift"
+#define STSINVERT "sinvert"
 PetscErrorCode STCreate(ST *st);
 PetscErrorCode STDestroy(ST *st);
+PetscErrorCode STSetType(ST st, const char *type);                                 /* stfunc.c / stregis.c */
+PetscErrorCode STGetType(ST st, const char **type);
+PetscErrorCode STGetKSP(ST st, KSP *ksp);                                          /* stsles.c:133 */
+PetscErrorCode STGetBilinearForm(ST st, Mat *B);                                   /* stfunc.c:578: B (NULL for a standard problem) */
 PetscErrorCode STSetMatrices(ST st, PetscInt n, Mat A[]);
 PetscErrorCode STSetShift(ST st, PetscScalar shift);
 PetscErrorCode STGetShift(ST st, PetscScalar *shift);
@@ -302,7 +332,7 @@ PetscErrorCode STBackTransform(ST st, PetscInt n, PetscScalar *eigr, PetscScalar
 
 /* ---- EPS (include/slepceps.h): Krylov-Schur, standard problems ------------------------------------- */
 #define EPSKRYLOVSCHUR "krylovschur"
-typedef enum { EPS_HEP = 1, EPS_NHEP = 3 } EPSProblemType;
+typedef enum { EPS_HEP = 1, EPS_GHEP = 2, EPS_NHEP = 3 } EPSProblemType;
 typedef enum { EPS_LARGEST_MAGNITUDE = 1, EPS_SMALLEST_MAGNITUDE, EPS_LARGEST_REAL, EPS_SMALLEST_REAL, EPS_LARGEST_IMAGINARY,
                EPS_SMALLEST_IMAGINARY, EPS_TARGET_MAGNITUDE, EPS_TARGET_REAL } EPSWhich;
 typedef enum { EPS_CONVERGED_TOL = 1, EPS_CONVERGED_USER = 2, EPS_DIVERGED_ITS = -1, EPS_DIVERGED_BREAKDOWN = -2,
@@ -314,7 +344,8 @@ typedef PetscErrorCode (*EPSMonitorFn)(EPS eps, PetscInt its, PetscInt nconv, Pe
 
 PetscErrorCode EPSCreate(EPS *eps);
 PetscErrorCode EPSDestroy(EPS *eps);
-PetscErrorCode EPSSetOperators(EPS eps, Mat A, Mat B /* must be NULL */);
+PetscErrorCode EPSSetOperators(EPS eps, Mat A, Mat B /* NULL: standard problem; else A x = k B x with B symmetric positive definite (EPS_GHEP) */);
+PetscErrorCode EPSSetPurify(EPS eps, PetscBool purify);                            /* epsopts.c:1469 */
 PetscErrorCode EPSSetProblemType(EPS eps, EPSProblemType type);
 PetscErrorCode EPSSetType(EPS eps, const char *type);
 PetscErrorCode EPSSetDimensions(EPS eps, PetscInt nev, PetscInt ncv, PetscInt mpd);

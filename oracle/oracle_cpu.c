@@ -31,6 +31,7 @@ typedef struct {
   PetscErrorCode (*dot_local)(Vec, Vec, PetscScalar *);
   PetscErrorCode (*axpy)(Vec, PetscScalar, Vec);
   PetscErrorCode (*scale)(Vec, PetscScalar);
+  PetscErrorCode (*pointwisemult)(Vec, Vec, Vec);        /* w = x .* y */
 } B2KVecHostOps;
 PetscErrorCode B2KVecRegisterHostOps(const B2KVecHostOps *ops);
 
@@ -70,6 +71,16 @@ static PetscErrorCode hv_scale(Vec v, PetscScalar a)
   const PetscInt n = v->n;
 #pragma omp parallel for if (n > 100000)
   for (PetscInt i = 0; i < n; i++) x[i] *= a;
+  return PETSC_SUCCESS;
+}
+
+static PetscErrorCode hv_pointwisemult(Vec w, Vec x, Vec y)
+{
+  double *ww = w->array;
+  const double *xx = x->array, *yy = y->array;
+  const PetscInt n = w->n;
+#pragma omp parallel for if (n > 100000)
+  for (PetscInt i = 0; i < n; i++) ww[i] = xx[i] * yy[i];
   return PETSC_SUCCESS;
 }
 
@@ -402,6 +413,19 @@ static PetscErrorCode MatMult_CPUCSR(Mat A, Vec x, Vec y)
   return PETSC_SUCCESS;
 }
 
+/* diagonal of the owned block (square matrices whose owned columns are the owned rows: local column r is global row r) */
+static PetscErrorCode MatGetDiagonal_CPUCSR(Mat A, Vec d)
+{
+  Mat_CPUCSR *a = (Mat_CPUCSR *)A->data;
+  PetscCheck(A->M == A->N && A->rstart == A->cstart && A->m == A->n, PETSC_ERR_SUP, "MatGetDiagonal needs a square matrix whose owned columns are its owned rows");
+  for (PetscInt r = 0; r < A->m; r++) {
+    double v = 0.0;
+    for (PetscInt k = a->rowptr[r]; k < a->rowptr[r + 1]; k++) if (a->colidx[k] == r) v = a->val[k];
+    d->array[r] = v;
+  }
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode MatDestroy_CPUCSR(Mat A)
 {
   Mat_CPUCSR *a = (Mat_CPUCSR *)A->data;
@@ -431,6 +455,7 @@ PetscErrorCode MatCreateOracleCSR(PetscInt M, PetscInt N, PetscInt rstart, Petsc
   A->mem = B2K_MEM_HOST;
   A->data = a;
   A->ops.mult = MatMult_CPUCSR;
+  A->ops.getdiagonal = MatGetDiagonal_CPUCSR;
   A->ops.destroy = MatDestroy_CPUCSR;
   const PetscInt m = A->m, nnz = m ? rowptr[m] : 0;
   a->rowptr = dupi(rowptr, m + 1);
@@ -506,7 +531,7 @@ void scipy_openblas_set_num_threads(int);
 PetscErrorCode OracleCPURegister(void)
 {
   scipy_openblas_set_num_threads(1);   /* parallelism comes from the OpenMP row chunks above; BLAS runs serial inside them */
-  static const B2KVecHostOps ops = {hv_set, hv_sumsq, hv_dot, hv_axpy, hv_scale};
+  static const B2KVecHostOps ops = {hv_set, hv_sumsq, hv_dot, hv_axpy, hv_scale, hv_pointwisemult};
   PetscCall(B2KVecRegisterHostOps(&ops));
   PetscCall(BVRegister("oraclecpu", BVCreate_OracleCPU));
   return PETSC_SUCCESS;

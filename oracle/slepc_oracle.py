@@ -92,6 +92,11 @@ class BV:
         self.buffer = np.zeros((nc + m, m), order="F")  # bvbasic.c:757-789 (col 0 scratch, col j = h_j)
         self.rng_seed = 0x5EED
         self.npasses = 0                                # instrumentation only
+        self.matrix = None                              # BVSetMatrix (bvbasic.c:497): inner product <x,y> = y^T B x
+
+    def _ip(self, x):
+        """BV_IPMatMult (bvimpl.h:147-157): B x, or x itself for the standard inner product."""
+        return x if self.matrix is None else self.matrix @ x
 
     # ---- column access (bvbasic.c:1116-1137: physical column = nc+j) -------------------------
     def col(self, j):
@@ -155,7 +160,10 @@ class BV:
         self.col(j)[:] *= alpha
 
     def norm_column(self, j):
-        """BVNormColumn (bvglobal.c:523 → svec.c:164 → bvlapack.c:37) NORM_2."""
+        """BVNormColumn (bvglobal.c:523 → svec.c:164 → bvlapack.c:37) NORM_2; sqrt(x^T B x) with BVSetMatrix (bvglobal.c:547)."""
+        if self.matrix is not None:
+            x = self.col(j)
+            return self._safe_sqrt(float(x @ (self.matrix @ x)))
         return float(np.linalg.norm(self.col(j)))
 
     def norm_fro(self):
@@ -183,19 +191,20 @@ class BV:
         w = self.col(j)
         self.npasses += 1
         onorm = norm = None
+        z = self._ip(w)                               # svec.c:117-120: the dot products use B w
         if want_onorm or want_norm:
-            c[0:nc + j] = W.T @ w                     # BVDotColumnInc :32-47 (k=j+1)
-            c[nc + j] = float(w @ w)
+            c[0:nc + j] = W.T @ z                     # BVDotColumnInc :32-47 (k=j+1)
+            c[nc + j] = float(w @ z)
             beta = self._safe_sqrt(c[nc + j])         # BV_SquareRoot
         else:
-            c[0:nc + j] = W.T @ w
+            c[0:nc + j] = W.T @ z
         w -= W @ c[0:nc + j]                          # BVMultColumn(-1,1,j,c)
         if want_onorm:
             onorm = beta
         if want_norm:
             s = float(np.sum(c[0:nc + j] ** 2))       # BV_SquareSum
             nr = beta * beta - s
-            norm = float(np.linalg.norm(w)) if nr <= 0.0 else math.sqrt(nr)
+            norm = self.norm_column(j) if nr <= 0.0 else math.sqrt(nr)
         if j > 0 or nc > 0:
             h[0:nc + j] += c[0:nc + j]                # BV_AddCoefficients
         return onorm, norm
@@ -207,13 +216,13 @@ class BV:
         h = self.buffer[:, j]
         w = self.col(j)
         self.npasses += 1
-        onorm = float(np.linalg.norm(w)) if want_onorm else None
+        onorm = self.norm_column(j) if want_onorm else None
         for i in range(-nc, j):
             vi = self.col(i)
-            d = float(w @ vi)
+            d = float(self._ip(w) @ vi)               # bvorthog.c:69-74
             c[nc + i] = d
             w -= d * vi
-        norm = float(np.linalg.norm(w)) if want_norm else None
+        norm = self.norm_column(j) if want_norm else None
         if j > 0 or nc > 0:
             h[0:nc + j] += c[0:nc + j]
         return onorm, norm
@@ -853,19 +862,78 @@ class EPSResult:
     pass
 
 
+class STOperator:
+    """The transformed operator of ST as `Op @ x` (STApply_Generic, stsolve.c:16-25: y = P^{-1} M x):
+         shift,   standard      Op = A - sigma I
+         shift,   generalized   Op = B^{-1} (A - sigma B)          (shift.c:60-114)
+         sinvert                Op = (A - sigma B)^{-1} [B]        (sinvert.c:79-150)
+    The linear solves use a sparse LU (scipy splu), the reference's default KSPPREONLY + PCLU (stsles.c:104-131)."""
+
+    def __init__(self, A, B=None, sigma=0.0, sinvert=False):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        self.A, self.B, self.sigma, self.sinvert = A, B, sigma, sinvert
+        n = A.shape[0]
+        Bm = sp.identity(n, format="csc") if B is None else sp.csc_matrix(B)
+        self.T = (sp.csc_matrix(A) - sigma * Bm).tocsc()
+        self.lu = None
+        if sinvert:
+            self.lu = spla.splu(self.T)
+        elif B is not None:
+            self.lu = spla.splu(Bm)
+
+    def __matmul__(self, x):
+        if self.sinvert:
+            return self.lu.solve(x if self.B is None else self.B @ x)
+        y = self.T @ x
+        return y if self.B is None else self.lu.solve(y)
+
+    def back(self, re, im=0.0):
+        """STBackTransform: shift.c:49-58, sinvert.c:51-77 (real eigenvalues)."""
+        if not self.sinvert:
+            return re + self.sigma, im
+        if im == 0.0:
+            return 1.0 / re + self.sigma, 0.0
+        z = 1.0 / complex(re, im)
+        return z.real + self.sigma, z.imag
+
+
 def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which="largest_magnitude",
-                    hermitian=True, v0=None, keep=0.5, lock=True, orthog=None, seed=0x5EED, monitor=None):
-    """EPSSolve with -eps_type krylovschur, standard problem, ST=shift(0).
+                    hermitian=True, v0=None, keep=0.5, lock=True, orthog=None, seed=0x5EED, monitor=None,
+                    B=None, sigma=0.0, sinvert=False, target=None, purify=True):
+    """EPSSolve with -eps_type krylovschur.  Standard problem with ST=shift(0) by default; with B (symmetric positive
+    definite, EPS_GHEP) and / or sinvert the operator is the ST's (STOperator), the basis is B-orthonormal (BVSetMatrix,
+    epssetup.c:372-381), the projected values are compared after STBackTransform (SlepcMap_ST), convergence of sinvert is tested
+    on the transformed value (epskrylov.c:246), the eigenvectors are purified and B-normalised (epsdefault.c:28-50).
     A: anything supporting A @ x. Follows EPSSetUp_KrylovSchur (krylovschur.c:93-194) and
     EPSSolve_KrylovSchur_Default (:227-336)."""
+    st = None
+    if B is not None or sinvert or sigma != 0.0:
+        st = STOperator(A, B, sigma, sinvert)
+        if target is None:
+            target = sigma
+        if sinvert and which == "largest_magnitude":
+            which = "target_magnitude"                      # EPSSetWhichEigenpairs_Default epsdefault.c:210-220
     ncv, mpd = eps_default_dims(n, nev, ncv, mpd)
     if ncv > nev + mpd:
         raise ValueError("The value of ncv must not be larger than nev+mpd")
     if max_it is None:
         max_it = max(100, 2 * n // ncv)                     # krylovschur.c:113
-    compare = COMPARATORS[which]
+    if which in ("target_magnitude", "target_real"):
+        tg = 0.0 if target is None else target
+        base = (lambda ar, ai, br, bi: cmp_smallest_magnitude(ar - tg, ai, br - tg, bi)) if which == "target_magnitude" else \
+               (lambda ar, ai, br, bi: (abs(ar - tg) > abs(br - tg)) - (abs(ar - tg) < abs(br - tg)))      # slepcsc.c:233-260
+    else:
+        base = COMPARATORS[which]
+    if st is not None:
+        compare = lambda ar, ai, br, bi: base(*st.back(ar, ai), *st.back(br, bi))     # SlepcMap_ST, slepcsc.c:40-63
+    else:
+        compare = base
+    Op = st if st is not None else A
     V = BV(n, ncv + 1)                                      # EPSAllocateSolution(eps,1) epssetup.c:692
     V.rng_seed = seed
+    if B is not None and hermitian:
+        V.matrix = B                                        # epssetup.c:372-381
     if orthog:
         V.orthog_type, V.orthog_ref, V.orthog_eta = orthog
     ld = ncv + 1
@@ -883,6 +951,8 @@ def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which=
         V.col(0)[:] = v0
     else:
         V.set_random_column(0)
+    if B is not None and hermitian:
+        V.col(0)[:] = Op @ V.col(0).copy()                  # into the range of OP for definite generalized problems, epssolve.c:855-862
     _, norm, lindep = V.orthogonalize_column(0)
     if lindep or norm == 0.0:
         raise RuntimeError("Initial vector is zero or belongs to the deflation space")
@@ -894,9 +964,9 @@ def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which=
         nv = min(nconv + mpd, ncv)
         ds.set_dimensions(nv, nconv, nconv + l)
         if hermitian:
-            nv, beta, breakdown = V.mat_lanczos(A, ds.T, nconv + l, nv)
+            nv, beta, breakdown = V.mat_lanczos(Op, ds.T, nconv + l, nv)
         else:
-            nv, beta, breakdown = V.mat_arnoldi(A, ds.A, nconv + l, nv)
+            nv, beta, breakdown = V.mat_arnoldi(Op, ds.A, nconv + l, nv)
         nmatvec += nv - (nconv + l)
         ds.set_dimensions(nv, nconv, nconv + l)
         ds.set_state(RAW if l else INTERMEDIATE)
@@ -911,6 +981,8 @@ def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which=
         k = nconv
         while k < nv:
             re, im = eigr[k], eigi[k]
+            if st is not None and not sinvert:
+                re, im = st.back(re, im)                    # only for STSHIFT, epskrylov.c:246
             newk, resnorm = ds.vectors_rnorm(k)
             resnorm *= beta
             w = math.hypot(re, im)
@@ -944,6 +1016,8 @@ def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which=
                 if k < nev:
                     # EPSGetStartVector(eps,k,&breakdown)
                     V.set_random_column(k)
+                    if B is not None and hermitian:
+                        V.col(k)[:] = Op @ V.col(k).copy()
                     V.set_active(0, k)  # not in the reference; GS below uses its own window
                     _, norm, lindep = V.orthogonalize_column(k)
                     V.set_active(nconv, nv)
@@ -965,11 +1039,19 @@ def eps_krylovschur(A, n, nev, ncv=None, mpd=None, tol=1e-8, max_it=None, which=
     res = EPSResult()
     res.nconv, res.its, res.reason, res.nmatvec = nconv, its, reason, nmatvec
     res.ncv, res.mpd, res.max_it = ncv, mpd, max_it
+    if st is not None:                                      # EPSComputeValues: STBackTransform, epssolve.c:160
+        for i in range(nconv):
+            eigr[i], eigi[i] = st.back(eigr[i], eigi[i])
+        compare = base                                      # the final ordering compares the back-transformed values (eps->sc has no map)
     res.eigr, res.eigi, res.errest = eigr[:nconv].copy(), eigi[:nconv].copy(), errest[:nconv].copy()
     res.V, res.ds = V, ds
     # EPSComputeVectors: Hermitian = Lanczos vectors as they are (epsdefault.c:28); NHEP = V*Z (:105-125)
     if hermitian:
         res.X = V.V[:, :nconv].copy()
+        if B is not None and purify:                        # EPSComputeVectors_Hermitian epsdefault.c:28-50: EPS_Purify + BVNormalize (B-norm)
+            for i in range(nconv):
+                x = Op @ res.X[:, i]
+                res.X[:, i] = x / math.sqrt(float(x @ (B @ x)))
     else:
         if nconv > 0:
             ds.vectors_nhep_all()      # state RAW after the trim ⇒ eigenvectors of T, no back-transform

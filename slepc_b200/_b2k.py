@@ -57,6 +57,8 @@ SIGNATURES = {
     "b2k_dot": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int],
     "b2k_set_random": [c_vp, c_vp, c_i64, c_i64, c_u64],
     "b2k_fill": [c_vp, c_vp, c_i64, c_dbl],
+    "b2k_pointwise_mult": [c_vp, c_vp, c_vp, c_vp, c_i64],
+    "b2k_csr_get_diagonal": [c_vp, c_vp, c_i64, c_vp],
     "b2k_gs_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     "b2k_gs_update_dot": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
     "b2k_gs_update_norm": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],

@@ -288,6 +288,12 @@ __global__ void __launch_bounds__(256) k_axpby(double *__restrict__ Y, int64_t l
   else
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = fma(alpha, x[r], beta * y[r]);
 }
+/* w = x .* y (Jacobi-preconditioned CG of the shift-and-invert ST: PETSc VecPointwiseMult) */
+__global__ void __launch_bounds__(256) k_pointwise_mult(double *__restrict__ w, const double *__restrict__ x, const double *__restrict__ y, int64_t n)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) w[r] = x[r] * y[r];
+}
 __global__ void __launch_bounds__(256) k_fill(double *__restrict__ x, int64_t n, double v)
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -763,6 +769,15 @@ extern "C" int b2k_axpby(b2k_ctx ctx, double *Y, int64_t ldy, const double *X, i
   if (n == 0 || k == 0) return B2K_OK;
   PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, (beta == 0.0 ? 16.0 : 24.0) * (double)n * k);
   k_axpby<<<grid2d(ctx, n, k), 256, 0, ctx->stream>>>(Y, ldy, X, ldx, n, alpha, beta);
+  PROF_END(ctx);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_pointwise_mult(b2k_ctx ctx, double *w, const double *x, const double *y, int64_t n)
+{
+  if (n == 0) return B2K_OK;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 24.0 * (double)n);
+  k_pointwise_mult<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(w, x, y, n);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;

@@ -599,6 +599,42 @@ extern "C" int b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **va
   return B2K_OK;
 }
 
+/* diag[r] = A(r, r + diag_col_offset) for the local rows (0 where the entry is not stored): MatGetDiagonal for the Jacobi
+   preconditioner of the shift-and-invert ST.  Works on whichever copy exists (SELL first). */
+__global__ void __launch_bounds__(256) k_sell_diag(const int64_t *__restrict__ sl_off, const int *__restrict__ col, const double *__restrict__ val,
+                                                    int64_t nrows, int64_t nslices, int coloff, double *__restrict__ diag)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= nslices) return;
+  const int64_t off = sl_off[s], r = s * 32 + lane;
+  const int width = (int)((sl_off[s + 1] - off) >> 5);
+  double d = 0.0;
+  for (int w = 0; w < width; w++) {
+    const int c = col[off + 32 * w + lane];
+    const double v = val[off + 32 * w + lane];
+    if ((int64_t)c == r + coloff && v != 0.0) d = v;        /* padding repeats a real column with value 0 */
+  }
+  if (r < nrows) diag[r] = d;
+}
+__global__ void __launch_bounds__(256) k_csr_diag(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ val,
+                                                   int64_t nrows, int coloff, double *__restrict__ diag)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  double d = 0.0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; k++) if ((int64_t)colidx[k] == r + coloff) d = val[k];
+  diag[r] = d;
+}
+extern "C" int b2k_csr_get_diagonal(b2k_ctx ctx, b2k_csr A, int64_t diag_col_offset, double *diag)
+{
+  if (A->nrows == 0) return B2K_OK;
+  if (A->nslices > 0) k_sell_diag<<<(unsigned)((A->nslices + 7) / 8), 256, 0, ctx->stream>>>(A->sl_off, A->sl_col, A->sl_val, A->nrows, A->nslices, (int)diag_col_offset, diag);
+  else k_csr_diag<<<(unsigned)((A->nrows + 255) / 256), 256, 0, ctx->stream>>>(A->rowptr, A->colidx, A->val, A->nrows, (int)diag_col_offset, diag);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+
 /* the caller is done with the arrays b2k_csr_arrays lent: drop the CSR copy again when a SELL copy serves the products */
 extern "C" int b2k_csr_release_arrays(b2k_csr A)
 {

@@ -88,6 +88,7 @@ typedef struct _MatOps {
   /* optional: Y(:,0:k) = A X(:,0:k) on column-major blocks in the Mat's own memory space (MatMatMult on a dense block, what
      BVMatMult uses in BV_MATMULT_MAT mode, svec.c:203-231); NULL = the caller loops over the columns with mult */
   PetscErrorCode (*multblock)(Mat, const PetscScalar *, PetscInt, PetscScalar *, PetscInt, PetscInt);
+  PetscErrorCode (*getdiagonal)(Mat, Vec);
 } MatOps;
 
 struct _p_Mat {
@@ -164,6 +165,10 @@ struct _p_BV {
   PetscErrorCode   (*ctor)(BV);   /* constructor deferred until the sizes are known (bvbasic.c:56-62) */
   PetscScalar       *work;        /* BVAllocateWork_Private (bvfunc.c:654) */
   size_t             lwork;
+  Mat                matrix;      /* inner-product matrix B (not owned), bvimpl.h:79 */
+  PetscBool          indef;
+  Vec                Bx;          /* B times the vector of the current inner product (BV_IPMatMult, bvimpl.h:147) */
+  BV                 cached;      /* B times the active columns (BV_IPMatMultBV, bvimpl.h:164) */
   void              *data;
 };
 #define BV_BUF(bv, i, j) ((bv)->buffer[(size_t)(i) + (size_t)(j) * ((bv)->nc + (bv)->m)])
@@ -192,10 +197,23 @@ struct _p_DS {
 };
 
 /* ---- ST -------------------------------------------------------------------------------------------- */
+struct _p_KSP {
+  Mat       A;
+  PetscReal rtol, abstol;
+  PetscInt  max_it, its, total_its;
+  Vec       dinv, r, z, p, q;    /* Jacobi preconditioner and the CG work vectors */
+  PetscBool setup;
+};
+
 struct _p_ST {
-  Mat         A;
+  Mat         A, B;              /* the problem matrices (B = NULL: standard problem)            */
+  PetscInt    nmat;
   PetscScalar sigma;
-  Mat         Op;                /* shell for A - sigma I when sigma != 0 */
+  PetscBool   sinvert;
+  Mat         Op;                /* shell of the transformed operator (NULL: A itself)            */
+  Mat         T;                 /* shell A - sigma B (coefficient matrix of the solve, or the multiplied one) */
+  KSP         ksp;
+  Vec         w;                 /* work vector of STApply                                        */
   PetscBool   setup;
 };
 
@@ -207,7 +225,8 @@ struct _p_EPS {
   EPSProblemType problem_type;
   EPSConv      conv;
   PetscScalar  target;
-  PetscBool    ishermitian;
+  PetscBool    ishermitian, isgeneralized, purify;
+  Mat          B;
   PetscReal    keep;
   PetscBool    lock;
   ST           st;

@@ -67,6 +67,8 @@ static PetscErrorCode BVReset_Private(BV bv)
   free(bv->h); bv->h = NULL;
   free(bv->c); bv->c = NULL;
   free(bv->work); bv->work = NULL; bv->lwork = 0;
+  PetscCall(VecDestroy(&bv->Bx));
+  PetscCall(BVDestroy(&bv->cached));
   return PETSC_SUCCESS;
 }
 
@@ -218,6 +220,7 @@ static PetscErrorCode BVDuplicate_Private(BV V, PetscInt m, BV *W)
   PetscCall(BVSetSizes(w, V->n, V->N, m));
   PetscCall(BVSetType(w, V->type_name));
   if (V->ops.duplicate) PetscCall(V->ops.duplicate(V, w));
+  w->matrix = V->matrix; w->indef = V->indef;            /* bvbasic.c:1413 */
   *W = w;
   return PETSC_SUCCESS;
 }
@@ -362,6 +365,57 @@ PetscErrorCode BVSetRandomColumn(BV bv, PetscInt j)
   return PETSC_SUCCESS;
 }
 
+/* ---- non-standard inner product: bvbasic.c:497-600, bvimpl.h:147-175, bvglobal.c:20-46 ------------------------------- */
+PetscErrorCode BVSetMatrix(BV bv, Mat B, PetscBool indef)
+{
+  if (B) {
+    PetscCheck(B->M == B->N, PETSC_ERR_ARG_SIZ, "Matrix argument is not square, it has %d rows and %d columns", B->M, B->N);
+    PetscCheck(!indef, PETSC_ERR_SUP, "indefinite inner products (GHIEP) are outside this path");
+    if (bv->sizes_set) PetscCheck(B->n == bv->n, PETSC_ERR_ARG_INCOMP, "Mismatching local dimension BV %d, Mat %d", bv->n, B->n);
+  }
+  if (B != bv->matrix || (B && indef != bv->indef)) {
+    bv->matrix = B;
+    bv->indef = B ? indef : PETSC_FALSE;
+    PetscCall(VecDestroy(&bv->Bx));
+    PetscCall(BVDestroy(&bv->cached));
+  }
+  return PETSC_SUCCESS;
+}
+PetscErrorCode BVGetMatrix(BV bv, Mat *B, PetscBool *indef) { if (B) *B = bv->matrix; if (indef) *indef = bv->indef; return PETSC_SUCCESS; }
+
+/* bv->Bx = B x (BV_IPMatMult; recomputed on every call: Vec objects carry no state counter here) */
+static PetscErrorCode BV_IPMatMult(BV bv, Vec x)
+{
+  if (!bv->Bx) PetscCall(MatCreateVecs(bv->matrix, &bv->Bx, NULL));
+  PetscCall(MatMult(bv->matrix, x, bv->Bx));
+  return PETSC_SUCCESS;
+}
+/* bv->cached(:, l:k) = B bv(:, l:k) (BV_IPMatMultBV) */
+static PetscErrorCode BV_IPMatMultBV(BV bv)
+{
+  if (!bv->cached) {
+    Mat B = bv->matrix;
+    bv->matrix = NULL;                            /* the cache itself uses the standard inner product */
+    PetscErrorCode ierr = BVDuplicate(bv, &bv->cached);
+    bv->matrix = B;
+    PetscCall(ierr);
+  }
+  PetscCall(BVSetActiveColumns(bv->cached, bv->l, bv->k));
+  PetscCall(BVMatMult(bv, bv->matrix, bv->cached));
+  return PETSC_SUCCESS;
+}
+/* sqrt(z^T B z): BVNorm_Private bvglobal.c:417-438 */
+static PetscErrorCode BVNorm_IP_Private(BV bv, Vec z, PetscReal *val)
+{
+  PetscScalar p;
+  PetscCall(BV_IPMatMult(bv, z));
+  PetscCall(VecDot(bv->Bx, z, &p));
+  const PetscReal deftol = 10 * PETSC_MACHINE_EPSILON;
+  PetscCheck(p > -deftol * fabs(p) - deftol, PETSC_ERR_FP, "The inner product is not well defined: indefinite matrix %g", p);
+  *val = (p < 0.0) ? 0.0 : sqrt(p);
+  return PETSC_SUCCESS;
+}
+
 /* ---- level-2/3 operations: bvops.c ------------------------------------------------------------------ */
 PetscErrorCode BVMult(BV Y, PetscScalar alpha, PetscScalar beta, BV X, Mat Q)
 {
@@ -466,7 +520,10 @@ PetscErrorCode BVDot(BV X, BV Y, Mat M)
   PetscCheck(M->n >= X->k, PETSC_ERR_ARG_SIZ, "Mat argument has %d columns, should have at least %d", M->n, X->k);
   PetscCheck(X->n == Y->n, PETSC_ERR_ARG_INCOMP, "Mismatching local dimension X %d, Y %d", X->n, Y->n);
   if (X->l == X->k || Y->l == Y->k) return PETSC_SUCCESS;
-  PetscCall(X->ops.dot(X, Y, M));
+  if (X->matrix) {                                /* M = Y^T (B X): bvglobal.c:84-91 */
+    PetscCall(BV_IPMatMultBV(X));
+    PetscCall(X->ops.dot(X->cached, Y, M));
+  } else PetscCall(X->ops.dot(X, Y, M));
   return PETSC_SUCCESS;
 }
 
@@ -476,7 +533,8 @@ PetscErrorCode BVDotVec(BV X, Vec y, PetscScalar m[])
   BVCheckOp(X, dotvec);
   PetscCheck(y, PETSC_ERR_ARG_NULL, "null vector");
   PetscCheck(X->n == y->n, PETSC_ERR_ARG_INCOMP, "Mismatching local dimension X %d, y %d", X->n, y->n);
-  PetscCall(X->ops.dotvec(X, y, m));
+  if (X->matrix) { PetscCall(BV_IPMatMult(X, y)); PetscCall(X->ops.dotvec(X, X->Bx, m)); }   /* svec.c:117-120 */
+  else PetscCall(X->ops.dotvec(X, y, m));
   return PETSC_SUCCESS;
 }
 
@@ -490,7 +548,9 @@ PetscErrorCode BVDotColumn(BV X, PetscInt j, PetscScalar *q)
   X->k = j;
   Vec y;
   PetscCall(BVGetColumn(X, j, &y));
-  PetscErrorCode ierr = X->ops.dotvec(X, y, q);
+  PetscErrorCode ierr = PETSC_SUCCESS;
+  if (X->matrix) { ierr = BV_IPMatMult(X, y); if (!ierr) ierr = X->ops.dotvec(X, X->Bx, q); }
+  else ierr = X->ops.dotvec(X, y, q);
   PetscCall(BVRestoreColumn(X, j, &y));
   X->k = ksave;
   PetscCall(ierr);
@@ -540,6 +600,7 @@ PetscErrorCode BVDotVecBegin(BV X, Vec y, PetscScalar *m)
   BVCheckSizes(X);
   PetscCheck(y, PETSC_ERR_ARG_NULL, "null vector");
   PetscCheck(X->n == y->n, PETSC_ERR_ARG_INCOMP, "Mismatching local dimension X %d, y %d", X->n, y->n);
+  PetscCheck(!X->matrix, PETSC_ERR_SUP, "split-phase reductions with a non-standard inner product are not available");
   if (X->ops.dotvec_begin) { PetscCall(X->ops.dotvec_begin(X, y, m)); return PETSC_SUCCESS; }
   BVCheckOp(X, dotvec_local);
   const PetscInt nv = X->k - X->l;
@@ -597,6 +658,7 @@ PetscErrorCode BVNormColumnBegin(BV bv, PetscInt j, NormType type, PetscReal *va
 {
   BVCheckSizes(bv);
   PetscCheck(j >= 0 && j < bv->m, PETSC_ERR_ARG_OUTOFRANGE, "Argument j has wrong value %d, the number of columns is %d", j, bv->m);
+  PetscCheck(!bv->matrix, PETSC_ERR_SUP, "split-phase reductions with a non-standard inner product are not available");
   if (bv->ops.norm_begin) { PetscCall(bv->ops.norm_begin(bv, j, type, val)); return PETSC_SUCCESS; }
   BVCheckOp(bv, norm_local);
   PetscCheck(!g_sr.reduced, PETSC_ERR_ORDER, "Called before all BVxxxEnd() called");
@@ -628,6 +690,7 @@ PetscErrorCode BVNorm(BV bv, NormType type, PetscReal *val)
   BVCheckSizes(bv);
   BVCheckOp(bv, norm);
   PetscCheck(type != NORM_2 || bv->k - bv->l <= 1, PETSC_ERR_SUP, "Requested norm not available");   /* bvglobal.c:496 */
+  PetscCheck(!bv->matrix, PETSC_ERR_SUP, "Matrix norm not available for non-standard inner product");   /* bvglobal.c:497 */
   PetscCall(bv->ops.norm(bv, -1, type, val));
   return PETSC_SUCCESS;
 }
@@ -637,7 +700,13 @@ PetscErrorCode BVNormColumn(BV bv, PetscInt j, NormType type, PetscReal *val)
   BVCheckSizes(bv);
   BVCheckOp(bv, norm);
   PetscCheck(j >= 0 && j < bv->m, PETSC_ERR_ARG_OUTOFRANGE, "Argument j has wrong value %d, the number of columns is %d", j, bv->m);
-  PetscCall(bv->ops.norm(bv, j, type, val));
+  if (bv->matrix) {                               /* sqrt(V[j]' B V[j]), the type is ignored: bvglobal.c:547-551 */
+    Vec z;
+    PetscCall(BVGetColumn(bv, j, &z));
+    PetscErrorCode ierr = BVNorm_IP_Private(bv, z, val);
+    PetscCall(BVRestoreColumn(bv, j, &z));
+    PetscCall(ierr);
+  } else PetscCall(bv->ops.norm(bv, j, type, val));
   return PETSC_SUCCESS;
 }
 
@@ -645,13 +714,25 @@ PetscErrorCode BVNormVec(BV bv, Vec v, NormType type, PetscReal *val)
 {
   BVCheckSizes(bv);
   PetscCheck(v->n == bv->n, PETSC_ERR_ARG_INCOMP, "Vec argument has local dimension %d, should be %d", v->n, bv->n);
-  PetscCall(VecNorm(v, type, val));               /* bvglobal.c:590: standard inner product */
+  if (bv->matrix) PetscCall(BVNorm_IP_Private(bv, v, val));   /* bvglobal.c:607-609 */
+  else PetscCall(VecNorm(v, type, val));
   return PETSC_SUCCESS;
 }
 
 PetscErrorCode BVNormalize(BV bv, PetscScalar *eigi)
 {
   BVCheckSizes(bv);
+  if (bv->matrix) {                               /* BVNormalize_Private bvglobal.c:800-834: B-norms, one column at a time */
+    PetscCheck(!eigi, PETSC_ERR_SUP, "conjugate pairs with a non-standard inner product are outside this path");
+    BVCheckOp(bv, scale);
+    for (PetscInt i = bv->l; i < bv->k; i++) {
+      PetscReal nrm;
+      PetscCall(BVNormColumn(bv, i, NORM_2, &nrm));
+      if (nrm != 0.0 && nrm != 1.0) PetscCall(bv->ops.scale(bv, i, 1.0 / nrm));
+    }
+    bv->state++;
+    return PETSC_SUCCESS;
+  }
   BVCheckOp(bv, normalize);
   PetscCall(bv->ops.normalize(bv, eigi));
   bv->state++;
@@ -717,7 +798,9 @@ static PetscErrorCode BVOrthogonalizeCGS1(BV bv, PetscInt j, Vec v, PetscBool *w
       Vec y;
       bv->k = j + 1;
       PetscCall(BVGetColumn(bv, j, &y));
-      PetscErrorCode ierr = bv->ops.dotvec(bv, y, c);
+      PetscErrorCode ierr = PETSC_SUCCESS;
+      if (bv->matrix) { ierr = BV_IPMatMult(bv, y); if (!ierr) ierr = bv->ops.dotvec(bv, bv->Bx, c); }   /* svec.c:117-120 */
+      else ierr = bv->ops.dotvec(bv, y, c);
       PetscCall(BVRestoreColumn(bv, j, &y));
       bv->k = j;
       PetscCall(ierr);
@@ -754,7 +837,8 @@ static PetscErrorCode BVOrthogonalizeMGS1(BV bv, PetscInt j, Vec v, PetscBool *w
   for (PetscInt i = -bv->nc; i < j; i++) {
     if (which && i >= 0 && !which[i]) continue;
     PetscCall(BVGetColumn(bv, i, &vi));
-    PetscCall(VecDot(w, vi, &dot));
+    if (bv->matrix) { PetscCall(BV_IPMatMult(bv, w)); PetscCall(VecDot(bv->Bx, vi, &dot)); }   /* bvorthog.c:69-73 */
+    else PetscCall(VecDot(w, vi, &dot));
     cc[bv->nc + i] = dot;
     PetscCall(VecAXPY(w, -dot, vi));
     PetscCall(BVRestoreColumn(bv, i, &vi));
@@ -773,7 +857,8 @@ static PetscErrorCode BVOrthogonalizeGS(BV bv, PetscInt j, Vec v, PetscBool *whi
   PetscInt k, l;
   const PetscBool mgs = (bv->orthog_type == BV_ORTHOG_MGS) ? PETSC_TRUE : PETSC_FALSE;
   PetscErrorCode (*gs1)(BV, PetscInt, Vec, PetscBool *, PetscScalar *, PetscScalar *, PetscReal *, PetscReal *) =
-      (bv->ops.gramschmidt && !mgs) ? bv->ops.gramschmidt : (mgs ? BVOrthogonalizeMGS1 : BVOrthogonalizeCGS1);   /* bvorthog.c:134 */
+      (bv->ops.gramschmidt && !mgs && !bv->matrix) ? bv->ops.gramschmidt : (mgs ? BVOrthogonalizeMGS1 : BVOrthogonalizeCGS1);   /* bvorthog.c:134; the
+      fused slot of type b200 implements the STANDARD inner product: with BVSetMatrix the generic pass (B x through MatMult) runs */
   if (v) { k = bv->k; h = bv->h; c = bv->c; }
   else { k = j; h = NULL; c = NULL; }
   const PetscBool dolindep = lindep ? PETSC_TRUE : PETSC_FALSE;

@@ -21,6 +21,7 @@ PetscErrorCode EPSCreate(EPS *out)
   eps->problem_type = (EPSProblemType)0;
   eps->conv = EPS_CONV_REL;
   eps->keep = 0.0; eps->lock = PETSC_TRUE;
+  eps->purify = PETSC_TRUE;                       /* epsbasic.c:80 */
   PetscCall(STCreate(&eps->st));
   PetscCall(BVCreate(&eps->V));
   PetscCall(DSCreate(&eps->ds));
@@ -46,10 +47,11 @@ PetscErrorCode EPSDestroy(EPS *peps)
 PetscErrorCode EPSSetOperators(EPS eps, Mat A, Mat B)
 {
   PetscCheck(A, PETSC_ERR_ARG_NULL, "null matrix");
-  PetscCheck(!B, PETSC_ERR_SUP, "generalized problems need a linear solve and are outside the Krylov hot path");
   PetscCheck(A->M == A->N, PETSC_ERR_ARG_WRONG, "A is a non-square matrix (%d rows, %d cols)", A->M, A->N);
-  Mat mats[1] = {A};
-  PetscCall(STSetMatrices(eps->st, 1, mats));
+  if (B) PetscCheck(B->M == B->N && B->M == A->M, PETSC_ERR_ARG_WRONG, "Dimensions of A and B do not match (%d, %d)", A->M, B->M);   /* epssetup.c:446-452 */
+  Mat mats[2] = {A, B};
+  PetscCall(STSetMatrices(eps->st, B ? 2 : 1, mats));
+  eps->B = B;
   eps->n = A->N; eps->nloc = A->n;
   eps->setup_done = PETSC_FALSE; eps->solved = PETSC_FALSE; eps->started = PETSC_FALSE;
   return PETSC_SUCCESS;
@@ -57,9 +59,10 @@ PetscErrorCode EPSSetOperators(EPS eps, Mat A, Mat B)
 
 PetscErrorCode EPSSetProblemType(EPS eps, EPSProblemType type)
 {
-  PetscCheck(type == EPS_HEP || type == EPS_NHEP, PETSC_ERR_SUP, "only EPS_HEP and EPS_NHEP are on the Krylov hot path");
+  PetscCheck(type == EPS_HEP || type == EPS_NHEP || type == EPS_GHEP, PETSC_ERR_SUP, "EPS_HEP, EPS_GHEP (B symmetric positive definite) and EPS_NHEP are available");
   eps->problem_type = type;
-  eps->ishermitian = (type == EPS_HEP) ? PETSC_TRUE : PETSC_FALSE;
+  eps->ishermitian = (type == EPS_HEP || type == EPS_GHEP) ? PETSC_TRUE : PETSC_FALSE;
+  eps->isgeneralized = (type == EPS_GHEP) ? PETSC_TRUE : PETSC_FALSE;
   eps->setup_done = PETSC_FALSE;
   return PETSC_SUCCESS;
 }
@@ -107,7 +110,15 @@ PetscErrorCode EPSSetWhichEigenpairs(EPS eps, EPSWhich which)
   eps->setup_done = PETSC_FALSE;
   return PETSC_SUCCESS;
 }
-PetscErrorCode EPSSetTarget(EPS eps, PetscScalar target) { eps->target = target; return PETSC_SUCCESS; }
+/* epsopts.c:882-903: the target is also the default shift of the ST (STSetDefaultShift) */
+PetscErrorCode EPSSetTarget(EPS eps, PetscScalar target)
+{
+  eps->target = target;
+  PetscCall(STSetShift(eps->st, target));
+  eps->setup_done = PETSC_FALSE;
+  return PETSC_SUCCESS;
+}
+PetscErrorCode EPSSetPurify(EPS eps, PetscBool purify) { eps->purify = purify; eps->setup_done = PETSC_FALSE; return PETSC_SUCCESS; }
 PetscErrorCode EPSSetConvergenceTest(EPS eps, EPSConv conv) { eps->conv = conv; return PETSC_SUCCESS; }
 PetscErrorCode EPSKrylovSchurSetRestart(EPS eps, PetscReal keep)
 {
@@ -141,15 +152,19 @@ PetscErrorCode EPSSetInitialSpace(EPS eps, PetscInt n, Vec is[])
 /* comparator seen by DS: SlepcSCCompare with map = STBackTransform (slepcsc.c:40-63) */
 static PetscErrorCode EPSCompare_Private(PetscScalar ar, PetscScalar ai, PetscScalar br, PetscScalar bi, PetscInt *res, void *ctx)
 {
-  EPS eps = (EPS)ctx;
-  return eps->sc.fn(ar + eps->st->sigma, ai, br + eps->st->sigma, bi, res, eps->sc.ctx);   /* live shift (SlepcMap_ST): never stale after STSetShift */
+  EPS eps = (EPS)ctx;                              /* SlepcMap_ST: the values are compared after STBackTransform, with the live shift */
+  PetscCall(STBackTransform(eps->st, 1, &ar, &ai));
+  PetscCall(STBackTransform(eps->st, 1, &br, &bi));
+  return eps->sc.fn(ar, ai, br, bi, res, eps->sc.ctx);
 }
 
 PetscErrorCode EPSSetUp(EPS eps)
 {
   if (eps->setup_done) return PETSC_SUCCESS;
   PetscCheck(eps->st->A, PETSC_ERR_ARG_WRONGSTATE, "EPSSetOperators() must be called first");
-  if (!eps->problem_type) PetscCall(EPSSetProblemType(eps, EPS_NHEP));          /* epssetup.c:311 */
+  if (!eps->problem_type) PetscCall(EPSSetProblemType(eps, eps->B ? EPS_GHEP : EPS_NHEP));   /* epssetup.c:311-318 (GNHEP is outside this path) */
+  PetscCheck(!eps->B || eps->isgeneralized, PETSC_ERR_ARG_INCOMP, "Inconsistent EPS state: the problem type does not match the number of matrices");   /* epssetup.c:319 */
+  PetscCheck(eps->B || !eps->isgeneralized, PETSC_ERR_ARG_INCOMP, "Inconsistent EPS state: the problem type does not match the number of matrices");
   if (eps->tol == (PetscReal)PETSC_DETERMINE) eps->tol = SLEPC_DEFAULT_TOL;
   PetscCall(STSetUp(eps->st));
   /* EPSSetUp_KrylovSchur krylovschur.c:108-116 */
@@ -165,7 +180,7 @@ PetscErrorCode EPSSetUp(EPS eps)
   eps->ncv = ncv; eps->mpd = mpd;
   PetscCheck(eps->ncv <= eps->nev + eps->mpd, PETSC_ERR_USER_INPUT, "The value of ncv must not be larger than nev+mpd");
   if (eps->max_it == PETSC_DETERMINE) eps->max_it = PetscMax(100, 2 * eps->n / eps->ncv);
-  if (!eps->which) eps->which = EPS_LARGEST_MAGNITUDE;                           /* EPSSetWhichEigenpairs_Default epsdefault.c:210-220 */
+  if (!eps->which) eps->which = eps->st->sinvert ? EPS_TARGET_MAGNITUDE : EPS_LARGEST_MAGNITUDE;   /* EPSSetWhichEigenpairs_Default epsdefault.c:210-220 */
   PetscCheck(eps->lock || eps->mpd >= eps->ncv, PETSC_ERR_SUP, "Should not use mpd parameter in non-locking variant");
   if (!eps->keep) eps->keep = 0.5;
 
@@ -204,6 +219,11 @@ PetscErrorCode EPSSetUp(EPS eps)
     PetscCall(ierr);
   } else if (oldsize != requested) PetscCall(BVResize(eps->V, requested, PETSC_FALSE));
 
+  /* generalized symmetric-definite problem: B-inner product in the basis (epssetup.c:372-381); purification only makes sense there */
+  if (eps->isgeneralized && eps->ishermitian) { Mat B; PetscCall(STGetBilinearForm(eps->st, &B)); PetscCall(BVSetMatrix(eps->V, B, PETSC_FALSE)); }
+  else PetscCall(BVSetMatrix(eps->V, NULL, PETSC_FALSE));
+  if (!eps->isgeneralized) eps->purify = PETSC_FALSE;                            /* epssetup.c:359-369 */
+
   /* DS: krylovschur.c:153-168 */
   if (eps->ishermitian) {
     PetscCall(DSSetType(eps->ds, DSHEP));
@@ -229,6 +249,19 @@ static PetscErrorCode EPSGetStartVector(EPS eps, PetscInt i, PetscBool *breakdow
   PetscReal norm;
   PetscBool lindep;
   if (i > 0 || eps->nini == 0) PetscCall(BVSetRandomColumn(eps->V, i));
+  if (eps->isgeneralized && eps->ishermitian) {   /* force the vector into the range of OP for definite generalized problems, epssolve.c:855-862 */
+    Vec w, z;
+    PetscCall(BVCreateVec(eps->V, &w));
+    PetscErrorCode ierr = BVCopyVec(eps->V, i, w);
+    if (!ierr) {
+      PetscCall(BVGetColumn(eps->V, i, &z));
+      ierr = STApply(eps->st, w, z);
+      PetscCall(BVRestoreColumn(eps->V, i, &z));
+      eps->V->state++;
+    }
+    PetscCall(VecDestroy(&w));
+    PetscCall(ierr);
+  }
   PetscCall(BVOrthogonalizeColumn(eps->V, i, NULL, &norm, &lindep));
   if (breakdown) *breakdown = lindep;
   else if (lindep || norm == 0.0) {
@@ -246,7 +279,7 @@ static PetscErrorCode EPSKrylovConvergence(EPS eps, PetscInt kini, PetscInt nits
   PetscReal resnorm;
   for (k = kini; k < kini + nits; k++) {
     PetscScalar re = eps->eigr[k], im = eps->eigi[k];
-    PetscCall(STBackTransform(eps->st, 1, &re, &im));   /* isshift branch, :246 */
+    if (!eps->st->sinvert) PetscCall(STBackTransform(eps->st, 1, &re, &im));   /* only for STSHIFT, epskrylov.c:246; sinvert tests the transformed value */
     newk = k;
     PetscCall(DSVectors(eps->ds, DS_MAT_X, &newk, &resnorm));
     resnorm *= beta;
@@ -348,7 +381,7 @@ static PetscErrorCode EPSSortEigenvalues_Private(EPS eps, PetscInt n, PetscScala
     j = i + 1;
     if (im != 0) { i--; im = eigi[perm[i]]; }      /* complex eigenvalue */
     while (j < n) {
-      PetscCall(EPSCompare_Private(re - eps->st->sigma, im, eigr[perm[j]] - eps->st->sigma, eigi[perm[j]], &result, eps));
+      PetscCall(eps->sc.fn(re, im, eigr[perm[j]], eigi[perm[j]], &result, eps->sc.ctx));   /* eps->sc has no map: the values are already back-transformed, epssolve.c:178 */
       if (result <= 0) break;
       if (!im) {
         if (eigi[perm[j]] == 0.0) { tmp = perm[j - 1]; perm[j - 1] = perm[j]; perm[j] = tmp; j++; }
@@ -372,7 +405,27 @@ static PetscErrorCode EPSComputeVectors(EPS eps)
 {
   if (eps->vectors_done) return PETSC_SUCCESS;
   eps->vectors_done = PETSC_TRUE;
-  if (eps->ishermitian || eps->nconv == 0) return PETSC_SUCCESS;
+  if (eps->nconv == 0) return PETSC_SUCCESS;
+  if (eps->ishermitian) {                         /* EPSComputeVectors_Hermitian epsdefault.c:28-50 */
+    if (eps->purify) {                            /* EPS_Purify epsimpl.h:297-312: x <- OP x, then B-normalise */
+      Vec v, z;
+      PetscCall(BVCreateVec(eps->V, &v));
+      PetscErrorCode ierr = PETSC_SUCCESS;
+      for (PetscInt i = 0; i < eps->nconv && !ierr; i++) {
+        ierr = BVCopyVec(eps->V, i, v);
+        if (ierr) break;
+        PetscCall(BVGetColumn(eps->V, i, &z));
+        ierr = STApply(eps->st, v, z);
+        PetscCall(BVRestoreColumn(eps->V, i, &z));
+        eps->V->state++;
+      }
+      PetscCall(VecDestroy(&v));
+      PetscCall(ierr);
+      PetscCall(BVSetActiveColumns(eps->V, 0, eps->nconv));
+      PetscCall(BVNormalize(eps->V, NULL));
+    }
+    return PETSC_SUCCESS;
+  }
   Mat Z;
   PetscCall(DSVectors(eps->ds, DS_MAT_X, NULL, NULL));
   PetscCall(DSGetMat(eps->ds, DS_MAT_X, &Z));
@@ -475,14 +528,18 @@ PetscErrorCode EPSGetErrorEstimate(EPS eps, PetscInt i, PetscReal *errest)
 /* EPSComputeResidualNorm_Private epssolve.c:666-722 (standard problem) */
 static PetscErrorCode EPSComputeResidualNorm_Private(EPS eps, PetscScalar kr, PetscScalar ki, Vec xr, Vec xi, Vec *z, PetscReal *norm)
 {
-  Mat A = eps->st->A;
+  Mat A = eps->st->A, B = eps->st->B;
   Vec u = z[0], v = z[1], w = z[2];
   PetscReal ni, nr;
   if (ki == 0 || fabs(ki) < fabs(kr * PETSC_MACHINE_EPSILON)) {
-    PetscCall(MatMult(A, xr, u));
-    if (fabs(kr) > PETSC_MACHINE_EPSILON) PetscCall(VecAXPY(u, -kr, xr));
+    PetscCall(MatMult(A, xr, u));                 /* u = A x */
+    if (fabs(kr) > PETSC_MACHINE_EPSILON) {
+      if (B) { PetscCall(MatMult(B, xr, w)); PetscCall(VecAXPY(u, -kr, w)); }   /* u = A x - k B x */
+      else PetscCall(VecAXPY(u, -kr, xr));
+    }
     PetscCall(VecNorm(u, NORM_2, norm));
   } else {
+    PetscCheck(!B, PETSC_ERR_SUP, "complex eigenvalues of a generalized problem are outside this path");
     PetscCall(MatMult(A, xr, u));
     if (SlepcAbsEigenvalue(kr, ki) > PETSC_MACHINE_EPSILON) {
       PetscCall(VecCopy(xr, v));
@@ -512,9 +569,11 @@ PetscErrorCode EPSComputeError(EPS eps, PetscInt i, EPSErrorType type, PetscReal
   PetscScalar kr, ki;
   PetscCall(EPSGetEigenpair(eps, i, &kr, &ki, xr, xi));
   PetscCall(EPSComputeResidualNorm_Private(eps, kr, ki, xr, xi, w, error));
+  PetscReal vecnorm = 1.0;
+  if (eps->problem_type == EPS_GHEP) PetscCall(VecNorm(xr, NORM_2, &vecnorm));   /* eigenvectors are B-normalised: epssolve.c:776 */
   switch (type) {
   case EPS_ERROR_ABSOLUTE: break;
-  case EPS_ERROR_RELATIVE: *error /= SlepcAbsEigenvalue(kr, ki); break;
+  case EPS_ERROR_RELATIVE: *error /= SlepcAbsEigenvalue(kr, ki) * vecnorm; break;
   default: SETERRQ(PETSC_ERR_SUP, "backward errors need a matrix norm operation, which this Mat type does not provide");
   }
   return PETSC_SUCCESS;

@@ -206,6 +206,15 @@ static PetscErrorCode MatMultTranspose_B200CSR(Mat A, Vec x, Vec y)
   return PETSC_SUCCESS;
 }
 
+static PetscErrorCode MatGetDiagonal_B200CSR(Mat A, Vec d)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  PetscCheck(d->mem == B2K_MEM_DEVICE, PETSC_ERR_ARG_INCOMP, "b200csr needs device vectors");
+  PetscCheck(A->M == A->N && A->rstart == A->cstart && A->m == A->n, PETSC_ERR_SUP, "MatGetDiagonal needs a square matrix whose owned columns are its owned rows");
+  B2KCall(b2k_csr_get_diagonal(CTX(), a->A, 0, d->array));
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode MatDestroy_B200CSR(Mat A)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
@@ -236,6 +245,7 @@ static PetscErrorCode MatSetUp_B200CSR(Mat A, PetscInt M, PetscInt N, PetscInt r
   A->ops.mult = MatMult_B200CSR;
   A->ops.multtranspose = MatMultTranspose_B200CSR;
   A->ops.multblock = MatMultBlock_B200CSR;
+  A->ops.getdiagonal = MatGetDiagonal_B200CSR;
   A->ops.destroy = MatDestroy_B200CSR;
   *out = a;
   return PETSC_SUCCESS;

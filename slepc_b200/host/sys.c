@@ -203,6 +203,7 @@ typedef struct {
   PetscErrorCode (*dot_local)(Vec, Vec, PetscScalar *);
   PetscErrorCode (*axpy)(Vec, PetscScalar, Vec);
   PetscErrorCode (*scale)(Vec, PetscScalar);
+  PetscErrorCode (*pointwisemult)(Vec, Vec, Vec);        /* w = x .* y */
 } B2KVecHostOps;
 static B2KVecHostOps g_hostvec;
 static PetscBool g_hostvec_set = PETSC_FALSE;
@@ -366,6 +367,34 @@ PetscErrorCode VecScale(Vec v, PetscScalar alpha)
   return PETSC_SUCCESS;
 }
 
+PetscErrorCode VecAYPX(Vec y, PetscScalar beta, Vec x)
+{
+  PetscCheck(x->mem == y->mem && x->n == y->n, PETSC_ERR_ARG_INCOMP, "incompatible vectors");
+  if (y->mem == B2K_MEM_DEVICE) { NEED_CTX(); B2KCall(b2k_axpby(g_ctx, y->array, y->n, x->array, x->n, y->n, 1, 1.0, beta)); }
+  else { PetscCall(VecScale(y, beta)); PetscCall(VecAXPY(y, 1.0, x)); }
+  return PETSC_SUCCESS;
+}
+
+PetscErrorCode VecPointwiseMult(Vec w, Vec x, Vec y)
+{
+  PetscCheck(w->mem == x->mem && x->mem == y->mem && w->n == x->n && x->n == y->n, PETSC_ERR_ARG_INCOMP, "incompatible vectors");
+  if (w->mem == B2K_MEM_DEVICE) { NEED_CTX(); B2KCall(b2k_pointwise_mult(g_ctx, w->array, x->array, y->array, w->n)); }
+  else { NEED_HOSTVEC(); PetscCheck(g_hostvec.pointwisemult, PETSC_ERR_SUP, "the host Vec plug-in has no pointwise product"); PetscCall(g_hostvec.pointwisemult(w, x, y)); }
+  return PETSC_SUCCESS;
+}
+
+/* set-up only (once per linear system): through the host */
+PetscErrorCode VecReciprocal(Vec v)
+{
+  PetscScalar *h = (PetscScalar *)malloc(sizeof(PetscScalar) * (size_t)(v->n > 0 ? v->n : 1));
+  PetscCheck(h, PETSC_ERR_MEM, "out of memory");
+  PetscErrorCode ierr = VecGetValuesHost(v, h);
+  if (!ierr) { for (PetscInt i = 0; i < v->n; i++) if (h[i] != 0.0) h[i] = 1.0 / h[i]; ierr = VecSetValuesHost(v, h); }
+  free(h);
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode VecCopy(Vec x, Vec y)
 {
   PetscCheck(x->n == y->n, PETSC_ERR_ARG_INCOMP, "incompatible vectors");
@@ -445,6 +474,14 @@ PetscErrorCode MatMult(Mat A, Vec x, Vec y)
   return PETSC_SUCCESS;
 }
 
+PetscErrorCode MatGetDiagonal(Mat A, Vec d)
+{
+  PetscCheck(A->ops.getdiagonal, PETSC_ERR_SUP, "Mat type %s has no MatGetDiagonal", A->type);
+  PetscCheck(d->n == A->m, PETSC_ERR_ARG_SIZ, "vector of %d entries for a matrix with %d local rows", d->n, A->m);
+  PetscCall(A->ops.getdiagonal(A, d));
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y)
 {
   PetscCheck(A->ops.multtranspose, PETSC_ERR_SUP, "Mat type %s has no MatMultTranspose", A->type);
@@ -500,6 +537,7 @@ PetscErrorCode MatCreateShell(PetscInt m, PetscInt n, PetscInt M, PetscInt N, B2
 PetscErrorCode MatShellGetContext(Mat A, void **ctx) { *ctx = A->data; return PETSC_SUCCESS; }
 PetscErrorCode MatShellSetMult(Mat A, MatMultFn f) { A->ops.mult = f; return PETSC_SUCCESS; }
 PetscErrorCode MatShellSetMultTranspose(Mat A, MatMultFn f) { A->ops.multtranspose = f; return PETSC_SUCCESS; }
+PetscErrorCode MatShellSetGetDiagonal(Mat A, MatGetDiagonalFn f) { A->ops.getdiagonal = f; return PETSC_SUCCESS; }
 
 /* ---- names and ASCII viewers: PetscObjectSetName, PetscViewerASCIIGetStdout / PushFormat / PopFormat, VecView, MatView --------
    Only what the reference's BV test programs print (bv/tests/test1.c -verbose): the default ASCII format and INFO_DETAIL. */

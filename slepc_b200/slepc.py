@@ -135,7 +135,7 @@ NORM_1, NORM_2, NORM_FROBENIUS, NORM_INFINITY = 0, 1, 2, 3
 BV_ORTHOG_CGS, BV_ORTHOG_MGS = 0, 1
 BV_ORTHOG_REFINE_IFNEEDED, BV_ORTHOG_REFINE_NEVER, BV_ORTHOG_REFINE_ALWAYS = 0, 1, 2
 BV_ORTHOG_BLOCK_GS, BV_ORTHOG_BLOCK_CHOL, BV_ORTHOG_BLOCK_TSQR, BV_ORTHOG_BLOCK_TSQRCHOL, BV_ORTHOG_BLOCK_SVQB = 0, 1, 2, 3, 4
-EPS_HEP, EPS_NHEP = 1, 3
+EPS_HEP, EPS_GHEP, EPS_NHEP = 1, 2, 3
 EPS_LARGEST_MAGNITUDE, EPS_SMALLEST_MAGNITUDE, EPS_LARGEST_REAL, EPS_SMALLEST_REAL = 1, 2, 3, 4
 EPS_LARGEST_IMAGINARY, EPS_SMALLEST_IMAGINARY, EPS_TARGET_MAGNITUDE, EPS_TARGET_REAL = 5, 6, 7, 8
 EPS_ERROR_ABSOLUTE, EPS_ERROR_RELATIVE = 0, 1
@@ -341,12 +341,27 @@ def _set_vec_rstart(vec, rstart):
 class EPS(Handle):
     _destroy = "EPSDestroy"
 
-    def __init__(self, A=None, hermitian=True):
+    def __init__(self, A=None, hermitian=True, B=None):
         super().__init__()
         S.EPSCreate(self.ref)
         if A is not None:
-            S.EPSSetOperators(self.h, A.h, None)
-            S.EPSSetProblemType(self.h, EPS_HEP if hermitian else EPS_NHEP)
+            S.EPSSetOperators(self.h, A.h, B.h if B is not None else None)
+            S.EPSSetProblemType(self.h, (EPS_GHEP if B is not None else EPS_HEP) if hermitian else EPS_NHEP)
+
+    def st_sinvert(self, sigma=0.0):
+        """-st_type sinvert -eps_target sigma"""
+        st = c_vp()
+        S.EPSGetST(self.h, ctypes.byref(st))
+        S.STSetType(st, b"sinvert")
+        S.EPSSetTarget(self.h, sigma)
+        S.EPSSetWhichEigenpairs(self.h, EPS_TARGET_MAGNITUDE)
+
+    def ksp_iterations(self):
+        st, ksp, n = c_vp(), c_vp(), c_int()
+        S.EPSGetST(self.h, ctypes.byref(st))
+        S.STGetKSP(st, ctypes.byref(ksp))
+        S.KSPGetTotalIterations(ksp, ctypes.byref(n))
+        return n.value
 
     def bv(self):
         h = c_vp()

@@ -308,3 +308,108 @@ def test_bv_split_phase_reductions():
     assert np.isclose(a.value, np.linalg.norm(Uh[:, 0]), rtol=1e-14)
     assert np.allclose(m2[:3], Xh[:, :3].T @ Xh[:, 3], rtol=1e-13, atol=1e-13)
     X.destroy(); U.destroy()
+
+
+# ---- generalized symmetric-definite problems, B-inner product, shift-and-invert ---------------------------
+def _ex13(n, m=None):
+    import scipy.sparse as sp
+    m = n if m is None else m
+    A = O.laplacian_2d(m, n)
+    B = sp.identity(n * m, format="csr") * 4.0
+    return A, B
+
+
+def test_eps_ex13_generalized_sinvert_golden_and_oracle_parity():
+    """ex13 -eps_nev 4 -eps_ncv 22 -eps_tol 1e-5 -st_type sinvert through the C host driver (EPS_GHEP, BVSetMatrix, STSINVERT with the
+    CG linear solves of ksp.c) on the CPU plug-in: the reference's golden 0.04051, 0.09963, 0.09963, 0.15875 and the numpy oracle
+    (which solves with a sparse LU like the reference) to 1e-9."""
+    A, B = _ex13(10)
+    Am, Bm = CP.mat_csr(A), CP.mat_csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, 22, SL.PETSC_DETERMINE)
+    S.EPSSetTolerances(eps.h, 1e-5, SL.PETSC_CURRENT)
+    eps.st_sinvert(0.0)
+    eps.solve()
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = [eps.eigenvalue(i)[0] for i in range(eps.nconv)]
+    assert [f"{x:.5f}" for x in lam[:4]] == ["0.04051", "0.09963", "0.09963", "0.15875"]
+    ref = O.eps_krylovschur(A, 100, nev=4, ncv=22, tol=1e-5, B=B, sigma=0.0, sinvert=True)
+    assert eps.nconv == ref.nconv and eps.its == ref.its
+    assert np.allclose(lam, ref.eigr[ref.perm], rtol=1e-9, atol=0)
+    assert max(eps.error(i) for i in range(4)) < 5e-5
+    assert eps.ksp_iterations() > 0
+    # eigenvectors are B-normalised
+    x, _ = Am.create_vecs()
+    bx, _ = Am.create_vecs()
+    S.EPSGetEigenpair(eps.h, 0, None, None, x.h, None)
+    S.MatMult(Bm.h, x.h, bx.h)
+    d = c_dbl()
+    S.VecDot(x.h, bx.h, ctypes.byref(d))
+    assert abs(d.value - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("sigma", [0.0, -0.3])
+def test_eps_generalized_nontrivial_mass_matrix(sigma):
+    """A x = k B x with a tridiagonal mass-like B (not a multiple of I): smallest eigenvalues by shift-and-invert against
+    scipy's generalized dense solver; B-orthonormality of the basis"""
+    import scipy.linalg as sla
+    import scipy.sparse as sp
+    n = 60
+    A = O.laplacian_1d(n) * (n + 1.0)
+    B = sp.diags([np.full(n - 1, 1.0), np.full(n, 4.0), np.full(n - 1, 1.0)], [-1, 0, 1], format="csr") / (6.0 * (n + 1.0))
+    w = sla.eigh(A.toarray(), B.toarray(), eigvals_only=True)
+    Am, Bm = CP.mat_csr(A), CP.mat_csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 5, 20, SL.PETSC_DETERMINE)
+    eps.st_sinvert(sigma)
+    eps.solve()
+    assert eps.nconv >= 5
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(5)])
+    assert np.allclose(lam, w[:5], rtol=1e-9, atol=0)
+    assert max(eps.error(i) for i in range(5)) < 5e-8
+
+
+def test_eps_generalized_shift_largest():
+    """EPS_GHEP with the default ST (shift 0): Op = B^{-1} A, largest eigenvalues, B-inner product"""
+    import scipy.linalg as sla
+    A, B = _ex13(9, 7)
+    w = sla.eigh(A.toarray(), B.toarray(), eigvals_only=True)[::-1]
+    Am, Bm = CP.mat_csr(A), CP.mat_csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 3, 16, SL.PETSC_DETERMINE)
+    eps.solve()
+    assert eps.nconv >= 3
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(3)])
+    assert np.allclose(lam, w[:3], rtol=1e-9, atol=0)
+    assert max(eps.error(i) for i in range(3)) < 5e-8
+
+
+def test_bv_set_matrix_inner_product():
+    """BVSetMatrix (bvbasic.c:497): BVDotVec / BVDot / BVNormColumn / BVOrthogonalize* use <x,y> = y^T B x"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    n, k = 40, 5
+    B = sp.diags([np.full(n - 1, -1.0), np.full(n, 3.0), np.full(n - 1, -1.0)], [-1, 0, 1], format="csr")
+    Bm = CP.mat_csr(B)
+    X = make_bv(n, k)
+    Xh = rng.standard_normal((n, k))
+    X.from_numpy(Xh)
+    S.BVSetMatrix(X.h, Bm.h, 0)
+    nrm = c_dbl()
+    S.BVNormColumn(X.h, 2, SL.NORM_2, ctypes.byref(nrm))
+    assert np.isclose(nrm.value, np.sqrt(Xh[:, 2] @ (B @ Xh[:, 2])), rtol=1e-13)
+    M = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVDot(X.h, X.h, M.h)
+    assert np.allclose(M.dense_array(), Xh.T @ (B @ Xh), rtol=1e-12, atol=1e-12)
+    for otype in (SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_MGS):
+        X.from_numpy(Xh)
+        S.BVSetOrthogonalization(X.h, otype, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_GS)
+        lin = c_int()
+        for j in range(k):
+            S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
+        Q = X.to_numpy()
+        assert np.linalg.norm(Q.T @ (B @ Q) - np.eye(k)) < 1e-13
+    X.destroy()

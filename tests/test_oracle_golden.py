@@ -218,3 +218,22 @@ def test_hash_uniform_is_stable():
     w = O.hash_uniform(np.array([0, 1, 2, 12345678901], dtype=np.uint64), 42)
     assert w.tobytes() == O.hash_uniform(np.array([0, 1, 2, 12345678901], dtype=np.uint64), 42).tobytes()
     assert math.isfinite(float(w.sum()))
+
+
+def test_eps_ex13_generalized_sinvert_golden():
+    """src/eps/tutorials/ex13.c, output/ex13_1.out (-eps_nev 4 -eps_ncv 22 -eps_tol 1e-5 -st_type sinvert): A = 5-point Laplacian
+    on a 10x10 grid, B = 4 I, A x = k B x — generalized symmetric-definite problem with the B-inner product in the basis
+    (BVSetMatrix) and shift-and-invert at the target 0.  Golden: 0.04051, 0.09963, 0.09963, 0.15875."""
+    import scipy.sparse as sp
+    n = 10
+    A = O.laplacian_2d(n)
+    N = n * n
+    B = sp.identity(N, format="csr") * 4.0
+    r = O.eps_krylovschur(A, N, nev=4, ncv=22, tol=1e-5, B=B, sigma=0.0, sinvert=True)
+    assert r.reason > 0 and r.nconv >= 4
+    lam = r.eigr[r.perm]
+    assert fmt5(lam[:4]) == ["0.04051", "0.09963", "0.09963", "0.15875"]
+    for i in range(4):
+        x = r.X[:, r.perm[i]]
+        assert abs(x @ (B @ x) - 1.0) < 1e-12                                    # B-normalised (epsdefault.c:36)
+        assert np.linalg.norm(A @ x - lam[i] * (B @ x)) / (abs(lam[i]) * np.linalg.norm(x)) < 5e-5   # epssolve.c:742-815, -terse criterion

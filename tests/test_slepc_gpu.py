@@ -587,3 +587,52 @@ def test_c1_ex1_1d_laplacian_1e6_matches_cpu_reference_path():
     lam_max = 2 - 2 * np.cos(n * np.pi / (n + 1))
     assert all(v <= lam_max * (1 + 1e-12) for v in g["hist"][-1][2])          # Ritz values never exceed the top of the spectrum
     assert g["hist"][-1][2][0] > g["hist"][0][2][0] > 3.9                       # and climb towards it
+
+
+# ---- generalized symmetric-definite problems + shift-and-invert on the GPU ----------------------------------
+def test_eps_ex13_generalized_sinvert_golden_gpu():
+    """ex13 -eps_nev 4 -eps_ncv 22 -eps_tol 1e-5 -st_type sinvert with BV type b200 / Mat type b200csr: B-inner product through the
+    generic CGS pass (B x = k_spmv), linear solves = Jacobi-CG on device vectors.  Golden output/ex13_1.out and the oracle."""
+    import scipy.sparse as sp
+    n = 10
+    A = O.laplacian_2d(n)
+    B = sp.identity(n * n, format="csr") * 4.0
+    Am, Bm = SL.Mat.b200csr(A), SL.Mat.b200csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    S.EPSSetDimensions(eps.h, 4, 22, SL.PETSC_DETERMINE)
+    S.EPSSetTolerances(eps.h, 1e-5, SL.PETSC_CURRENT)
+    eps.st_sinvert(0.0)
+    eps.solve()
+    assert eps.reason > 0 and eps.nconv >= 4
+    lam = [eps.eigenvalue(i)[0] for i in range(eps.nconv)]
+    assert [f"{x:.5f}" for x in lam[:4]] == ["0.04051", "0.09963", "0.09963", "0.15875"]
+    ref = O.eps_krylovschur(A, n * n, nev=4, ncv=22, tol=1e-5, B=B, sigma=0.0, sinvert=True)
+    assert eps.nconv == ref.nconv
+    assert np.allclose(lam, ref.eigr[ref.perm], rtol=1e-9, atol=0)
+    assert max(eps.error(i) for i in range(4)) < 5e-5
+    for o in (eps, Am, Bm):
+        o.destroy()
+
+
+def test_eps_generalized_sinvert_large_vs_scipy_gpu():
+    """smallest eigenvalues of A x = k B x, A = 5-point Laplacian 200x200, B = tridiagonal mass-like matrix, by shift-and-invert at
+    0 on the GPU against scipy's ARPACK in shift-invert mode (different algorithm, direct solves): 1e-9 relative"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    g = 200
+    N = g * g
+    A = O.laplacian_2d(g).tocsr()
+    B = sp.diags([np.full(N - 1, 0.5), np.full(N, 3.0), np.full(N - 1, 0.5)], [-1, 0, 1], format="csr")
+    w = np.sort(spla.eigsh(A.tocsc(), k=6, M=B.tocsc(), sigma=0.0, which="LM", return_eigenvectors=False))
+    Am, Bm = SL.Mat.b200csr(A), SL.Mat.b200csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    S.EPSSetDimensions(eps.h, 6, 24, SL.PETSC_DETERMINE)
+    eps.st_sinvert(0.0)
+    eps.solve()
+    assert eps.nconv >= 6
+    lam = np.array([eps.eigenvalue(i)[0] for i in range(6)])
+    assert np.allclose(lam, w[:6], rtol=1e-9, atol=0), (lam, w)
+    assert max(eps.error(i) for i in range(6)) < 5e-8
+    assert eps.ksp_iterations() > 0
+    for o in (eps, Am, Bm):
+        o.destroy()
