@@ -171,7 +171,8 @@ int  b2k_csr_bytes(b2k_csr A, int64_t *bytes);
 #define B2K_SPMV_KERNEL_SELL            2   /* k_spmv_sell                            */
 #define B2K_SPMV_KERNEL_SELL_PIPE       3   /* k_spmv_sell_pipe<false> (no ghosts)    */
 #define B2K_SPMV_KERNEL_SELL_PIPE_GHOST 4   /* k_spmv_sell_pipe<true>  (halo columns) */
-#define B2K_SPMV_KERNEL_SPMM            5   /* k_spmm_sell (block of vectors)         */
+#define B2K_SPMV_KERNEL_SPMM            5   /* k_spmm_sell (block of vectors, small matrices)               */
+#define B2K_SPMV_KERNEL_SPMM_PIPE       6   /* k_spmv_sell_pipe<.,true> (block of vectors, matrix read once) */
 int  b2k_csr_last_kernel(b2k_csr A, int *which);
 /* the bulk-copy pipeline kernel runs when the SELL copy has at least this many chunks (default 4 per SM, i.e. about 6e5 rows;
    env B2K_SPMV_PIPE_MIN_CHUNKS); < 0 restores the default.  Tests lower it to push small matrices through the pipeline. */

@@ -52,6 +52,30 @@ __device__ __forceinline__ void gr_dmma(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+/* one 64-row tile for a warp that owns nb <= NBP blocks: RS = 8 / NBP row splits give every warp 8 independent DMMA chains
+   (accumulator u*RS + sp), so narrow results (few blocks per warp) are not bound by the latency of a single dependent chain —
+   measured before the split: 32 x 32 took as long as 64 x 64 (profiles/r02_kernels.md) */
+template <int NBP>
+__device__ __forceinline__ void gr_tile(const double *__restrict__ ap, const double *__restrict__ bp, int G, int nb, double (&c0)[8], double (&c1)[8])
+{
+  constexpr int RS = 8 / NBP, KS = (GR_ROWS / 4) / RS;
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+    for (int sp = 0; sp < RS; sp++) {
+      const int kk = ks + sp * KS;
+      const double a = ap[4 * kk];
+#pragma unroll
+      for (int u = 0; u < NBP; u++) {
+        if (u < nb) {                                            /* warp-uniform */
+          const double b = bp[(size_t)(8 * u * G) * GR_SROWS + 4 * kk];
+          gr_dmma(c0[u * RS + sp], c1[u * RS + sp], a, b);
+        }
+      }
+    }
+  }
+}
+
 /* SAME: X is Y (one box per stage).  The 8 warps own (block row r = warp % nbr) x (block columns g, g + G, …), G = 8 / nbr
    groups, nbr = ceil(ky/8) block rows: 8 blocks per warp at 64 x 64, fewer for narrower results. */
 template <bool SAME>
@@ -108,6 +132,7 @@ k_gram_tma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
   const int G = 8 / nbr;                                         /* column groups (nbr <= 8) */
   const bool active = warp < nbr * G;
   const int r = warp % nbr, g = warp / nbr;
+  const int nb = (active && g < nbc) ? (nbc - g + G - 1) / G : 0; /* my 8 x 8 blocks: columns g, g + G, … */
   const int fr = lane >> 2, fk = lane & 3;
   double c0[8], c1[8];
 #pragma unroll
@@ -116,38 +141,38 @@ k_gram_tma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
   uint32_t ph = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     gr_wait(gr_smem_u32(&full[s]), ph);
-    if (active) {
+    if (nb > 0) {
       const double *Ys = stages + (size_t)s * STAGE;
       const double *Xs = SAME ? Ys : Ys + BOX;
       const double *ap = Ys + (size_t)(8 * r + fr) * GR_SROWS + fk;
       const double *bp = Xs + (size_t)(8 * g + fr) * GR_SROWS + fk;
-#pragma unroll 4
-      for (int ks = 0; ks < GR_ROWS / 4; ks++) {
-        const double a = ap[4 * ks];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          if (g + u * G < nbc) {                                 /* warp-uniform */
-            const double b = bp[(size_t)(8 * u * G) * GR_SROWS + 4 * ks];
-            gr_dmma(c0[u], c1[u], a, b);
-          }
-        }
-      }
+      /* always 8 independent accumulator chains per warp: a warp with fewer than 8 blocks splits the 64 rows of the tile */
+      if (nb > 4) gr_tile<8>(ap, bp, G, nb, c0, c1);
+      else if (nb > 2) gr_tile<4>(ap, bp, G, nb, c0, c1);
+      else if (nb > 1) gr_tile<2>(ap, bp, G, nb, c0, c1);
+      else gr_tile<1>(ap, bp, G, nb, c0, c1);
     }
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gr_smem_u32(&empty[s])) : "memory");
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
-  /* the CTA's partial: M(8r + fr, 8c + 2fk + {0,1}), column-major ky x kx */
-  if (active) {
+  /* the CTA's partial: M(8r + fr, 8c + 2fk + {0,1}), column-major ky x kx; row splits summed in fixed order */
+  if (nb > 0) {
     double *P = part + (size_t)blockIdx.x * pstride;
     const int row = 8 * r + fr;
+    const int nbp = nb > 4 ? 8 : (nb > 2 ? 4 : (nb > 1 ? 2 : 1)), rs = 8 / nbp;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int cb = g + u * G;
-      if (cb < nbc && row < ky) {
-        const int col = 8 * cb + 2 * fk;
-        if (col < kx) P[(size_t)col * ky + row] = c0[u];
-        if (col + 1 < kx) P[(size_t)(col + 1) * ky + row] = c1[u];
+      if (u < nb) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (q >= u * rs && q < (u + 1) * rs) { a0 += c0[q]; a1 += c1[q]; }
+        const int col = 8 * (g + u * G) + 2 * fk;
+        if (row < ky) {
+          if (col < kx) P[(size_t)col * ky + row] = a0;
+          if (col + 1 < kx) P[(size_t)(col + 1) * ky + row] = a1;
+        }
       }
     }
   }

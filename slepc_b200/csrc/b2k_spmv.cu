@@ -178,13 +178,17 @@ __device__ __forceinline__ void sp_pair(const int *__restrict__ cp0, const doubl
   for (int u = 0; u < W; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
 }
 
-template <bool GHOST>
+/* MULTI: a block of kcols vectors (column-major, leading dimensions ldx / ldg / ldy): the matrix chunk staged in shared memory is
+   multiplied by every column before the stage is released, so the matrix is read from HBM ONCE for the whole block
+   (BVMatMult in BV_MATMULT_MAT mode, svec.c:203-231).  MULTI = false is the SpMV: kcols = 1 at compile time. */
+template <bool GHOST, bool MULTI>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__restrict__ sl_off, const int *__restrict__ col,
-                 const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int ncl,
-                 double *__restrict__ y, int64_t nrows, double sigma, int cap, int nstages)
+                 const double *__restrict__ val, const double *__restrict__ xb, const double *__restrict__ xgb, int ncl,
+                 double *__restrict__ yb, int64_t nrows, double sigma, int cap, int nstages, int kcols_, int64_t ldx, int64_t ldg, int64_t ldy)
 {
   b2k_pdl_enter();
+  const int kcols = MULTI ? kcols_ : 1;
   extern __shared__ __align__(128) unsigned char sp_raw[];
   const size_t stage_bytes = SP_STAGE_BYTES((size_t)cap);
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sp_raw);
@@ -253,46 +257,50 @@ k_spmv_sell_pipe(const int *__restrict__ chunk, int nchunks, const int64_t *__re
       const int o1 = two ? (int)(offs[j1] - base) : 0, width1 = two ? (int)((offs[j1 + 1] - offs[j1]) >> 5) : 0;
       const int *cp0 = scol + o0 + lane, *cp1 = scol + o1 + lane;
       const double *vp0 = sval + o0 + lane, *vp1 = sval + o1 + lane;
-      double acc0 = 0.0, acc1 = 0.0;
-      int wmax = max(width0, width1);
-      if (two && width0 == width1 && width0 <= 8) {       /* the common case: specialised on the width */
-        switch (width0) {
-          case 1: sp_pair<1, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 2: sp_pair<2, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 3: sp_pair<3, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 4: sp_pair<4, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 5: sp_pair<5, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 6: sp_pair<6, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 7: sp_pair<7, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          case 8: sp_pair<8, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
-          default: break;
+      for (int jc = 0; jc < kcols; jc++) {
+        const double *x = xb + (MULTI ? (int64_t)jc * ldx : 0), *xg = xgb + (MULTI ? (int64_t)jc * ldg : 0);
+        double *y = yb + (MULTI ? (int64_t)jc * ldy : 0);
+        double acc0 = 0.0, acc1 = 0.0;
+        int wmax = max(width0, width1);
+        if (two && width0 == width1 && width0 <= 8) {       /* the common case: specialised on the width */
+          switch (width0) {
+            case 1: sp_pair<1, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 2: sp_pair<2, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 3: sp_pair<3, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 4: sp_pair<4, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 5: sp_pair<5, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 6: sp_pair<6, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 7: sp_pair<7, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            case 8: sp_pair<8, GHOST>(cp0, vp0, cp1, vp1, x, xg, ncl, acc0, acc1); break;
+            default: break;
+          }
+          wmax = 0;
         }
-        wmax = 0;
+        for (int w = 0; w < wmax; w += SELL_CHUNK) {
+          int c0[SELL_CHUNK], c1[SELL_CHUNK];
+          double v0[SELL_CHUNK], v1[SELL_CHUNK], x0[SELL_CHUNK], x1[SELL_CHUNK];
+#pragma unroll
+          for (int u = 0; u < SELL_CHUNK; u++) {
+            const bool on0 = w + u < width0, on1 = w + u < width1;
+            c0[u] = on0 ? cp0[32 * (w + u)] : 0;
+            v0[u] = on0 ? vp0[32 * (w + u)] : 0.0;
+            c1[u] = on1 ? cp1[32 * (w + u)] : 0;
+            v1[u] = on1 ? vp1[32 * (w + u)] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < SELL_CHUNK; u++) {
+            const double *p0 = (c0[u] < ncl) ? x + c0[u] : xg + (c0[u] - ncl);
+            const double *p1 = (c1[u] < ncl) ? x + c1[u] : xg + (c1[u] - ncl);
+            x0[u] = __ldg(p0);
+            x1[u] = __ldg(p1);
+          }
+#pragma unroll
+          for (int u = 0; u < SELL_CHUNK; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
+        }
+        const int64_t r0 = (int64_t)(s0 + j) * 32 + lane, r1 = (int64_t)(s0 + j1) * 32 + lane;
+        if (r0 < nrows) { if (sigma != 0.0) acc0 -= sigma * x[r0]; y[r0] = acc0; }
+        if (two && r1 < nrows) { if (sigma != 0.0) acc1 -= sigma * x[r1]; y[r1] = acc1; }
       }
-      for (int w = 0; w < wmax; w += SELL_CHUNK) {
-        int c0[SELL_CHUNK], c1[SELL_CHUNK];
-        double v0[SELL_CHUNK], v1[SELL_CHUNK], x0[SELL_CHUNK], x1[SELL_CHUNK];
-#pragma unroll
-        for (int u = 0; u < SELL_CHUNK; u++) {
-          const bool on0 = w + u < width0, on1 = w + u < width1;
-          c0[u] = on0 ? cp0[32 * (w + u)] : 0;
-          v0[u] = on0 ? vp0[32 * (w + u)] : 0.0;
-          c1[u] = on1 ? cp1[32 * (w + u)] : 0;
-          v1[u] = on1 ? vp1[32 * (w + u)] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < SELL_CHUNK; u++) {
-          const double *p0 = (c0[u] < ncl) ? x + c0[u] : xg + (c0[u] - ncl);
-          const double *p1 = (c1[u] < ncl) ? x + c1[u] : xg + (c1[u] - ncl);
-          x0[u] = __ldg(p0);
-          x1[u] = __ldg(p1);
-        }
-#pragma unroll
-        for (int u = 0; u < SELL_CHUNK; u++) { acc0 = fma(v0[u], x0[u], acc0); acc1 = fma(v1[u], x1[u], acc1); }
-      }
-      const int64_t r0 = (int64_t)(s0 + j) * 32 + lane, r1 = (int64_t)(s0 + j1) * 32 + lane;
-      if (r0 < nrows) { if (sigma != 0.0) acc0 -= sigma * x[r0]; y[r0] = acc0; }
-      if (two && r1 < nrows) { if (sigma != 0.0) acc1 -= sigma * x[r1]; y[r1] = acc1; }
     }
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sp_smem_u32(&empty[s])) : "memory");
@@ -671,6 +679,35 @@ extern "C" int b2k_spmv_set_pipe_min_chunks(int min_chunks)
   return B2K_OK;
 }
 
+static int g_pipe_mode = -1;          /* env B2K_SPMV_PIPE: 1 (default) bulk-copy pipeline over the SELL copy, 0 plain SELL kernel */
+/* ring depth of the bulk-copy pipeline for this matrix, 0 = the pipeline does not take it (too few chunks, no SELL copy, switched off) */
+static int sp_pipe_stages(b2k_ctx ctx, b2k_csr A, size_t *shm)
+{
+  if (g_pipe_mode < 0) {
+    const char *e = getenv("B2K_SPMV_PIPE");
+    g_pipe_mode = (e && e[0] == '0') ? 0 : 1;
+    if (g_pipe_mode) {
+      cudaError_t ce = cudaFuncSetAttribute(k_spmv_sell_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_spmv_sell_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_spmv_sell_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_spmv_sell_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
+      if (ce != cudaSuccess) { cudaGetLastError(); g_pipe_mode = 0; }
+    }
+  }
+  if (g_pipe_min_chunks == -2) {
+    const char *e = getenv("B2K_SPMV_PIPE_MIN_CHUNKS");
+    g_pipe_min_chunks = e ? atoi(e) : -1;
+  }
+  const int min_chunks = g_pipe_min_chunks >= 0 ? (g_pipe_min_chunks > 0 ? g_pipe_min_chunks : 1) : 4 * ctx->sm_count;
+  int st = 0;
+  if (A->nslices > 0 && sell_mode() && g_pipe_mode && A->nchunks >= min_chunks) {
+    st = (int)(SP_SMEM_BUDGET / SP_STAGE_BYTES((size_t)A->sp_cap));
+    if (st > SP_STAGES) st = SP_STAGES;
+    *shm = 128 + (size_t)st * SP_STAGE_BYTES((size_t)A->sp_cap);
+  }
+  return st >= 2 ? st : 0;
+}
+
 extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const double *xghost, double *y, double sigma)
 {
   if (A->nrows == 0) return B2K_OK;
@@ -679,37 +716,18 @@ extern "C" int b2k_csr_spmv_shift(b2k_ctx ctx, b2k_csr A, const double *x, const
   /* algorithmic bytes of the CSR product whichever storage runs: the SELL copy moves 12 B per stored
      entry (padding included) and no row pointers */
   PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 4.0 * (double)(A->nrows + 1) + 8.0 * (double)(A->ncols_local + A->nghost) + 8.0 * (double)A->nrows);
-  static int pipe_mode = -1;          /* env B2K_SPMV_PIPE: 1 (default) bulk-copy pipeline over the SELL copy, 0 plain SELL kernel */
-  if (pipe_mode < 0) {
-    const char *e = getenv("B2K_SPMV_PIPE");
-    pipe_mode = (e && e[0] == '0') ? 0 : 1;
-    if (pipe_mode) {
-      cudaError_t ce = cudaFuncSetAttribute(k_spmv_sell_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
-      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_spmv_sell_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + SP_SMEM_BUDGET);
-      if (ce != cudaSuccess) { cudaGetLastError(); pipe_mode = 0; }
-    }
-  }
-  if (g_pipe_min_chunks == -2) {
-    const char *e = getenv("B2K_SPMV_PIPE_MIN_CHUNKS");
-    g_pipe_min_chunks = e ? atoi(e) : -1;
-  }
-  const int min_chunks = g_pipe_min_chunks >= 0 ? (g_pipe_min_chunks > 0 ? g_pipe_min_chunks : 1) : 4 * ctx->sm_count;
-  int sp_stages = 0;
   size_t sp_shm = 0;
-  if (A->nslices > 0 && sell_mode() && pipe_mode && A->nchunks >= min_chunks) {
-    sp_stages = (int)(SP_SMEM_BUDGET / SP_STAGE_BYTES((size_t)A->sp_cap));
-    if (sp_stages > SP_STAGES) sp_stages = SP_STAGES;
-    sp_shm = 128 + (size_t)sp_stages * SP_STAGE_BYTES((size_t)A->sp_cap);
-  }
+  const int sp_stages = sp_pipe_stages(ctx, A, &sp_shm);
   A->last_kernel = (sp_stages >= 2) ? (A->nghost > 0 ? B2K_SPMV_KERNEL_SELL_PIPE_GHOST : B2K_SPMV_KERNEL_SELL_PIPE)
                                      : ((A->nslices > 0 && sell_mode()) ? B2K_SPMV_KERNEL_SELL : B2K_SPMV_KERNEL_CSR_STREAM);
   if (sp_stages >= 2 && A->nghost > 0)
-    b2k_launch_pdl(k_spmv_sell_pipe<true>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
+    b2k_launch_pdl(k_spmv_sell_pipe<true, false>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
                    A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, sigma,
-                   A->sp_cap, sp_stages);
+                   A->sp_cap, sp_stages, 1, (int64_t)0, (int64_t)0, (int64_t)0);
   else if (sp_stages >= 2)
-    b2k_launch_pdl(k_spmv_sell_pipe<false>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
-                   A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, x, (int)A->ncols_local, y, A->nrows, sigma, A->sp_cap, sp_stages);
+    b2k_launch_pdl(k_spmv_sell_pipe<false, false>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream,
+                   A->sp_chunk, A->nchunks, A->sl_off, A->sl_col, A->sl_val, x, x, (int)A->ncols_local, y, A->nrows, sigma, A->sp_cap, sp_stages,
+                   1, (int64_t)0, (int64_t)0, (int64_t)0);
   else if (A->nslices > 0 && sell_mode())
     b2k_launch_pdl(k_spmv_sell, dim3((unsigned)std::min<int64_t>((A->nslices + 15) / 16, (int64_t)ctx->sm_count * 8)), dim3(256), 0, ctx->stream,
                    A->sl_off, A->sl_col, A->sl_val, x, xghost ? xghost : x, (int)A->ncols_local, y, A->nrows, A->nslices, sigma);
@@ -786,6 +804,24 @@ extern "C" int b2k_csr_spmm(b2k_ctx ctx, b2k_csr A, const double *X, int64_t ldx
     }
     return B2K_OK;
   }
+  size_t sp_shm = 0;
+  const int sp_stages = sp_pipe_stages(ctx, A, &sp_shm);
+  if (sp_stages) {
+    /* large matrices: the bulk-copy pipeline with the column loop inside the consumers — the matrix streams through shared
+       memory once for the whole block */
+    PROF_BEGIN(ctx, B2K_PROF_SPMV, 12.0 * (double)A->nnz + 8.0 * (double)(A->ncols_local + A->nghost) * k + 8.0 * (double)A->nrows * k);
+    if (A->nghost > 0)
+      b2k_launch_pdl(k_spmv_sell_pipe<true, true>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream, A->sp_chunk, A->nchunks, A->sl_off,
+                     A->sl_col, A->sl_val, X, XG, (int)A->ncols_local, Y, A->nrows, 0.0, A->sp_cap, sp_stages, k, ldx, ldg, ldy);
+    else
+      b2k_launch_pdl(k_spmv_sell_pipe<false, true>, dim3(ctx->sm_count), dim3(SP_THREADS), sp_shm, ctx->stream, A->sp_chunk, A->nchunks, A->sl_off,
+                     A->sl_col, A->sl_val, X, X, (int)A->ncols_local, Y, A->nrows, 0.0, A->sp_cap, sp_stages, k, ldx, (int64_t)0, ldy);
+    PROF_END(ctx);
+    CKLAUNCH(ctx);
+    A->last_kernel = B2K_SPMV_KERNEL_SPMM_PIPE;
+    return B2K_OK;
+  }
+  /* small matrices: one launch per 16 columns instead of one per column */
   const unsigned grid = (unsigned)std::min<int64_t>((A->nslices + 7) / 8, (int64_t)ctx->sm_count * 8);
   const int KT = (k > 8) ? 16 : 8;
   const int passes = (k + KT - 1) / KT;

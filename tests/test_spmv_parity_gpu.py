@@ -316,12 +316,43 @@ def test_spmm_block_of_vectors(ctx, kind, k):
     dY = ctx.to_device(np.full((ldy, k), 7.0, order="F"))
     _check(ctx.lib.b2k_csr_spmm(ctx.h, h, dX.ptr, ldx, dG.ptr if ng else None, ldg, dY.ptr, ldy, k))
     ctx.sync()
-    assert _last_kernel(ctx, h) == 5
+    assert _last_kernel(ctx, h) == 5                                          # small matrix: k_spmm_sell
     Y = dY.to_host((ldy, k))
     ref = A @ np.vstack([X[:ncl], G[:ng]])
     tol = 1e-13 * max(int(np.diff(A.indptr).max()), 1) * max(np.abs(A.data).max(), 1.0) * 6
     assert np.abs(Y[:n] - ref).max() <= tol
     assert np.array_equal(Y[n:], np.full((ldy - n, k), 7.0))                 # rows past n untouched
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    for d in (dX, dG, dY):
+        d.free()
+
+
+@pytest.mark.parametrize("ghost", [False, True], ids=["owned_columns", "ghost_columns"])
+@pytest.mark.parametrize("k", [3, 16])
+def test_spmm_through_the_pipeline_1m_rows(ctx, k, ghost):
+    """large matrices: b2k_csr_spmm runs the bulk-copy pipeline with the column loop inside the consumers (k_spmv_sell_pipe<.,true>):
+    the matrix is read once for the k vectors; element-wise against scipy on the 1 M-row random matrix"""
+    import scipy.sparse as sp
+    from slepc_b200 import matgen
+    M, N = 1 << 20, 900001
+    rp, ci, va = matgen.random_sparse_rows(M, N, 20, seed=5)
+    A = sp.csr_matrix((va, ci, rp), shape=(M, N))
+    rng = np.random.default_rng(9)
+    ncl = 600000 if ghost else N
+    ng = N - ncl
+    ldx, ldg, ldy = ncl + 2, ng + 2, M + 4
+    X = np.zeros((ldx, k), order="F"); X[:ncl] = rng.uniform(-1, 1, (ncl, k))
+    G = np.zeros((ldg, k), order="F"); G[:ng] = rng.uniform(-1, 1, (ng, k))
+    h = ctypes.c_void_p()
+    rp32, ci32 = np.ascontiguousarray(rp, dtype=np.int32), np.ascontiguousarray(ci, dtype=np.int32)
+    _check(ctx.lib.b2k_csr_create(ctx.h, M, ncl, ng, rp32.ctypes.data, ci32.ctypes.data, va.ctypes.data, ctypes.byref(h)))
+    dX, dG, dY = ctx.to_device(X), ctx.to_device(G), ctx.empty(ldy * k)
+    _check(ctx.lib.b2k_csr_spmm(ctx.h, h, dX.ptr, ldx, dG.ptr if ng else None, ldg, dY.ptr, ldy, k))
+    ctx.sync()
+    assert _last_kernel(ctx, h) == 6
+    Y = dY.to_host((ldy, k))
+    ref = A @ np.vstack([X[:ncl], G[:ng]])
+    assert np.abs(Y[:M] - ref).max() <= 1e-13 * int(np.diff(rp).max()) * np.abs(va).max()
     _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
     for d in (dX, dG, dY):
         d.free()
