@@ -145,6 +145,19 @@ int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
    3 (default) 2-D tensor-map (TMA) pipelined single sweep, register tile for k <= 4 or fewer than 4096 rows       */
 int  b2k_gs_set_fused(int mode);
 
+/* ---- tall-skinny QR (BVOrthogonalize with BV_ORTHOG_BLOCK_TSQR / TSQRCHOL, bvorthog.c:611-656, bvlapack.c:347-560) ---- */
+#define B2K_TSQR_MAX_K 64
+/* the row blocking of the two kernels: nblk blocks of rows_per_blk rows (a multiple of 128; the last one shorter);
+   coef_elems = doubles of reflector scalars the forward kernel writes when it stores the reflectors                     */
+int  b2k_tsqr_plan(b2k_ctx ctx, int64_t n, int k, int *nblk, int64_t *rows_per_blk, int64_t *coef_elems);
+/* Householder QR of every row block of V(:,0:k): Rblk_dev[b] = its k x k upper-triangular factor (column-major, ld k).
+   store != 0: the reflectors overwrite V and coef_dev receives their scalars (then b2k_tsqr_backward forms Q);
+   store == 0: V is left untouched (only R is wanted: TSQRCHOL, BVOrthogonalize_LAPACK_TSQR_OnlyR bvlapack.c:520-560)    */
+int  b2k_tsqr_forward(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, int store, double *Rblk_dev, double *coef_dev);
+/* rows of block b <- Q_b * Wblk_dev[b] (k x k, column-major, ld k): with W = the blocks of the orthogonal factor of the stacked
+   triangles this is the explicit Q of the whole basis (orgqr + the tree accumulation of bvlapack.c:386-462)            */
+int  b2k_tsqr_backward(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, const double *Wblk_dev, const double *coef_dev);
+
 /* ---- sparse matrix-vector product (replaces PETSc MatMult behind bvops.c:879 / stsolve.c:22) -- */
 /* CSR with int32 indices.  Column indices < ncols_local address x, the rest address
    xghost[col-ncols_local] (halo entries received from the neighbouring GPUs).                     */
@@ -160,6 +173,11 @@ int  b2k_csr_info(b2k_csr A, int64_t *nrows, int64_t *ncols_local, int64_t *ngho
    rebuilds them from the SELL copy on A's stream, b2k_csr_release_arrays drops them again.  env B2K_CSR_KEEP=1 keeps both. */
 int  b2k_csr_arrays(b2k_csr A, int **rowptr, int **colidx, double **val);
 int  b2k_csr_release_arrays(b2k_csr A);
+/* local transpose built in HBM (set-up): ATown = (ncols_local x nrows) rows of A^T that this GPU owns, ATghost = (nghost x nrows)
+   rows that belong to the ghost columns (NULL when A has none; pass ATghost = NULL then).  Entries of a transposed row keep the
+   ascending row order of A, so y = A^T x sums in a fixed order.  Replaces MatMultTranspose_MPIAIJ's scatter (reached from
+   gklanczos.c:80,103 with the implicit transpose of svdsetup.c:273-279) and MatTranspose for the explicit one (svdsetup.c:300-306) */
+int  b2k_csr_transpose_split(b2k_ctx ctx, b2k_csr A, b2k_csr *ATown, b2k_csr *ATghost);
 /* diag[r] = A(r, r + diag_col_offset) of the local rows, 0 where not stored (MatGetDiagonal; offset = position of the diagonal
    block in the local column numbering, 0 for a square matrix whose owned columns are its owned rows)          */
 int  b2k_csr_get_diagonal(b2k_ctx ctx, b2k_csr A, int64_t diag_col_offset, double *diag);

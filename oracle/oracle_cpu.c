@@ -21,7 +21,7 @@
 void LAPACK(dgemm)(const char *, const char *, const int *, const int *, const int *, const double *, const double *, const int *,
                    const double *, const int *, const double *, double *, const int *, size_t, size_t);
 
-typedef struct { double *V; } BV_CPU;
+typedef struct { double *V; double *ts_fact; PetscInt ts_nk, ts_rows; } BV_CPU;   /* ts_*: LAPACK-factored copy kept between tsqr_factor and tsqr_formq */
 #define COL(bv, d, j) ((d)->V + (size_t)((bv)->nc + (j)) * (size_t)(bv)->ld)
 
 /* ---- host Vec arithmetic registered with libb2kslepc (B2KVecRegisterHostOps, sys.c) ---------------- */
@@ -334,10 +334,48 @@ static PetscErrorCode BVSetRandomColumn_CPU(BV bv, PetscInt j)
   for (PetscInt i = 0; i < bv->n; i++) x[i] = B2KHashUniform((uint64_t)(bv->row0 + i), bv->rng_seed + (uint64_t)j);
   return PETSC_SUCCESS;
 }
+/* local Householder QR of the active columns with LAPACK, as BVOrthogonalize_LAPACK_TSQR does on the raw array (bvlapack.c:378-396):
+   geqrf -> R; with wantq the factored copy is kept and tsqr_formq applies it to [W ; 0] (ormqr) */
+static PetscErrorCode BVTSQRFactor_CPU(BV bv, PetscBool wantq, PetscScalar *R)
+{
+  BV_CPU *d = (BV_CPU *)bv->data;
+  const PetscInt nk = bv->k - bv->l, rows = bv->n > nk ? bv->n : nk;      /* padded with zero rows when this rank has fewer rows than columns */
+  free(d->ts_fact); d->ts_fact = NULL;
+  if (nk <= 0) return PETSC_SUCCESS;
+  int rows_ = rows, nk_ = nk, lwork = 64 * (int)nk + 64, info = 0;
+  double *F = (double *)calloc((size_t)rows * (size_t)nk + (size_t)nk + (size_t)lwork, sizeof(double));
+  PetscCheck(F, PETSC_ERR_MEM, "out of memory");
+  for (PetscInt c = 0; c < nk; c++) memcpy(F + (size_t)c * rows, COL(bv, d, bv->l + c), sizeof(double) * (size_t)bv->n);
+  LAPACK(dgeqrf)(&rows_, &nk_, F, &rows_, F + (size_t)rows * nk, F + (size_t)rows * nk + nk, &lwork, &info);
+  if (info) { free(F); SETERRQ(PETSC_ERR_LIB, "Error in LAPACK subroutine geqrf: info=%d", info); }
+  for (PetscInt c = 0; c < nk; c++) for (PetscInt i = 0; i < nk; i++) R[i + (size_t)c * nk] = (i <= c) ? F[i + (size_t)c * rows] : 0.0;
+  if (wantq) { d->ts_fact = F; d->ts_nk = nk; d->ts_rows = rows; }
+  else free(F);
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode BVTSQRFormQ_CPU(BV bv, const PetscScalar *W)
+{
+  BV_CPU *d = (BV_CPU *)bv->data;
+  const PetscInt nk = bv->k - bv->l;
+  if (nk <= 0) return PETSC_SUCCESS;
+  PetscCheck(d->ts_fact && d->ts_nk == nk, PETSC_ERR_ORDER, "tsqr_formq without a matching tsqr_factor(wantq)");
+  const PetscInt rows = d->ts_rows;
+  int rows_ = rows, nk_ = nk, lwork = 64 * (int)nk + 64, info = 0;
+  double *C = (double *)calloc((size_t)rows * (size_t)nk + (size_t)lwork, sizeof(double));
+  PetscCheck(C, PETSC_ERR_MEM, "out of memory");
+  for (PetscInt c = 0; c < nk; c++) memcpy(C + (size_t)c * rows, W + (size_t)c * nk, sizeof(double) * (size_t)nk);
+  LAPACK(dormqr)("L", "N", &rows_, &nk_, &nk_, d->ts_fact, &rows_, d->ts_fact + (size_t)rows * nk, C, &rows_, C + (size_t)rows * nk, &lwork, &info, 1, 1);
+  if (!info) for (PetscInt c = 0; c < nk; c++) memcpy(COL(bv, d, bv->l + c), C + (size_t)c * rows, sizeof(double) * (size_t)bv->n);
+  free(C);
+  free(d->ts_fact); d->ts_fact = NULL;
+  PetscCheck(!info, PETSC_ERR_LIB, "Error in LAPACK subroutine ormqr: info=%d", info);
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode BVDestroy_CPU(BV bv)
 {
   BV_CPU *d = (BV_CPU *)bv->data;
-  if (d) { free(d->V); free(d); }
+  if (d) { free(d->ts_fact); free(d->V); free(d); }
   bv->data = NULL;
   return PETSC_SUCCESS;
 }
@@ -370,6 +408,8 @@ PetscErrorCode BVCreate_OracleCPU(BV bv)
   bv->ops.getarray = BVGetArray_CPU;
   bv->ops.destroy = BVDestroy_CPU;
   bv->ops.setrandomcolumn = BVSetRandomColumn_CPU;
+  bv->ops.tsqr_factor = BVTSQRFactor_CPU;
+  bv->ops.tsqr_formq = BVTSQRFormQ_CPU;
   return PETSC_SUCCESS;
 }
 

@@ -325,8 +325,23 @@ class BV:
             R12 = V1.T @ self.V[:, l:k]
             Rbuf[0:l, l:k] = R12
             self.V[:, l:k] -= V1 @ R12
-        G = self.V[:, l:k].T @ self.V[:, l:k]                   # BVDot(V,V,R)
         n = k - l
+        if method in ("tsqr", "tsqrchol"):                      # bvorthog.c:611-656: Householder QR (LAPACK geqrf, bvlapack.c:378-396)
+            Qh, Rh = np.linalg.qr(self.V[:, l:k])               # R normalised to a non-negative diagonal (unique factor)
+            sg = np.where(np.diag(Rh) < 0, -1.0, 1.0)
+            Rh = Rh * sg[:, None]
+            Rbuf[l:k, l:k] = np.triu(Rh)
+            if method == "tsqr":
+                self.V[:, l:k] = Qh * sg[None, :]               # orgqr
+            else:
+                self.V[:, l:k] = self.V[:, l:k] @ np.triu(sla.solve_triangular(Rh, np.eye(n), lower=False))   # BVMatTriInv + BVMultInPlace
+            if want_R:
+                R = np.zeros((k, k), order="F")
+                for j in range(l, k):
+                    R[0:j + 1, j] = Rbuf[0:j + 1, j]
+                return R
+            return None
+        G = self.V[:, l:k].T @ self.V[:, l:k]                   # BVDot(V,V,R)
         if method == "chol":
             try:
                 C = sla.cholesky(G, lower=False)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "b2k_csr_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
     "b2k_csr_arrays": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)],
     "b2k_csr_release_arrays": [c_vp],
+    "b2k_csr_transpose_split": [c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)],
     "b2k_csr_bytes": [c_vp, ctypes.POINTER(c_i64)],
     "b2k_csr_last_kernel": [c_vp, ctypes.POINTER(c_int)],
     "b2k_spmv_set_pipe_min_chunks": [c_int],
@@ -81,6 +82,9 @@ SIGNATURES = {
     "b2k_csr_spmv_shift": [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl],
     "b2k_csr_laplacian": [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),
                           ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "b2k_tsqr_plan": [c_vp, c_i64, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
+    "b2k_tsqr_forward": [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp],
+    "b2k_tsqr_backward": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     "b2k_gather": [c_vp, c_vp, c_vp, c_vp, c_i64],
     "b2k_scatter_add": [c_vp, c_vp, c_vp, c_vp, c_i64],
     "b2k_comm_unique_id": [c_vp],

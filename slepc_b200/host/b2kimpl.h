@@ -34,6 +34,10 @@ static inline PetscReal SlepcAbsEigenvalue(PetscScalar re, PetscScalar im) { ret
 
 /* ---- host BLAS/LAPACK (scipy-bundled OpenBLAS, LP64, `scipy_` prefix) ------------------------------ */
 #define LAPACK(name) scipy_##name##_
+void LAPACK(dgeqrf)(const int *, const int *, double *, const int *, double *, double *, const int *, int *);
+void LAPACK(dorgqr)(const int *, const int *, const int *, double *, const int *, const double *, double *, const int *, int *);
+void LAPACK(dormqr)(const char *, const char *, const int *, const int *, const int *, const double *, const int *, const double *, double *,
+                    const int *, double *, const int *, int *, size_t, size_t);
 void LAPACK(dsteqr)(const char *, const int *, double *, double *, double *, const int *, double *, int *, size_t);
 void LAPACK(dlartg)(const double *, const double *, double *, double *, double *);
 void LAPACK(drot)(const int *, double *, const int *, double *, const int *, const double *, const double *);
@@ -136,6 +140,11 @@ typedef struct _BVOps {
   /* extensions of this build (NULL is always allowed) */
   PetscErrorCode (*setrandomcolumn)(BV, PetscInt);        /* deterministic hash fill          */
   PetscErrorCode (*duplicate)(BV, BV);                    /* bvimpl.h:56                      */
+  /* Householder QR of the LOCAL rows of the active columns l..k-1 (what BVOrthogonalize_LAPACK_TSQR / _TSQR_OnlyR do on the raw
+     array, bvlapack.c:347-560): tsqr_factor returns the (k-l) x (k-l) upper-triangular factor of this rank's rows in R (column-major,
+     leading dimension k-l); with wantq the type keeps what it needs so that tsqr_formq(W) overwrites the columns with Q_local * W */
+  PetscErrorCode (*tsqr_factor)(BV, PetscBool wantq, PetscScalar *R);
+  PetscErrorCode (*tsqr_formq)(BV, const PetscScalar *W);
 } BVOps;
 
 struct _p_BV {

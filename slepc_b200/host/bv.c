@@ -993,7 +993,7 @@ PetscErrorCode BVView(BV bv, PetscViewer viewer)
 /* ---- block orthogonalisation: bvorthog.c:488-765, bvlapack.c:136-345 ------------------------------------------
    CHOL and SVQB are two BLAS-3 sweeps of the basis (BVDot = V^T V, BVMultInPlace = V S) around a k x k host
    factorisation, i.e. the level-3 kernels of the restart; TSQR/TSQRCHOL (host Householder panels over a raw
-   BVGetArray pointer, bvlapack.c:347-560) have no device counterpart in this build. */
+   BVGetArray pointer in the reference, bvlapack.c:347-560) go through the type's tsqr_factor / tsqr_formq. */
 
 /* the buffer seen as an (nc+m) x m dense matrix, BV_GetBufferMat bvorthog.c:545-559 */
 static PetscErrorCode BV_GetBufferMat(BV bv, Mat *R)
@@ -1110,6 +1110,108 @@ static PetscErrorCode BVOrthogonalize_Gram(BV V, Mat Rin, PetscBool svqb)
   return PETSC_SUCCESS;
 }
 
+/* every rank's block of `count` doubles, in rank order, on every rank (the communicators of this build reduce: a zero-padded sum) */
+static PetscErrorCode BVAllgatherHost_Private(BV bv, const double *mine, PetscInt count, double *all)
+{
+  int rank = 0, size = 1;
+  PetscCall(B2KCommGetRank(bv->comm, &rank, &size));
+  memset(all, 0, sizeof(double) * (size_t)count * (size_t)size);
+  memcpy(all + (size_t)rank * (size_t)count, mine, sizeof(double) * (size_t)count);
+  if (size == 1) return PETSC_SUCCESS;
+  if (bv->comm->kind == 2) return B2KCommAllreduce(bv->comm, all, (int)(count * size), 0, B2K_MEM_HOST);
+  b2k_ctx ctx = B2KGetContext();                 /* NCCL communicator: device buffers */
+  double *d = NULL;
+  const size_t bytes = sizeof(double) * (size_t)count * (size_t)size;
+  B2KCall(b2k_malloc(ctx, (void **)&d, bytes));
+  B2KCall(b2k_h2d(ctx, d, all, bytes));
+  PetscErrorCode ierr = B2KCommAllreduce(bv->comm, d, (int)(count * size), 0, B2K_MEM_DEVICE);
+  if (!ierr) B2KCall(b2k_d2h(ctx, all, d, bytes));
+  B2KCall(b2k_free(ctx, d));
+  return ierr;
+}
+
+/* BVMatTriInv_LAPACK_Private bvlapack.c:208-250: S(l:k,l:k) = inv(R(l:k,l:k)), R upper triangular; S == R inverts in place */
+static PetscErrorCode BVMatTriInv_Private(BV bv, Mat R, Mat S)
+{
+  const PetscInt l = bv->l, k = bv->k, n = k - l, ld = R->lda;
+  int n_ = n, ld_ = ld, info = 0;
+  PetscScalar *pR = R->dense;
+  if (S == R) LAPACK(dtrtri)("U", "N", &n_, pR + (size_t)l * ld + l, &ld_, &info, 1, 1);
+  else {
+    PetscScalar *pS = S->dense;
+    const PetscInt lds = S->lda;
+    int lds_ = lds;
+    memset(pS + (size_t)l * lds, 0, sizeof(PetscScalar) * (size_t)(k - l) * (size_t)lds);
+    for (PetscInt i = l; i < k; i++) memcpy(pS + (size_t)i * lds + l, pR + (size_t)i * ld + l, sizeof(PetscScalar) * (size_t)n);
+    LAPACK(dtrtri)("U", "N", &n_, pS + (size_t)l * lds + l, &lds_, &info, 1, 1);
+  }
+  PetscCheck(!info, PETSC_ERR_LIB, "Error in LAPACK subroutine trtri: info=%d", info);
+  return PETSC_SUCCESS;
+}
+
+/* BVOrthogonalize_TSQR bvorthog.c:611-631 (onlyr = PETSC_FALSE: Q formed from the reflectors) and BVOrthogonalize_TSQRCHOL :636-656
+   (onlyr = PETSC_TRUE: only R from the Householder tree, then Q = V inv(R) with BVMultInPlace).  The local factorisation is the
+   type's (ops.tsqr_factor / ops.tsqr_formq: device kernels for BV type b200, LAPACK for a host type); the level over the ranks —
+   the binary tree of bvlapack.c:386-462 and the packed-Givens reduction of :474-560 in the reference — is ONE QR of the gathered
+   k x k triangles here (at most 8 of them), done redundantly by every rank, so all ranks hold the same R. */
+static PetscErrorCode BVOrthogonalize_TSQR(BV V, Mat Rin, PetscBool onlyr)
+{
+  Mat R, S;
+  const PetscInt l = V->l, k = V->k, n = k - l;
+  int rank = 0, size = 1;
+  PetscCheck(V->ops.tsqr_factor && (onlyr || V->ops.tsqr_formq), PETSC_ERR_SUP, "BV type %s has no TSQR block orthogonalization; use chol or svqb", V->type_name);
+  PetscCall(B2KCommGetRank(V->comm, &rank, &size));
+  PetscCall(BV_GetBufferMat(V, &R));
+  S = Rin ? Rin : R;
+  double *Rl = (double *)calloc((size_t)n * (size_t)n + 1, sizeof(double)), *W = (double *)calloc((size_t)n * (size_t)n + 1, sizeof(double));
+  double *all = NULL, *stack = NULL;
+  PetscErrorCode ierr = (Rl && W) ? PETSC_SUCCESS : PETSC_ERR_MEM;
+  if (!ierr && V->l) ierr = BVOrthogonalize_BlockGS(V, R);
+  if (!ierr) ierr = V->ops.tsqr_factor(V, onlyr ? PETSC_FALSE : PETSC_TRUE, Rl);
+  for (PetscInt i = 0; i < n; i++) W[i + (size_t)i * n] = 1.0;
+  if (!ierr && size > 1 && n > 0) {
+    const PetscInt rows = (PetscInt)size * n;
+    int rows_ = rows, n_ = n, lwork = 64 * (int)n + 64, info = 0;
+    all = (double *)malloc(sizeof(double) * (size_t)rows * (size_t)n);
+    stack = (double *)malloc(sizeof(double) * ((size_t)rows * (size_t)n + (size_t)n + (size_t)lwork));
+    if (!all || !stack) ierr = PETSC_ERR_MEM;
+    if (!ierr) ierr = BVAllgatherHost_Private(V, Rl, n * n, all);
+    if (!ierr) {
+      double *tau = stack + (size_t)rows * n, *work = tau + n;
+      for (int r = 0; r < size; r++)
+        for (PetscInt c = 0; c < n; c++) memcpy(stack + (size_t)r * n + (size_t)c * rows, all + (size_t)r * n * n + (size_t)c * n, sizeof(double) * (size_t)n);
+      LAPACK(dgeqrf)(&rows_, &n_, stack, &rows_, tau, work, &lwork, &info);
+      if (!info) {
+        for (PetscInt c = 0; c < n; c++) for (PetscInt i = 0; i < n; i++) Rl[i + (size_t)c * n] = (i <= c) ? stack[i + (size_t)c * rows] : 0.0;
+        if (!onlyr) {
+          LAPACK(dorgqr)(&rows_, &n_, &n_, stack, &rows_, tau, work, &lwork, &info);
+          for (PetscInt c = 0; c < n; c++) memcpy(W + (size_t)c * n, stack + (size_t)rank * n + (size_t)c * rows, sizeof(double) * (size_t)n);
+        }
+      }
+      if (info) ierr = PETSC_ERR_LIB;
+    }
+  }
+  if (!ierr) {
+    for (PetscInt i = 0; i < n; i++) {            /* R with a non-negative diagonal (the unique factor; LAPACK's sign is arbitrary) */
+      if (Rl[i + (size_t)i * n] < 0.0) {
+        for (PetscInt c = i; c < n; c++) Rl[i + (size_t)c * n] = -Rl[i + (size_t)c * n];
+        for (PetscInt r = 0; r < n; r++) W[r + (size_t)i * n] = -W[r + (size_t)i * n];
+      }
+    }
+    const PetscInt ldr = R->lda;
+    for (PetscInt c = 0; c < n; c++) for (PetscInt i = 0; i < n; i++) R->dense[(l + i) + (size_t)(l + c) * ldr] = Rl[i + (size_t)c * n];
+    if (onlyr) {
+      ierr = BVMatTriInv_Private(V, R, S);
+      if (!ierr) ierr = BVMultInPlace(V, S, V->l, V->k);
+    } else ierr = V->ops.tsqr_formq(V, W);
+  }
+  if (!ierr && Rin) ierr = BV_StoreCoeffsBlock(V, Rin, PETSC_TRUE);
+  free(Rl); free(W); free(all); free(stack);
+  PetscCall(MatDestroy(&R));
+  PetscCall(ierr);
+  return PETSC_SUCCESS;
+}
+
 /* BVOrthogonalize_GS bvorthog.c:504-540: column by column */
 static PetscErrorCode BVOrthogonalize_GS(BV V, Mat R)
 {
@@ -1147,9 +1249,8 @@ PetscErrorCode BVOrthogonalize(BV V, Mat R)
   case BV_ORTHOG_BLOCK_GS: PetscCall(BVOrthogonalize_GS(V, R)); break;
   case BV_ORTHOG_BLOCK_CHOL: PetscCall(BVOrthogonalize_Gram(V, R, PETSC_FALSE)); break;
   case BV_ORTHOG_BLOCK_SVQB: PetscCall(BVOrthogonalize_Gram(V, R, PETSC_TRUE)); break;
-  case BV_ORTHOG_BLOCK_TSQR:
-  case BV_ORTHOG_BLOCK_TSQRCHOL:
-    SETERRQ(PETSC_ERR_SUP, "TSQR block orthogonalization (bvlapack.c:347-560: host Householder panels) is not available for device-resident BVs; use chol or svqb");
+  case BV_ORTHOG_BLOCK_TSQR: PetscCall(BVOrthogonalize_TSQR(V, R, PETSC_FALSE)); break;
+  case BV_ORTHOG_BLOCK_TSQRCHOL: PetscCall(BVOrthogonalize_TSQR(V, R, PETSC_TRUE)); break;
   }
   V->state++;
   return PETSC_SUCCESS;

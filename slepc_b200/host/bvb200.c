@@ -39,6 +39,10 @@ typedef struct {
   PetscBool pend2_valid; /* the second pass was issued with the first                              */
   PetscBool pend2_ran;   /* ... and the criterion let it run                                       */
   PetscReal pend2_nrm2;  /* ||w||^2 after it                                                       */
+  /* TSQR between tsqr_factor(wantq) and tsqr_formq: reflector scalars in HBM, the factored stack of the CTAs' triangles on the host */
+  double   *ts_coef;     /* device */
+  double   *ts_stack;    /* host: (nblk*nk) x nk factored by dgeqrf, then nk tau                    */
+  PetscInt  ts_nk, ts_nblk;
 } BV_B200;
 
 #define CTX() B2KGetContext()
@@ -528,10 +532,88 @@ static PetscErrorCode BVSetRandomColumn_B200(BV bv, PetscInt j)
   return PETSC_SUCCESS;
 }
 
+/* ---- tall-skinny QR of the local rows of the active columns (BVOrthogonalize TSQR / TSQRCHOL; b2k_tsqr.cu) --------------------
+   level 1 on the device (flat Householder tree over 128-row tiles inside every CTA), level 2 = one LAPACK QR of the CTAs'
+   stacked triangles on the host.  The reference does LAPACK geqrf/orgqr on the host copy of the rows (bvlapack.c:378-396). */
+static void BVTSQRReset_B200(BV_B200 *d)
+{
+  if (d->ts_coef && CTX()) b2k_free(CTX(), d->ts_coef);
+  free(d->ts_stack);
+  d->ts_coef = NULL; d->ts_stack = NULL; d->ts_nk = d->ts_nblk = 0;
+}
+
+static PetscErrorCode BVTSQRFactor_B200(BV bv, PetscBool wantq, PetscScalar *R)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt nk = bv->k - bv->l;
+  int nblk = 0;
+  int64_t rpc = 0, ncoef = 0;
+  BVTSQRReset_B200(d);
+  if (nk <= 0) return PETSC_SUCCESS;
+  PetscCheck(nk <= B2K_TSQR_MAX_K, PETSC_ERR_SUP, "TSQR on BV type b200 takes at most %d active columns (%d given); use chol or svqb", B2K_TSQR_MAX_K, nk);
+  B2KCall(b2k_tsqr_plan(ctx, bv->n, (int)nk, &nblk, &rpc, &ncoef));
+  double *dR = NULL;
+  const size_t relems = (size_t)nblk * (size_t)nk * (size_t)nk;
+  B2KCall(b2k_malloc(ctx, (void **)&dR, sizeof(double) * relems));
+  if (wantq) B2KCall(b2k_malloc(ctx, (void **)&d->ts_coef, sizeof(double) * (size_t)ncoef));
+  int rc = b2k_tsqr_forward(ctx, COL(bv, d, bv->l), bv->ld, bv->n, (int)nk, wantq ? 1 : 0, dR, d->ts_coef);
+  const PetscInt rows = (PetscInt)nblk * nk;
+  int rows_ = rows, nk_ = nk, lwork = 64 * (int)nk + 64, info = 0;
+  double *blk = (double *)malloc(sizeof(double) * relems);
+  double *stack = (double *)malloc(sizeof(double) * ((size_t)rows * (size_t)nk + (size_t)nk + (size_t)lwork));
+  if (!rc && (!blk || !stack)) rc = B2K_ERR_MEM;
+  if (!rc) rc = b2k_d2h(ctx, blk, dR, sizeof(double) * relems);
+  b2k_free(ctx, dR);
+  if (rc) { free(blk); free(stack); BVTSQRReset_B200(d); SETERRQ(PETSC_ERR_GPU, "TSQR forward sweep failed (%d): %s", rc, b2k_last_error()); }
+  for (int b = 0; b < nblk; b++)
+    for (PetscInt c = 0; c < nk; c++) memcpy(stack + (size_t)b * nk + (size_t)c * rows, blk + ((size_t)b * nk + c) * nk, sizeof(double) * (size_t)nk);
+  free(blk);
+  double *tau = stack + (size_t)rows * nk, *work = tau + nk;
+  LAPACK(dgeqrf)(&rows_, &nk_, stack, &rows_, tau, work, &lwork, &info);
+  if (info) { free(stack); BVTSQRReset_B200(d); SETERRQ(PETSC_ERR_LIB, "Error in LAPACK subroutine geqrf: info=%d", info); }
+  for (PetscInt c = 0; c < nk; c++) for (PetscInt i = 0; i < nk; i++) R[i + (size_t)c * nk] = (i <= c) ? stack[i + (size_t)c * rows] : 0.0;
+  if (wantq) { d->ts_stack = stack; d->ts_nk = nk; d->ts_nblk = nblk; }
+  else free(stack);
+  return PETSC_SUCCESS;
+}
+
+/* columns l..k-1 <- Q_local W: the blocks of (orthogonal factor of the stack) * W start the backward sweep of every CTA */
+static PetscErrorCode BVTSQRFormQ_B200(BV bv, const PetscScalar *W)
+{
+  BV_B200 *d = (BV_B200 *)bv->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt nk = bv->k - bv->l;
+  if (nk <= 0) return PETSC_SUCCESS;
+  PetscCheck(d->ts_stack && d->ts_nk == nk, PETSC_ERR_ORDER, "tsqr_formq without a matching tsqr_factor(wantq)");
+  const PetscInt nblk = d->ts_nblk, rows = nblk * nk;
+  int rows_ = rows, nk_ = nk, lwork = 64 * (int)nk + 64, info = 0;
+  double *C = (double *)calloc((size_t)rows * (size_t)nk + (size_t)lwork, sizeof(double));
+  double *blk = (double *)malloc(sizeof(double) * (size_t)rows * (size_t)nk);
+  PetscCheck(C && blk, PETSC_ERR_MEM, "out of memory");
+  for (PetscInt c = 0; c < nk; c++) memcpy(C + (size_t)c * rows, W + (size_t)c * nk, sizeof(double) * (size_t)nk);     /* [W ; 0] */
+  LAPACK(dormqr)("L", "N", &rows_, &nk_, &nk_, d->ts_stack, &rows_, d->ts_stack + (size_t)rows * nk, C, &rows_, C + (size_t)rows * nk, &lwork, &info, 1, 1);
+  if (info) { free(C); free(blk); SETERRQ(PETSC_ERR_LIB, "Error in LAPACK subroutine ormqr: info=%d", info); }
+  for (PetscInt b = 0; b < nblk; b++)
+    for (PetscInt c = 0; c < nk; c++) memcpy(blk + ((size_t)b * nk + c) * nk, C + (size_t)b * nk + (size_t)c * rows, sizeof(double) * (size_t)nk);
+  free(C);
+  double *dW = NULL;
+  int rc = b2k_malloc(ctx, (void **)&dW, sizeof(double) * (size_t)rows * (size_t)nk);
+  if (!rc) rc = b2k_h2d(ctx, dW, blk, sizeof(double) * (size_t)rows * (size_t)nk);
+  if (!rc) rc = b2k_tsqr_backward(ctx, COL(bv, d, bv->l), bv->ld, bv->n, (int)nk, dW, d->ts_coef);
+  if (!rc) rc = b2k_ctx_sync(ctx);
+  if (dW) b2k_free(ctx, dW);
+  free(blk);
+  BVTSQRReset_B200(d);
+  PetscCheck(!rc, PETSC_ERR_GPU, "TSQR backward sweep failed (%d): %s", rc, b2k_last_error());
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode BVDestroy_B200(BV bv)
 {
   BV_B200 *d = (BV_B200 *)bv->data;
   if (!d) return PETSC_SUCCESS;
+  BVTSQRReset_B200(d);
   if (CTX()) b2k_free(CTX(), d->V);
   PetscCall(BVFreeScratch_B200(d));
   free(d);
@@ -586,5 +668,7 @@ PetscErrorCode BVCreate_B200(BV bv)
   bv->ops.gramschmidt = BVGramSchmidt_B200;
   bv->ops.destroy = BVDestroy_B200;
   bv->ops.setrandomcolumn = BVSetRandomColumn_B200;
+  bv->ops.tsqr_factor = BVTSQRFactor_B200;
+  bv->ops.tsqr_formq = BVTSQRFormQ_B200;
   return PETSC_SUCCESS;
 }

@@ -126,43 +126,16 @@ static PetscErrorCode MatMultBlock_B200CSR(Mat A, const PetscScalar *X, PetscInt
   return PETSC_SUCCESS;
 }
 
-/* A_loc^T from the CSR arrays in HBM: rows = local columns [owned | ghosts], columns = local rows.  Host counting sort
-   (set-up cost, once); the owned and the ghost block become two CSR matrices so that the owned part of y = A^T x is
-   written in place and only the ghost part travels. */
+/* A_loc^T built in HBM (b2k_csr_transpose_split: stable radix sort of the column indices + gather): rows = local columns
+   [owned | ghosts], columns = local rows.  Set-up cost, once; the owned and the ghost block become two matrices so that the
+   owned part of y = A^T x is written in place and only the ghost part travels. */
 static PetscErrorCode MatBuildLocalTranspose_B200CSR(Mat A)
 {
   Mat_B200CSR *a = (Mat_B200CSR *)A->data;
   b2k_ctx ctx = CTX();
-  const PetscInt m = A->m, ncl = A->n, ng = a->nghost, nt = ncl + ng;
-  const int64_t nnz = a->nnz;
-  int *drp, *dci;
-  double *dv;
-  B2KCall(b2k_csr_arrays(a->A, &drp, &dci, &dv));
-  PetscInt *rp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(m + 1)), *ci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
-  double *v = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
-  PetscInt *trp = (PetscInt *)calloc((size_t)nt + 2, sizeof(PetscInt)), *tci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
-  double *tv = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
-  PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
-  B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
-  if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
-  B2KCall(b2k_csr_release_arrays(a->A));          /* the CSR copy was rebuilt from the SELL copy for this read only */
-  for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
-  for (PetscInt c = 0; c < nt; c++) trp[c + 2] += trp[c + 1];
-  for (PetscInt r = 0; r < m; r++)
-    for (PetscInt k = rp[r]; k < rp[r + 1]; k++) { const PetscInt p = trp[ci[k] + 1]++; tci[p] = r; tv[p] = v[k]; }
-  /* trp[0..nt] is now the row pointer of the (ncl+ng) x m transpose */
-  int rc = b2k_csr_create(ctx, ncl, m, 0, trp, tci, tv, &a->ATown);
-  if (!rc && ng) {
-    const PetscInt base = trp[ncl];
-    PetscInt *grp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(ng + 1));
-    PetscCheck(grp, PETSC_ERR_MEM, "out of memory");
-    for (PetscInt c = 0; c <= ng; c++) grp[c] = trp[ncl + c] - base;
-    rc = b2k_csr_create(ctx, ng, m, 0, grp, tci + base, tv + base, &a->ATgh);
-    free(grp);
-    if (!rc) rc = b2k_malloc(ctx, (void **)&a->zghost, sizeof(double) * (size_t)ng);
-  }
-  if (!rc && a->nsendtot) rc = b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot);
-  free(rp); free(ci); free(v); free(trp); free(tci); free(tv);
+  int rc = b2k_csr_transpose_split(ctx, a->A, &a->ATown, a->nghost ? &a->ATgh : NULL);
+  if (!rc && a->nghost) rc = b2k_malloc(ctx, (void **)&a->zghost, sizeof(double) * (size_t)a->nghost);
+  if (!rc && a->nsendtot && !a->rbuf) rc = b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot);
   PetscCheck(!rc, PETSC_ERR_GPU, "building the local transpose failed (%d): %s", rc, b2k_last_error());
   return PETSC_SUCCESS;
 }
@@ -431,32 +404,19 @@ PetscErrorCode MatCreateB200Laplacian(PetscInt dim, PetscInt nx, PetscInt ny, Pe
   return PETSC_SUCCESS;
 }
 
-/* explicit transpose (single rank): what SVDSetUp builds by default, svdsetup.c:300-306 */
+/* explicit transpose (single rank): what SVDSetUp builds by default, svdsetup.c:300-306 — on the device, nothing crosses PCIe */
 PetscErrorCode MatB200CSRTranspose(Mat A, Mat *At)
 {
   PetscCheck(!strcmp(A->type, "b200csr"), PETSC_ERR_ARG_WRONG, "not a b200csr matrix");
-  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data, *t;
   b2k_ctx ctx = CTX();
   PetscCheck(a->nghost == 0 && A->m == A->M && A->n == A->N, PETSC_ERR_SUP, "explicit transpose is implemented for a single rank; pass A^T with SVDSetTransposeMatrix() otherwise");
-  const PetscInt m = A->m, n = A->n;
-  const int64_t nnz = a->nnz;
-  int *drp, *dci;
-  double *dv;
-  B2KCall(b2k_csr_arrays(a->A, &drp, &dci, &dv));
-  PetscInt *rp = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(m + 1)), *ci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
-  double *v = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
-  PetscInt *trp = (PetscInt *)calloc((size_t)n + 2, sizeof(PetscInt)), *tci = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nnz ? nnz : 1));
-  double *tv = (double *)malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
-  PetscCheck(rp && ci && v && trp && tci && tv, PETSC_ERR_MEM, "out of memory");
-  B2KCall(b2k_d2h(ctx, rp, drp, sizeof(int) * (size_t)(m + 1)));
-  if (nnz) { B2KCall(b2k_d2h(ctx, ci, dci, sizeof(int) * (size_t)nnz)); B2KCall(b2k_d2h(ctx, v, dv, sizeof(double) * (size_t)nnz)); }
-  B2KCall(b2k_csr_release_arrays(a->A));          /* the CSR copy was rebuilt from the SELL copy for this read only */
-  for (int64_t k = 0; k < nnz; k++) trp[ci[k] + 2]++;
-  for (PetscInt c = 0; c < n; c++) trp[c + 2] += trp[c + 1];      /* trp[c+1] = start of column c (shifted by one) */
-  for (PetscInt r = 0; r < m; r++)
-    for (PetscInt k = rp[r]; k < rp[r + 1]; k++) { const PetscInt p = trp[ci[k] + 1]++; tci[p] = r; tv[p] = v[k]; }
-  PetscErrorCode ierr = MatCreateB200CSR(n, m, 0, n, trp, tci, tv, 0, m, At);
-  free(rp); free(ci); free(v); free(trp); free(tci); free(tv);
-  PetscCall(ierr);
+  Mat T;
+  PetscCall(MatCreate_Private(&T));
+  PetscCall(MatSetUp_B200CSR(T, A->N, A->M, 0, A->N, 0, A->M, &t));
+  t->nnz = a->nnz;
+  const int rc = b2k_csr_transpose_split(ctx, a->A, &t->A, NULL);
+  if (rc) { MatDestroy(&T); SETERRQ(PETSC_ERR_GPU, "b2k_csr_transpose_split failed (%d): %s", rc, b2k_last_error()); }
+  *At = T;
   return PETSC_SUCCESS;
 }

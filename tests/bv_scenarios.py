@@ -185,12 +185,16 @@ def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
         for i in range(n // 2 + 1):
             if i + j < n:
                 X0[i + j, j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
-    gram = block != SL.BV_ORTHOG_BLOCK_GS
-    if (n, l, k) == (20, 2, 8) or ((n, l, k) == (180, 0, 7) and not gram):
+    gram = block in (SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB)        # TSQR is Householder: orthogonal whatever the conditioning
+    if block == SL.BV_ORTHOG_BLOCK_TSQRCHOL and (n, l, k) != (20, 2, 8):
+        gram = None                                                           # Q = V inv(R) with a backward-stable R: eps*cond
+    if (n, l, k) == (20, 2, 8) or ((n, l, k) == (180, 0, 7) and block == SL.BV_ORTHOG_BLOCK_GS):
         tol_orth = tol_res = 100 * EPS
     else:
         c = np.linalg.cond(X0)
         tol_orth = 100 * EPS * k * (c * c if gram else c)
+        if block == SL.BV_ORTHOG_BLOCK_TSQR:
+            tol_orth = 100 * EPS * k
         tol_res = 100 * EPS * np.linalg.norm(X0)
     X.from_numpy(X0)
     Y = SL.BV()
@@ -200,7 +204,8 @@ def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
     M = SL.Mat.seqdense(np.zeros((k, k)))
     R = SL.Mat.seqdense(np.zeros((k, k))) if resid else None
     Rh = R.h if resid else None
-    name = {SL.BV_ORTHOG_BLOCK_GS: None, SL.BV_ORTHOG_BLOCK_CHOL: "chol", SL.BV_ORTHOG_BLOCK_SVQB: "svqb"}[block]
+    name = {SL.BV_ORTHOG_BLOCK_GS: None, SL.BV_ORTHOG_BLOCK_CHOL: "chol", SL.BV_ORTHOG_BLOCK_SVQB: "svqb",
+            SL.BV_ORTHOG_BLOCK_TSQR: "tsqr", SL.BV_ORTHOG_BLOCK_TSQRCHOL: "tsqrchol"}[block]
     Yo = O.BV(n, k)
     Yo.V[:, :] = X0
 
@@ -234,7 +239,7 @@ def scenario_test11(make_bv, block, n=20, l=2, k=8, resid=True):
         Yo.set_active(l, k)
         Ro = Yo.orthogonalize_block(name, want_R=True)
         Qo = Yo.V[:, :k]
-        if name == "chol":                                    # unique factorisation: column for column
+        if name in ("chol", "tsqr", "tsqrchol"):              # unique factorisation (R with a positive diagonal): column for column
             assert np.linalg.norm(Q - Qo) < 1e3 * tol_orth
             if resid:
                 assert np.linalg.norm(R.dense_array()[:, l:k] - Ro[:, l:k]) < 1e3 * tol_orth * np.linalg.norm(Ro)

@@ -126,7 +126,7 @@ def main():
         norms_o = [Xo.orthonormalize_column(j)[0] for j in range(k)]
         res.update(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), dq=float(np.abs(Q - Xo.V).max()),
                    dn=float(np.abs(np.array(norms) - np.array(norms_o)).max()))
-    elif case in ("bvchol", "bvsvqb"):
+    elif case in ("bvchol", "bvsvqb", "bvtsqr", "bvtsqrchol"):
         # BVOrthogonalize CHOL / SVQB (bvorthog.c:586-675) on a split basis with 2 leading columns: the Gram matrix is
         # globally reduced by BVDot, the k x k factorisation is replicated, BVMult/BVMultInPlace are local
         n, k, l = 57, 7, 2
@@ -134,7 +134,8 @@ def main():
         rng = np.random.default_rng(7)
         Aglob = rng.standard_normal((n, k))
         name = case[2:]
-        block = SL.BV_ORTHOG_BLOCK_CHOL if name == "chol" else SL.BV_ORTHOG_BLOCK_SVQB
+        block = {"chol": SL.BV_ORTHOG_BLOCK_CHOL, "svqb": SL.BV_ORTHOG_BLOCK_SVQB, "tsqr": SL.BV_ORTHOG_BLOCK_TSQR,
+                 "tsqrchol": SL.BV_ORTHOG_BLOCK_TSQRCHOL}[name]    # TSQR: the ranks' triangles are gathered and factored once more (bv.c)
         X = CP.bv_cpu(re - rs, k, N=n, rstart=rs)
         X.from_numpy(Aglob[rs:re])
         S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, block)

@@ -52,11 +52,21 @@ def case_bv(rank, world, n=100003, k=9):
         S.BVOrthonormalizeColumn(X.h, j, 0, ctypes.byref(nrm), ctypes.byref(lin))
         norms.append(nrm.value)
     Q = np.concatenate(gather(X.to_numpy()), axis=0)
-    X.destroy()
     Qr, R = np.linalg.qr(Ag)
+    # block orthogonalisation by the Householder tree (TSQR): tiles inside the CTAs, CTAs on the host, ranks in bv.c
+    X.from_numpy(Ag[r0:r1])
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_TSQR)
+    Rt = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVOrthogonalize(X.h, Rt.h)
+    Qt = np.concatenate(gather(X.to_numpy()), axis=0)
+    Rm = Rt.dense_array()
+    sg = np.where(np.diag(R) < 0, -1.0, 1.0)
+    tsqr = dict(orth=float(np.linalg.norm(Qt.T @ Qt - np.eye(k))), resid=float(np.linalg.norm(Ag - Qt @ Rm) / np.linalg.norm(Ag)),
+                dr=float(np.linalg.norm(Rm - R * sg[:, None]) / np.linalg.norm(R)))
+    X.destroy(); Rt.destroy()
     return dict(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), span=float(np.linalg.norm(Q - Qr @ (Qr.T @ Q))),
                 dn=float(np.abs(np.array(norms) - np.abs(np.diag(R))).max() / np.abs(np.diag(R)).max()),
-                norms=norms, q_checksum=[float(x) for x in Q[::997].ravel()])
+                norms=norms, q_checksum=[float(x) for x in Q[::997].ravel()], tsqr=tsqr)
 
 
 def case_bv_transports(rank, world):
@@ -181,6 +191,8 @@ def verify(case, r):
     try:
         if case == "bv":
             assert r["orth"] < 1e-13 and r["span"] < 1e-10 and r["dn"] < 1e-12, (r["orth"], r["span"], r["dn"])
+            t = r["tsqr"]
+            assert t["orth"] < 1e-13 and t["resid"] < 1e-14 and t["dr"] < 1e-12, t
         elif case == "bv_transports":
             a, b = r["a"], r["b"]
             assert np.allclose(a["norms"], b["norms"], rtol=1e-14, atol=0)

@@ -50,9 +50,12 @@ def test_bv_orthonormalize_split_rows(world, tmp_path):
     assert r["orth"] < 1e-13 and r["dq"] < 1e-12 and r["dn"] < 1e-12
 
 
-@pytest.mark.parametrize("case", ["bvchol", "bvsvqb"])
-def test_bv_block_orthogonalize_split_rows(case, tmp_path):
-    r = run_case(case, 2, tmp_path)
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["bvchol", "bvsvqb", "bvtsqr", "bvtsqrchol"])
+def test_bv_block_orthogonalize_split_rows(case, world, tmp_path):
+    if world == 3 and case in ("bvchol", "bvsvqb"):
+        pytest.skip("covered on 2 ranks")
+    r = run_case(case, world, tmp_path)
     assert r["orth"] < 1e-13 and r["dq"] < 1e-12 and r["resid"] < 1e-12
 
 

@@ -46,19 +46,18 @@ def test_bv_test4_trans():
     SC.scenario_test4(make_bv, trans=True)
 
 
-@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB])
+@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB, SL.BV_ORTHOG_BLOCK_TSQR,
+                                   SL.BV_ORTHOG_BLOCK_TSQRCHOL])
 @pytest.mark.parametrize("resid", [False, True])
 def test_bv_test11_block_orthogonalize(block, resid):
+    """bv/tests/test11.c with every -bv_orthog_block of its test list (:255-268: gs, chol, tsqr, tsqrchol, svqb)"""
     SC.scenario_test11(make_bv, block, resid=resid)
 
 
-def test_bv_block_orthogonalize_tsqr_unsupported():
-    X = make_bv(20, 4)
-    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_TSQR)
-    X.from_numpy(np.random.default_rng(0).standard_normal((20, 4)))
-    with pytest.raises(SL.SlepcError):
-        S.BVOrthogonalize(X.h, None)
-    X.destroy()
+@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_TSQR, SL.BV_ORTHOG_BLOCK_TSQRCHOL])
+def test_bv_block_orthogonalize_tsqr_other_shapes(block):
+    SC.scenario_test11(make_bv, block, n=180, l=0, k=7, resid=True)
+    SC.scenario_test11(make_bv, block, n=4099, l=3, k=17, resid=True)
 
 
 def test_bv_norm_types():

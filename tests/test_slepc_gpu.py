@@ -49,11 +49,71 @@ def test_bv_test4(trans):
     SC.scenario_test4(make_bv, trans=trans)
 
 
-@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB])
+@pytest.mark.parametrize("block", [SL.BV_ORTHOG_BLOCK_GS, SL.BV_ORTHOG_BLOCK_CHOL, SL.BV_ORTHOG_BLOCK_SVQB, SL.BV_ORTHOG_BLOCK_TSQR,
+                                   SL.BV_ORTHOG_BLOCK_TSQRCHOL])
 @pytest.mark.parametrize("shape", [(20, 2, 8), (4099, 3, 17), (180, 0, 7)])
 def test_bv_test11_block_orthogonalize(block, shape):
     n, l, k = shape
     SC.scenario_test11(make_bv, block, n=n, l=l, k=k, resid=True)
+
+
+@pytest.mark.parametrize("k", [5, 16, 25, 32, 64])
+@pytest.mark.parametrize("onlyr", [False, True], ids=["tsqr", "tsqrchol"])
+def test_bv_tsqr_device_kernels_large(k, onlyr):
+    """k_tsqr_fwd / k_tsqr_bwd (b2k_tsqr.cu) on 300 007 rows (many tiles per CTA, a ragged last tile) against numpy's Householder
+    QR: R to 1e-12 relative (non-negative diagonal makes it unique), ||Q^T Q - I|| and ||X - Q R|| at the level the reference
+    asserts in bv/tests/test11.c (< 100 eps, here times k for the random matrix)"""
+    n = 300007
+    rng = np.random.default_rng(40 + k)
+    X0 = rng.standard_normal((n, k)) * np.logspace(0, 3, k)[None, :]
+    X0[:, k // 2] += 0.5 * X0[:, 0]
+    X = make_bv(n, k)
+    X.from_numpy(X0)
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071,
+                             SL.BV_ORTHOG_BLOCK_TSQRCHOL if onlyr else SL.BV_ORTHOG_BLOCK_TSQR)
+    R = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVOrthogonalize(X.h, R.h)
+    Q, Rm = X.to_numpy(), R.dense_array()
+    Qn, Rn = np.linalg.qr(X0)
+    sg = np.where(np.diag(Rn) < 0, -1.0, 1.0)
+    Rn, Qn = Rn * sg[:, None], Qn * sg[None, :]
+    assert np.allclose(np.tril(Rm, -1), 0.0) and np.all(np.diag(Rm) > 0)
+    assert np.linalg.norm(Rm - Rn) < 1e-12 * np.linalg.norm(Rn)
+    cond = np.linalg.cond(X0)
+    assert np.linalg.norm(Q.T @ Q - np.eye(k)) < 100 * EPS * k * (cond if onlyr else 1.0)
+    assert np.linalg.norm(X0 - Q @ Rm) < 100 * EPS * np.linalg.norm(X0)
+    assert np.linalg.norm(Q - Qn) < 1e-9 * cond
+    for o in (X, R):
+        o.destroy()
+
+
+def test_bv_tsqr_stays_orthogonal_where_cholesky_cannot():
+    """cond(X) = 1e9: the Gram matrix has cond 1e18 and CHOL / SVQB lose orthogonality completely (or fail), the Householder tree
+    does not — the reason the reference offers TSQR (bvorthog.c:611)"""
+    n, k = 100003, 12
+    rng = np.random.default_rng(5)
+    U, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    W, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    X0 = (U * np.logspace(0, -9, k)[None, :]) @ W.T
+    X = make_bv(n, k)
+    X.from_numpy(X0)
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_TSQR)
+    R = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVOrthogonalize(X.h, R.h)
+    Q = X.to_numpy()
+    assert np.linalg.norm(Q.T @ Q - np.eye(k)) < 100 * EPS * k
+    assert np.linalg.norm(X0 - Q @ R.dense_array()) < 100 * EPS * np.linalg.norm(X0)
+    for o in (X, R):
+        o.destroy()
+
+
+def test_bv_tsqr_more_than_64_columns_is_refused():
+    X = make_bv(1000, 70)
+    X.from_numpy(np.random.default_rng(0).standard_normal((1000, 70)))
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_TSQR)
+    with pytest.raises(SL.SlepcError):
+        S.BVOrthogonalize(X.h, None)
+    X.destroy()
 
 
 def test_bv_norm_types():

@@ -356,3 +356,78 @@ def test_spmm_through_the_pipeline_1m_rows(ctx, k, ghost):
     _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
     for d in (dX, dG, dY):
         d.free()
+
+
+# ---- local transpose built in HBM (b2k_csr_transpose_split): what MatMultTranspose / the explicit transpose of SVDSetUp multiply with ----
+def _csr_to_host(ctx, h):
+    nr, ncl, ng, nnz = (ctypes.c_int64() for _ in range(4))
+    _check(ctx.lib.b2k_csr_info(h, ctypes.byref(nr), ctypes.byref(ncl), ctypes.byref(ng), ctypes.byref(nnz)))
+    prp, pci, pv = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    _check(ctx.lib.b2k_csr_arrays(h, ctypes.byref(prp), ctypes.byref(pci), ctypes.byref(pv)))
+    rp = np.empty(nr.value + 1, dtype=np.int32); ci = np.empty(max(nnz.value, 1), dtype=np.int32); va = np.empty(max(nnz.value, 1))
+    _check(ctx.lib.b2k_d2h(ctx.h, rp.ctypes.data, prp, rp.nbytes))
+    if nnz.value:
+        _check(ctx.lib.b2k_d2h(ctx.h, ci.ctypes.data, pci, 4 * nnz.value))
+        _check(ctx.lib.b2k_d2h(ctx.h, va.ctypes.data, pv, 8 * nnz.value))
+    _check(ctx.lib.b2k_csr_release_arrays(h))
+    return rp, ci[:nnz.value], va[:nnz.value], (nr.value, ncl.value)
+
+
+@pytest.mark.parametrize("case", ["random_ghost", "random_noghost", "irregular_empty", "markov", "no_entries"])
+def test_device_transpose_matches_scipy_exactly(ctx, case):
+    """AT_own / AT_ghost from the device radix sort + gather against scipy's transpose: identical row pointers, identical column
+    order inside every transposed row (ascending row of A: the summation order of y = A^T x is fixed), identical values; then
+    y = A^T x through the product kernels"""
+    import scipy.sparse as sp
+    from slepc_b200 import matgen
+    rng = np.random.default_rng(21)
+    if case in ("random_ghost", "random_noghost"):
+        M, N = 300007, 90001
+        rp, ci, va = matgen.random_sparse_rows(M, N, 12, seed=9)
+        A = sp.csr_matrix((va, ci, rp), shape=(M, N))
+        ncl = 50000 if case == "random_ghost" else N
+    elif case == "irregular_empty":
+        A = _irregular("empty_chunks", rng).tocsr()
+        ncl = A.shape[0]                              # columns beyond n are ghosts
+    elif case == "markov":
+        m = 300
+        N = matgen.markov_size(m)
+        rp, ci, va = matgen.markov_rows(m)
+        A = sp.csr_matrix((va, ci, rp), shape=(N, N))
+        ncl = N
+    else:
+        A = sp.csr_matrix((40, 70))
+        ncl = 30
+    A.sort_indices()
+    M, N = A.shape
+    ng = N - ncl
+    h, hown, hgh = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32); va = np.ascontiguousarray(A.data)
+    _check(ctx.lib.b2k_csr_create(ctx.h, M, ncl, ng, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h)))
+    _check(ctx.lib.b2k_csr_transpose_split(ctx.h, h, ctypes.byref(hown), ctypes.byref(hgh) if ng else None))
+    AT = A.T.tocsr()
+    AT.sort_indices()
+    for hh, blk in ((hown, AT[:ncl]), (hgh, AT[ncl:])):
+        if not hh:
+            assert blk.shape[0] == 0
+            continue
+        trp, tci, tva, shape = _csr_to_host(ctx, hh)
+        assert shape == (blk.shape[0], M)
+        assert np.array_equal(trp, blk.indptr) and np.array_equal(tci, blk.indices) and np.array_equal(tva, blk.data)
+    # y = A^T x through the transposed blocks (whatever kernel the dispatch picks)
+    x = rng.standard_normal(M)
+    dx = ctx.to_device(x)
+    ref = AT @ x
+    for hh, lo, hi in ((hown, 0, ncl), (hgh, ncl, N)):
+        if not hh or hi == lo:
+            continue
+        dy = ctx.empty(hi - lo)
+        _check(ctx.lib.b2k_csr_spmv(ctx.h, hh, dx.ptr, None, dy.ptr))
+        ctx.sync()
+        tol = 1e-13 * max(np.abs(x).max(), 1.0) * max(int(np.diff(AT.indptr).max()), 1) * max(np.abs(A.data).max() if A.nnz else 1.0, 1.0)
+        assert np.abs(dy.to_host() - ref[lo:hi]).max() <= tol
+        dy.free()
+    dx.free()
+    for hh in (hown, hgh, h):
+        if hh:
+            _check(ctx.lib.b2k_csr_destroy(ctx.h, hh))
