@@ -140,6 +140,11 @@ int  b2k_gs_update_norm_gated(b2k_ctx ctx, const double *V, int64_t ld, int64_t 
 /* x *= 1/sqrt(sumsq[0]) guarded (no-op if sumsq is 0 or 1): normalisation with the norm still on
    the device                                  — BVOrthonormalizeColumn bvorthog.c:417-422        */
 int  b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *sumsq);
+/* x *= 1/sqrt(s), s = nrm2_second[0] if the DGKS gate (onrm2, nrm2_first, eta) of b2k_gs_update_norm_gated let the refinement run,
+   nrm2_first[0] otherwise; no-op when s is 0 or 1.  With it a whole Lanczos/Arnoldi step is enqueued without the host knowing
+   the outcome of the refinement test (BVOrthonormalizeColumn bvorthog.c:417-422 after BVOrthogonalizeGS :174-203)        */
+int  b2k_scale_rsqrt_gated(b2k_ctx ctx, double *x, int64_t n, const double *onrm2, const double *nrm2_first, const double *nrm2_second,
+                           double eta);
 /* implementation of the update sweeps (b2k_multvec, b2k_gs_update_norm, b2k_gs_update_dot); env B2K_GS_FUSED:
    0 generic kernels, two sweeps for update+dot; 1 register-tile single sweep;
    3 (default) 2-D tensor-map (TMA) pipelined single sweep, register tile for k <= 4 or fewer than 4096 rows       */

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2k_gs_update_norm": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
     "b2k_gs_update_norm_gated": [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl],
     "b2k_scale_rsqrt": [c_vp, c_vp, c_i64, c_vp],
+    "b2k_scale_rsqrt_gated": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_dbl],
     "b2k_gs_set_fused": [c_int],
     "b2k_spmv_set_sell": [c_int],
     "b2k_vq_set_tma": [c_int],

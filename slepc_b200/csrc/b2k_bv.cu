@@ -269,6 +269,17 @@ __global__ void __launch_bounds__(256) k_scale_rsqrt(double *__restrict__ x, int
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] *= a;
 }
+/* the normalisation of a column whose DGKS refinement was decided on the device: sumsq = ||w||^2 after the second pass when the
+   gate let it run, after the first otherwise.  Same IEEE operations as the host's 1/nrm, nrm = sqrt(sumsq). */
+__global__ void __launch_bounds__(256) k_scale_rsqrt_gated(double *__restrict__ x, int64_t n, const b2k_gate_s gate, const double *__restrict__ nrm2_second)
+{
+  b2k_pdl_enter();
+  const double s = b2k_gate_closed(gate) ? *reinterpret_cast<const volatile double *>(gate.nrm2) : nrm2_second[0];
+  if (!(s > 0.0) || s == 1.0) return;
+  const double a = 1.0 / sqrt(s);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) x[r] *= a;
+}
 __global__ void __launch_bounds__(256) k_copy(double *__restrict__ Y, int64_t ldy, const double *__restrict__ X, int64_t ldx,
                                                int64_t n)
 {
@@ -750,6 +761,19 @@ extern "C" int b2k_scale_rsqrt(b2k_ctx ctx, double *x, int64_t n, const double *
   if (n == 0) return B2K_OK;
   PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n);
   k_scale_rsqrt<<<grid2d(ctx, n, 1), 256, 0, ctx->stream>>>(x, n, sumsq);
+  PROF_END(ctx);
+  CKLAUNCH(ctx);
+  return B2K_OK;
+}
+extern "C" int b2k_scale_rsqrt_gated(b2k_ctx ctx, double *x, int64_t n, const double *onrm2, const double *nrm2_first, const double *nrm2_second,
+                                     double eta)
+{
+  ARGCHK(onrm2 && nrm2_first && nrm2_second, "null argument");
+  if (n == 0) return B2K_OK;
+  b2k_gate_s g;
+  g.onrm2 = onrm2; g.nrm2 = nrm2_first; g.eta = eta;
+  PROF_BEGIN(ctx, B2K_PROF_ELEMWISE, 16.0 * (double)n);
+  b2k_launch_pdl(k_scale_rsqrt_gated, grid2d(ctx, n, 1), dim3(256), 0, ctx->stream, x, n, g, nrm2_second);
   PROF_END(ctx);
   CKLAUNCH(ctx);
   return B2K_OK;

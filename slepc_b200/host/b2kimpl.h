@@ -143,6 +143,11 @@ typedef struct _BVOps {
   /* Householder QR of the LOCAL rows of the active columns l..k-1 (what BVOrthogonalize_LAPACK_TSQR / _TSQR_OnlyR do on the raw
      array, bvlapack.c:347-560): tsqr_factor returns the (k-l) x (k-l) upper-triangular factor of this rank's rows in R (column-major,
      leading dimension k-l); with wantq the type keeps what it needs so that tsqr_formq(W) overwrites the columns with Q_local * W */
+  /* Krylov steps j = k..m-1 (v_{j+1} = A v_j, orthonormalised against v_0..v_j with the DGKS rule, coefficients into the buffer
+     exactly as BVMatMultColumn + BVOrthonormalizeColumn leave them) enqueued WITHOUT host round trips; *jnext = first step the
+     type did not complete (k when it declines, m when all went through; a breakdown or a third DGKS pass stops it early and the
+     front-end's step-by-step loop takes over from there), *beta = the norm of the last completed step */
+  PetscErrorCode (*krylov_steps)(BV, Mat A, PetscInt k, PetscInt m, PetscInt *jnext, PetscReal *beta);
   PetscErrorCode (*tsqr_factor)(BV, PetscBool wantq, PetscScalar *R);
   PetscErrorCode (*tsqr_formq)(BV, const PetscScalar *W);
 } BVOps;

@@ -43,6 +43,10 @@ typedef struct {
   double   *ts_coef;     /* device */
   double   *ts_stack;    /* host: (nblk*nk) x nk factored by dgeqrf, then nk tau                    */
   PetscInt  ts_nk, ts_nblk;
+  /* asynchronous Krylov cycle (krylov_steps): 4 coefficient slots PER STEP in HBM and their pinned mirror */
+  int       async;       /* env B2K_BV_ASYNC, default 1                                           */
+  double   *kr_d, *kr_h;
+  PetscInt  kr_steps;
 } BV_B200;
 
 #define CTX() B2KGetContext()
@@ -240,6 +244,86 @@ static PetscErrorCode BVGramSchmidt_B200(BV bv, PetscInt j, Vec v, PetscBool *wh
     if (norm) *norm = sqrt(d->pend_nrm2 > 0.0 ? d->pend_nrm2 : 0.0);   /* explicit, not the beta^2 - sum c^2 estimate of :124 */
   }
   BV_AddCoefficients(bv, j, h, c);
+  return PETSC_SUCCESS;
+}
+
+/* ---- a whole Krylov cycle without host round trips --------------------------------------------------------------------------
+   BVMatLanczos / BVMatArnoldi (bvkrylov.c:56-226) call, per column, MatMult, then BVOrthonormalizeColumn whose DGKS loop
+   (bvorthog.c:174-203) and final scaling (:417-422) need beta, the norms and the refinement decision ON THE HOST: one blocking
+   round trip per column at best.  Here the steps k..m-1 are enqueued back to back: SpMV, dot sweep, update+dot sweep, the
+   refinement's update sweep gated on the device by the same criterion, and the normalisation by 1/sqrt of whichever norm the gate
+   selected (b2k_scale_rsqrt_gated) — every step writes its coefficients into its own slots, the host copies all of them once and
+   rebuilds the coefficient buffer (h = c1 [+ c2], norm, passes) with the reference's arithmetic.  The launch queue never drains,
+   so the per-kernel launch latency and the synchronisation gap disappear from the latency-bound regime (small local row counts,
+   strong scaling).  A step that needs what the device did not do (third pass, breakdown, zero norm) ends the asynchronous part:
+   everything before it is final, the step-by-step loop of bv.c redoes it. */
+static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, PetscInt *jnext, PetscReal *beta)
+{
+  BV_B200 *d = (BV_B200 *)V->data;
+  b2k_ctx ctx = CTX();
+  const PetscInt steps = m - k;
+  *jnext = k;
+  if (!d->async || !d->onesync || d->fuse_mode == 0 || steps < 2 || V->orthog_type != BV_ORTHOG_CGS || V->orthog_ref != BV_ORTHOG_REFINE_IFNEEDED ||
+      V->matrix || V->nc != 0)
+    return PETSC_SUCCESS;                          /* every condition is the same on all ranks: the choice is collective */
+  if (d->kr_steps < steps) {
+    if (d->kr_d) B2KCall(b2k_free(ctx, d->kr_d));
+    if (d->kr_h) b2k_host_free(d->kr_h);
+    d->kr_d = d->kr_h = NULL; d->kr_steps = 0;
+    const size_t bytes = sizeof(double) * 4 * (size_t)d->slot * (size_t)V->m;
+    B2KCall(b2k_malloc(ctx, (void **)&d->kr_d, bytes));
+    B2KCall(b2k_host_alloc((void **)&d->kr_h, bytes));
+    d->kr_steps = V->m;
+  }
+  d->pend_valid = PETSC_FALSE; d->pend2_valid = PETSC_FALSE; d->last_j = -1;
+  PetscBool fused = PETSC_FALSE, anyfused = PETSC_FALSE;
+  for (PetscInt j = k; j < m; j++) {
+    PetscCall(BVMatMultColumn(V, A, j));
+    const PetscInt kk = j + 1;
+    double *w = COL(V, d, kk), *S0 = d->kr_d + 4 * (size_t)d->slot * (size_t)(j - k), *S1 = S0 + d->slot, *S3 = S0 + 3 * d->slot;
+    PetscCall(BVScope_B200(V, PETSC_TRUE, &fused));
+    anyfused = fused ? PETSC_TRUE : anyfused;
+    B2KCall(b2k_gs_dot(ctx, d->V, V->ld, V->n, (int)kk, w, S0));
+    if (!fused) PetscCall(B2KCommAllreduce(V->comm, S0, (int)kk + 1, 0, B2K_MEM_DEVICE));
+    B2KCall(b2k_gs_update_dot(ctx, d->V, V->ld, V->n, (int)kk, w, S0, S1));
+    if (!fused) PetscCall(B2KCommAllreduce(V->comm, S1, (int)kk + 1, 0, B2K_MEM_DEVICE));
+    B2KCall(b2k_gs_update_norm_gated(ctx, d->V, V->ld, V->n, (int)kk, w, S1, S3, S0 + kk, S1 + kk, V->orthog_eta));
+    if (!fused) PetscCall(B2KCommAllreduce(V->comm, S3, 1, 0, B2K_MEM_DEVICE));
+    if (fused) PetscCall(B2KCommReduceScope(V->comm, PETSC_FALSE, NULL));
+    B2KCall(b2k_scale_rsqrt_gated(ctx, w, V->n, S0 + kk, S1 + kk, S3, V->orthog_eta));
+  }
+  B2KCall(b2k_d2h_async(ctx, d->kr_h, d->kr_d, sizeof(double) * 4 * (size_t)d->slot * (size_t)steps));
+  B2KCall(b2k_ctx_sync(ctx));
+  if (anyfused) {
+    int bad = 0;
+    B2KCall(b2k_comm_p2p_error(V->comm->nccl, &bad));
+    PetscCheck(!bad, PETSC_ERR_LIB, "peer-memory reduction timed out: a rank did not take part in the collective");
+  }
+  const size_t ldb = (size_t)(V->nc + V->m);
+  PetscInt j;
+  for (j = k; j < m; j++) {
+    const PetscInt kk = j + 1;
+    const double *H0 = d->kr_h + 4 * (size_t)d->slot * (size_t)(j - k), *H1 = H0 + d->slot, *H3 = H0 + 3 * d->slot;
+    const PetscReal deftol = 10 * PETSC_MACHINE_EPSILON;
+    if (!(H0[kk] > -deftol) || !(H1[kk] > -deftol)) break;                                        /* BV_SafeSqrt: let the synchronous path raise it */
+    const PetscReal onrm = sqrt(H0[kk] > 0.0 ? H0[kk] : 0.0), nrm1 = sqrt(H1[kk] > 0.0 ? H1[kk] : 0.0);
+    const PetscBool refine = (nrm1 != 0.0 && fabs(nrm1) < V->orthog_eta * fabs(onrm)) ? PETSC_TRUE : PETSC_FALSE;   /* bvorthog.c:180, = the gate */
+    PetscReal nrm = nrm1, on = onrm;
+    if (refine) {
+      if (!(H3[0] > -deftol)) break;
+      nrm = sqrt(H3[0] > 0.0 ? H3[0] : 0.0); on = nrm1;
+      if (nrm != 0.0 && fabs(nrm) < V->orthog_eta * fabs(on)) break;                              /* a third pass is due (l < 3) */
+    }
+    if (!(nrm != 0.0 && fabs(nrm) >= V->orthog_eta * fabs(on))) break;                            /* lindep / breakdown */
+    PetscScalar *hcol = V->buffer + (size_t)kk * ldb;
+    for (PetscInt i = 0; i < kk; i++) hcol[i] = refine ? (0.0 + H0[i]) + H1[i] : 0.0 + H0[i];    /* BV_CleanCoefficients, then h += c per pass */
+    memcpy(V->buffer, refine ? H1 : H0, sizeof(double) * (size_t)(kk + 1));                        /* column 0 = c of the last pass (+ its (w,w)) */
+    hcol[kk] = nrm;                                                                               /* BV_SetValue(bv,k,k,h,nrm) bvorthog.c:212 */
+    V->n_gs_passes += refine ? 2 : 1;
+    V->state += 2;
+    *beta = nrm;
+  }
+  *jnext = j;
   return PETSC_SUCCESS;
 }
 
@@ -614,6 +698,8 @@ static PetscErrorCode BVDestroy_B200(BV bv)
   BV_B200 *d = (BV_B200 *)bv->data;
   if (!d) return PETSC_SUCCESS;
   BVTSQRReset_B200(d);
+  if (CTX() && d->kr_d) b2k_free(CTX(), d->kr_d);
+  if (d->kr_h) b2k_host_free(d->kr_h);
   if (CTX()) b2k_free(CTX(), d->V);
   PetscCall(BVFreeScratch_B200(d));
   free(d);
@@ -640,6 +726,8 @@ PetscErrorCode BVCreate_B200(BV bv)
   d->fuse_mode = e ? atoi(e) : 2;
   e = getenv("B2K_BV_ONESYNC");
   d->onesync = e ? atoi(e) : 1;
+  e = getenv("B2K_BV_ASYNC");
+  d->async = e ? atoi(e) : 1;
   d->expect_refine = PETSC_TRUE;
   d->last_j = -1;
 
@@ -668,6 +756,7 @@ PetscErrorCode BVCreate_B200(BV bv)
   bv->ops.gramschmidt = BVGramSchmidt_B200;
   bv->ops.destroy = BVDestroy_B200;
   bv->ops.setrandomcolumn = BVSetRandomColumn_B200;
+  bv->ops.krylov_steps = BVKrylovSteps_B200;
   bv->ops.tsqr_factor = BVTSQRFactor_B200;
   bv->ops.tsqr_formq = BVTSQRFormQ_B200;
   return PETSC_SUCCESS;

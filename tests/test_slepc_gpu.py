@@ -589,7 +589,8 @@ print(json.dumps(dict(syncs=n.value - s0, steps=steps, passes=passes, nconv=eps.
 ''' % (os.path.dirname(HERE), refine.upper())
     res = {}
     for one in ("1", "0"):
-        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2K_BV_ONESYNC=one), capture_output=True, text=True, timeout=300)
+        # B2K_BV_ASYNC=0: this test is about the step-by-step path (the asynchronous cycle has its own tests below)
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2K_BV_ONESYNC=one, B2K_BV_ASYNC="0"), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         res[one] = json.loads(r.stdout.strip().splitlines()[-1])
     a, b = res["1"], res["0"]
@@ -699,3 +700,88 @@ def test_eps_generalized_sinvert_large_vs_scipy_gpu():
     assert eps.ksp_iterations() > 0
     for o in (eps, Am, Bm):
         o.destroy()
+
+
+# ---- the asynchronous Krylov cycle (ops.krylov_steps of BV type b200) against the step-by-step path -----------------------------------
+def _solve_with_async(flag, build, hermitian, nev, ncv, which=None, x0=None):
+    old, oldf = os.environ.get("B2K_BV_ASYNC"), os.environ.get("B2K_BV_FUSE")
+    os.environ["B2K_BV_ASYNC"] = flag               # read when the BV is created
+    # the step-by-step path fuses the second pass' dot into the update sweep only once it has seen a refinement (adaptive), the
+    # asynchronous cycle always does; B2K_BV_FUSE=1 makes both fuse from the first column on, so that the only thing compared
+    # is who takes the decisions (the fused and the separate dot sweep sum in different orders: rounding-level differences)
+    os.environ["B2K_BV_FUSE"] = "1"
+    try:
+        M = build()
+        eps = SL.EPS(M, hermitian=hermitian)
+        if which is not None:
+            S.EPSSetWhichEigenpairs(eps.h, which)
+        S.EPSSetDimensions(eps.h, nev, ncv, SL.PETSC_DETERMINE)
+        keep = None
+        if x0 is not None:
+            keep, _ = M.create_vecs()
+            keep.set_values(x0)
+            S.EPSSetInitialSpace(eps.h, 1, (ctypes.c_void_p * 1)(keep.h))
+        ctx = S.B2KGetContext()
+        from slepc_b200 import _b2k
+        lib = _b2k.load()
+        n0 = ctypes.c_uint64(); lib.b2k_ctx_syncs(ctx, ctypes.byref(n0))
+        eps.solve()
+        n1 = ctypes.c_uint64(); lib.b2k_ctx_syncs(ctx, ctypes.byref(n1))
+        bv = eps.bv()
+        out = dict(its=eps.its, nconv=eps.nconv, reason=eps.reason, lam=[eps.eigenvalue(i) for i in range(eps.nconv)],
+                   errs=[eps.error(i) for i in range(eps.nconv)], counters=bv.counters(), syncs=n1.value - n0.value)
+        for o in (eps, M) + ((keep,) if keep is not None else ()):
+            o.destroy()
+        return out
+    finally:
+        for key, val in (("B2K_BV_ASYNC", old), ("B2K_BV_FUSE", oldf)):
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
+
+
+@pytest.mark.parametrize("case", ["lanczos_2d", "lanczos_3d_default_ncv", "arnoldi_markov"])
+def test_async_krylov_cycle_is_bitwise_the_step_by_step_path(case):
+    """the cycle enqueued without host round trips does the reference's arithmetic in the reference's order (same sweeps, same
+    DGKS decisions, same normalisation): iteration counts, eigenvalues, Gram-Schmidt pass and MatMult counters are IDENTICAL to
+    the synchronised path, and the host waits far less often"""
+    if case == "lanczos_2d":
+        args = (lambda: SL.Mat.laplacian(2, 200, 150), True, 6, 32)
+        kw = {}
+    elif case == "lanczos_3d_default_ncv":
+        args = (lambda: SL.Mat.laplacian(3, 40, 36, 32), True, 10, SL.PETSC_DETERMINE)
+        kw = {}
+    else:
+        from slepc_b200 import matgen
+        m = 60
+        N = matgen.markov_size(m)
+        A = O.markov_model(m)
+        x0 = np.zeros(N); x0[:3] = 1.0
+        args = (lambda: SL.Mat.b200csr(A), False, 5, SL.PETSC_DETERMINE)
+        kw = dict(which=SL.EPS_LARGEST_REAL, x0=x0)
+    a = _solve_with_async("1", *args, **kw)
+    b = _solve_with_async("0", *args, **kw)
+    assert a["reason"] > 0 and a["nconv"] >= args[2]
+    assert (a["its"], a["nconv"], a["counters"]) == (b["its"], b["nconv"], b["counters"])
+    assert a["lam"] == b["lam"]                      # bit for bit
+    assert a["errs"] == b["errs"]
+    steps = a["counters"][1]
+    assert b["syncs"] - a["syncs"] > 0.5 * steps, (a["syncs"], b["syncs"], steps)      # one wait per step became one per cycle
+
+
+def test_async_krylov_cycle_hands_a_breakdown_to_the_synchronous_path():
+    """start vector = an exact eigenvector of a diagonal matrix: the very first step of the first asynchronous cycle ends with
+    w - (v^T w) v = 0 exactly; the device cannot take the breakdown branch (bvkrylov.c:198-201, krylovschur.c:262-270: new start
+    vector), so the cycle must stop there and the step-by-step loop must carry on exactly as it does on its own"""
+    import scipy.sparse as sp
+    n = 4000
+    dvals = np.repeat([1.0, 2.0, 3.5, 5.0, 9.0], n // 5)
+    A = sp.diags(dvals).tocsr()
+    x0 = np.zeros(n); x0[0] = 1.0
+    args = (lambda: SL.Mat.b200csr(A), True, 2, 12)
+    a = _solve_with_async("1", *args, x0=x0)
+    b = _solve_with_async("0", *args, x0=x0)
+    assert a["reason"] > 0 and a["nconv"] == b["nconv"] >= 2 and a["its"] == b["its"]
+    assert a["lam"] == b["lam"]
+    assert abs(a["lam"][0][0] - 9.0) < 1e-12 and abs(a["lam"][1][0] - 9.0) < 1e-12      # 9 has multiplicity 800
