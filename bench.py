@@ -384,9 +384,13 @@ def run_b200(args, wl):
     e2e = None
     if not args.no_e2e:
         h = build_host_csr_slab(lib, wl, nx_total, rank, world)
-        v0 = np.empty(h["nloc"])
+        def pinned_f64(nelem):                      # the step's host buffers are pinned, like the CSR arrays
+            p = ctypes.c_void_p()
+            assert lib.b2k_host_alloc(ctypes.byref(p), 8 * nelem) == 0
+            return np.frombuffer((ctypes.c_char * (8 * nelem)).from_address(p.value), dtype=np.float64), p
+        v0, v0_p = pinned_f64(h["nloc"])
         v0[:] = np.sin(0.37 * np.arange(h["row0"], h["row0"] + h["nloc"]) + 0.1) + 0.5
-        out = np.empty(h["nloc"])
+        out, out_p = pinned_f64(h["nloc"])
         hb0, db0 = ctypes.c_uint64(), ctypes.c_uint64()
         lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb0), ctypes.byref(db0))
         barrier()
@@ -426,7 +430,8 @@ def run_b200(args, wl):
         e2.destroy()
         x0.destroy()
         A.destroy()
-        for _, p in (h["rowptr"], h["colidx"], h["val"]):
+        del v0, out
+        for p in (h["rowptr"][1], h["colidx"][1], h["val"][1], v0_p, out_p):
             lib.b2k_host_free(p)
         del h
 
