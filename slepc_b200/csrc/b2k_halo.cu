@@ -1,6 +1,8 @@
 /*
- * b2k_halo.cu — SpMV halo exchange over NVLink peer memory (OPT-IN: B2K_HALO_P2P=1; the default halo is the grouped
- * ncclSend/ncclRecv of matb200.c).  Replaces the VecScatter of PETSc's MatMult_MPIAIJ (reached from bvops.c:879) for the
+ * b2k_halo.cu — SpMV halo exchange over NVLink peer memory (default on one box; B2K_HALO_P2P=0 keeps the grouped
+ * ncclSend/ncclRecv of matb200.c).  The same object with the roles exchanged carries the REVERSE halo of MatMultTranspose
+ * (ghost-column contributions pushed to their owners).  Replaces the VecScatter of PETSc's MatMult_MPIAIJ /
+ * MatMultTranspose_MPIAIJ (reached from bvops.c:879, gklanczos.c:80,103) for the
  * GPUs of one NVSwitch box: every rank PUSHES the entries of x its neighbours need straight into the neighbours' ghost
  * buffers (peer-mapped HBM, CUDA IPC) and raises a sequence-numbered flag; the receiver waits for the flags of its senders
  * and multiplies.  No packing buffer, no NCCL launch, 2 small kernels per MatMult.
@@ -23,7 +25,8 @@
 #include "b2k_internal.h"
 
 #define HL_MAXP 8                      /* peers per direction (= ranks of one box)                  */
-#define HL_CTAS 16                     /* CTAs per destination in k_halo_push                       */
+#define HL_CTAS 16                     /* CTAs per destination in k_halo_push: at least this many …  */
+#define HL_CTAS_MAX 64                 /* … and one more per 8192 entries up to this (C5: 1.25e6 entries = 10 MB per destination) */
 
 typedef unsigned long long u64;
 
@@ -55,6 +58,7 @@ struct b2k_halo_s {
   int     *err_host;
   hl_args  args;
   u64      seq;
+  int      ctas;                       /* CTAs per destination                                        */
 };
 
 /* the communicator internals this file needs (b2k_comm.cu) */
@@ -229,6 +233,12 @@ extern "C" int b2k_halo_create(b2k_comm comm, int nrecv, const int *recvrank, co
     a->peer_ack[p] = hl_ack(h->peer[r], hl_data_bytes((long long)pr[8])) + slot_there;
   }
   free(mine); free(all);
+  {
+    long long maxcount = 0;
+    for (int q = 0; q < nsend; q++) if (sendcount[q] > maxcount) maxcount = sendcount[q];
+    long long c = (maxcount + 8191) / 8192;
+    h->ctas = (int)(c < HL_CTAS ? HL_CTAS : (c > HL_CTAS_MAX ? HL_CTAS_MAX : c));
+  }
   h->seq = 0;
   *out = h;
   return B2K_OK;
@@ -240,7 +250,7 @@ extern "C" int b2k_halo_exchange(b2k_halo h, const double *x, const double **gho
   b2k_ctx ctx = h->ctx;
   const u64 seq = ++h->seq;
   if (h->args.nsend > 0 || h->args.nrecv > 0) {
-    dim3 grid(HL_CTAS, h->args.nsend > 0 ? h->args.nsend : 1);
+    dim3 grid(h->ctas, h->args.nsend > 0 ? h->args.nsend : 1);
     b2k_launch_pdl(k_halo_push, grid, dim3(256), 0, ctx->stream, x, h->args, seq);
     CKLAUNCH(ctx);
   }

@@ -1275,15 +1275,19 @@ static PetscErrorCode BVKrylovLoop_Private(BV V, Mat A, PetscInt k, PetscInt *m,
 {
   PetscBool lindep = PETSC_FALSE;
   PetscReal b = 0.0;
-  PetscInt j0 = k;
-  if (V->ops.krylov_steps) {
-    /* the type runs the recurrence on its own (BV type b200: the whole cycle is enqueued on the stream, the DGKS decision and the
-       normalisation are taken on the device, the host reads every coefficient once at the end); whatever it leaves — the
-       full-basis step j = N-1, a breakdown, a third refinement pass — continues below, one synchronised step at a time */
-    const PetscInt mm = (*m > V->N - 1) ? V->N - 1 : *m;
-    if (mm > k) PetscCall(V->ops.krylov_steps(V, A, k, mm, &j0, &b));
-  }
-  for (PetscInt j = j0; j < *m; j++) {
+  /* ops.krylov_steps: the type runs the recurrence on its own (BV type b200: the whole cycle is enqueued on the stream, the DGKS
+     decision and the normalisation are taken on the device, the host reads every coefficient once at the end); whatever it
+     leaves — the full-basis step j = N-1, a breakdown, a refinement pass it had not prepared — is done here, one synchronised
+     step, after which the type is asked again for the rest */
+  const PetscInt mm = (*m > V->N - 1) ? V->N - 1 : *m;
+  const PetscBool ask = V->ops.krylov_steps ? PETSC_TRUE : PETSC_FALSE;
+  for (PetscInt j = k; j < *m; j++) {
+    if (ask && j < mm) {
+      PetscInt jn = j;
+      PetscCall(V->ops.krylov_steps(V, A, j, mm, &jn, &b));
+      j = jn;
+      if (j >= *m) break;
+    }
     PetscCall(BVMatMultColumn(V, A, j));
     if (j == V->N - 1) PetscCall(BV_OrthogonalizeColumn_Safe(V, j + 1, &b, &lindep));
     else PetscCall(BVOrthonormalizeColumn(V, j + 1, PETSC_FALSE, &b, &lindep));

@@ -47,6 +47,7 @@ typedef struct {
   int       async;       /* env B2K_BV_ASYNC, default 1                                           */
   double   *kr_d, *kr_h;
   PetscInt  kr_steps;
+  PetscBool kr_probed;
 } BV_B200;
 
 #define CTX() B2KGetContext()
@@ -277,6 +278,12 @@ static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, Pe
   }
   d->pend_valid = PETSC_FALSE; d->pend2_valid = PETSC_FALSE; d->last_j = -1;
   PetscBool fused = PETSC_FALSE, anyfused = PETSC_FALSE;
+  /* two schedules, chosen like the step-by-step path chooses (expect_refine follows what DGKS did last): `spec` prepares the
+     refinement pass speculatively (3 sweeps enqueued, the third gated); otherwise 2 sweeps (dot, update + norm) and a step that
+     turns out to need a refinement ends the asynchronous part there (Arnoldi on the Markov matrix refines once in 3 500 steps) */
+  const PetscBool spec = (d->fuse_mode == 1 || d->expect_refine) ? PETSC_TRUE : PETSC_FALSE;
+  if (!spec && !d->kr_probed && m > k + 3) m = k + 3;        /* nothing is known about this recurrence yet: a short probe, not a whole cycle */
+  d->kr_probed = PETSC_TRUE;
   for (PetscInt j = k; j < m; j++) {
     PetscCall(BVMatMultColumn(V, A, j));
     const PetscInt kk = j + 1;
@@ -285,14 +292,20 @@ static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, Pe
     anyfused = fused ? PETSC_TRUE : anyfused;
     B2KCall(b2k_gs_dot(ctx, d->V, V->ld, V->n, (int)kk, w, S0));
     if (!fused) PetscCall(B2KCommAllreduce(V->comm, S0, (int)kk + 1, 0, B2K_MEM_DEVICE));
-    B2KCall(b2k_gs_update_dot(ctx, d->V, V->ld, V->n, (int)kk, w, S0, S1));
-    if (!fused) PetscCall(B2KCommAllreduce(V->comm, S1, (int)kk + 1, 0, B2K_MEM_DEVICE));
-    B2KCall(b2k_gs_update_norm_gated(ctx, d->V, V->ld, V->n, (int)kk, w, S1, S3, S0 + kk, S1 + kk, V->orthog_eta));
-    if (!fused) PetscCall(B2KCommAllreduce(V->comm, S3, 1, 0, B2K_MEM_DEVICE));
+    if (spec) {
+      B2KCall(b2k_gs_update_dot(ctx, d->V, V->ld, V->n, (int)kk, w, S0, S1));
+      if (!fused) PetscCall(B2KCommAllreduce(V->comm, S1, (int)kk + 1, 0, B2K_MEM_DEVICE));
+      B2KCall(b2k_gs_update_norm_gated(ctx, d->V, V->ld, V->n, (int)kk, w, S1, S3, S0 + kk, S1 + kk, V->orthog_eta));
+      if (!fused) PetscCall(B2KCommAllreduce(V->comm, S3, 1, 0, B2K_MEM_DEVICE));
+    } else {
+      B2KCall(b2k_gs_update_norm(ctx, d->V, V->ld, V->n, (int)kk, w, S0, S1 + kk));      /* ||w_1||^2 where the other schedule leaves it */
+      if (!fused) PetscCall(B2KCommAllreduce(V->comm, S1 + kk, 1, 0, B2K_MEM_DEVICE));
+    }
     if (fused) PetscCall(B2KCommReduceScope(V->comm, PETSC_FALSE, NULL));
-    B2KCall(b2k_scale_rsqrt_gated(ctx, w, V->n, S0 + kk, S1 + kk, S3, V->orthog_eta));
+    if (spec) B2KCall(b2k_scale_rsqrt_gated(ctx, w, V->n, S0 + kk, S1 + kk, S3, V->orthog_eta));
+    else B2KCall(b2k_scale_rsqrt(ctx, w, V->n, S1 + kk));
   }
-  B2KCall(b2k_d2h_async(ctx, d->kr_h, d->kr_d, sizeof(double) * 4 * (size_t)d->slot * (size_t)steps));
+  B2KCall(b2k_d2h_async(ctx, d->kr_h, d->kr_d, sizeof(double) * 4 * (size_t)d->slot * (size_t)(m - k)));
   B2KCall(b2k_ctx_sync(ctx));
   if (anyfused) {
     int bad = 0;
@@ -300,7 +313,7 @@ static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, Pe
     PetscCheck(!bad, PETSC_ERR_LIB, "peer-memory reduction timed out: a rank did not take part in the collective");
   }
   const size_t ldb = (size_t)(V->nc + V->m);
-  PetscInt j;
+  PetscInt j, nrefined = 0;
   for (j = k; j < m; j++) {
     const PetscInt kk = j + 1;
     const double *H0 = d->kr_h + 4 * (size_t)d->slot * (size_t)(j - k), *H1 = H0 + d->slot, *H3 = H0 + 3 * d->slot;
@@ -309,6 +322,8 @@ static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, Pe
     const PetscReal onrm = sqrt(H0[kk] > 0.0 ? H0[kk] : 0.0), nrm1 = sqrt(H1[kk] > 0.0 ? H1[kk] : 0.0);
     const PetscBool refine = (nrm1 != 0.0 && fabs(nrm1) < V->orthog_eta * fabs(onrm)) ? PETSC_TRUE : PETSC_FALSE;   /* bvorthog.c:180, = the gate */
     PetscReal nrm = nrm1, on = onrm;
+    nrefined += refine ? 1 : 0;
+    if (refine && !spec) { d->expect_refine = PETSC_TRUE; break; }                               /* not prepared: the step-by-step loop refines it */
     if (refine) {
       if (!(H3[0] > -deftol)) break;
       nrm = sqrt(H3[0] > 0.0 ? H3[0] : 0.0); on = nrm1;
@@ -323,6 +338,7 @@ static PetscErrorCode BVKrylovSteps_B200(BV V, Mat A, PetscInt k, PetscInt m, Pe
     V->state += 2;
     *beta = nrm;
   }
+  if (spec && j == m && nrefined == 0 && d->fuse_mode == 2) d->expect_refine = PETSC_FALSE;   /* a whole cycle without refinement: 2 sweeps next time */
   *jnext = j;
   return PETSC_SUCCESS;
 }

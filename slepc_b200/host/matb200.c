@@ -30,6 +30,7 @@ typedef struct {
   double   *zghost, *rbuf;
   /* default on one NVSwitch box (B2K_HALO_P2P=0 turns it off): the forward halo pushed over NVLink peer memory instead of ncclSend/ncclRecv */
   b2k_halo  halo;
+  b2k_halo  halo_rev;        /* the same plan run backwards (MatMultTranspose): ghost-column contributions pushed to their owners     */
   double   *gblock;          /* device: ghost values of a block of vectors, nghost x gblock_cols (MatMultBlock) */
   PetscInt  gblock_cols;
 } Mat_B200CSR;
@@ -44,6 +45,7 @@ static PetscErrorCode MatHaloSetUpP2P_B200CSR(Mat A)
   B2KComm comm = B2KCommWorld();
   const char *e = getenv("B2K_HALO_P2P");
   if ((e && e[0] == '0') || !comm || comm->kind != 1 || comm->size < 2 || comm->size > 8 || !b2k_comm_p2p_enabled(comm->nccl)) return PETSC_SUCCESS;
+  if (a->halo_rev) { B2KCall(b2k_halo_destroy(a->halo_rev)); a->halo_rev = NULL; }
   if (a->halo) { B2KCall(b2k_halo_destroy(a->halo)); a->halo = NULL; }
   int64_t off[8] = {0};
   for (PetscInt q = 0; q < a->nsend && q < 8; q++) off[q] = a->sendoff ? a->sendoff[q] : 0;
@@ -140,6 +142,20 @@ static PetscErrorCode MatBuildLocalTranspose_B200CSR(Mat A)
   return PETSC_SUCCESS;
 }
 
+/* collective, on the first MatMultTranspose: the peer-memory halo with the roles exchanged — what I receive in MatMult (ghost
+   segment p, contiguous in zghost) I now push to its owner, and from every rank I send to in MatMult I receive the contributions
+   to the entries I sent (in the order of my send list) */
+static PetscErrorCode MatHaloReverseSetUp_B200CSR(Mat A)
+{
+  Mat_B200CSR *a = (Mat_B200CSR *)A->data;
+  B2KComm comm = B2KCommWorld();
+  int64_t off[8] = {0};
+  PetscInt roff = 0;
+  for (PetscInt p = 0; p < a->nrecv && p < 8; p++) { off[p] = roff; roff += a->recvcount[p]; }
+  B2KCall(b2k_halo_create(comm->nccl, a->nsend, a->sendrank, a->sendcount, a->nrecv, a->recvrank, a->recvcount, NULL, off, &a->halo_rev));
+  return PETSC_SUCCESS;
+}
+
 /* y = A^T x with A row-partitioned: local y_own = A_own^T x, ghost-column contributions z = A_gh^T x are sent to the owners
    of those columns (the halo plan run backwards) and accumulated in peer order — deterministic.  This is PETSc's
    MatMultTranspose_MPIAIJ (local transpose products + VecScatter SCATTER_REVERSE/ADD_VALUES), reached from
@@ -154,10 +170,27 @@ static PetscErrorCode MatMultTranspose_B200CSR(Mat A, Vec x, Vec y)
   PetscCall(B2KCommGetRank(comm, NULL, &size));
   if (!a->ATown) PetscCall(MatBuildLocalTranspose_B200CSR(A));
   B2KCall(b2k_csr_spmv(ctx, a->ATown, x->array, NULL, y->array));
-  if (size == 1 || (a->nghost == 0 && a->nsend == 0)) return PETSC_SUCCESS;
-  PetscCheck(a->halo_set, PETSC_ERR_ORDER, "MatB200CSRSetHalo() must be called before MatMultTranspose() on more than one rank");
+  if (size == 1 || (!a->halo && a->nghost == 0 && a->nsend == 0)) return PETSC_SUCCESS;    /* with a peer-memory halo every rank takes part */
+  PetscCheck(a->halo_set || a->halo, PETSC_ERR_ORDER, "MatB200CSRSetHalo() must be called before MatMultTranspose() on more than one rank");
   PetscCheck(comm->kind == 1, PETSC_ERR_SUP, "b200csr needs the NCCL communicator (B2KCommInitNCCL)");
   if (a->nghost) B2KCall(b2k_csr_spmv(ctx, a->ATgh, x->array, NULL, a->zghost));
+  if (a->halo) {
+    /* reverse halo over NVLink peer memory (default on one box): push + flags instead of grouped ncclSend/ncclRecv, then the
+       contributions are added in the order of the send list — the same fixed order as below */
+    int bad = 0;
+    if (!a->halo_rev) PetscCall(MatHaloReverseSetUp_B200CSR(A));
+    B2KCall(b2k_halo_error(a->halo_rev, &bad));
+    PetscCheck(!bad, PETSC_ERR_LIB, "peer-memory reverse halo exchange timed out (code %d): a rank did not take part in MatMultTranspose", bad);
+    const double *rb = NULL;
+    B2KCall(b2k_halo_exchange(a->halo_rev, a->zghost, &rb));
+    PetscInt so = 0;
+    for (PetscInt q = 0; q < a->nsend; q++) {
+      if (a->d_sendidx) B2KCall(b2k_scatter_add(ctx, y->array, a->d_sendidx + so, rb + so, a->sendcount[q]));
+      else B2KCall(b2k_axpby(ctx, y->array + a->sendoff[q], A->n, rb + so, a->sendcount[q], a->sendcount[q], 1, 1.0, 1.0));
+      so += a->sendcount[q];
+    }
+    return PETSC_SUCCESS;
+  }
   if (a->nsendtot && !a->rbuf) B2KCall(b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot));
   B2KCall(b2k_comm_group_start(comm->nccl));
   PetscInt roff = 0, soff = 0;
@@ -194,6 +227,7 @@ static PetscErrorCode MatDestroy_B200CSR(Mat A)
   if (!a) return PETSC_SUCCESS;
   b2k_ctx ctx = CTX();
   if (ctx) {
+    if (a->halo_rev) b2k_halo_destroy(a->halo_rev); /* collective */
     if (a->halo) b2k_halo_destroy(a->halo);         /* collective */
     b2k_csr_destroy(ctx, a->ATown); b2k_csr_destroy(ctx, a->ATgh);
     b2k_free(ctx, a->zghost); b2k_free(ctx, a->rbuf); b2k_free(ctx, a->gblock);

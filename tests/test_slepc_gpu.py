@@ -703,13 +703,16 @@ def test_eps_generalized_sinvert_large_vs_scipy_gpu():
 
 
 # ---- the asynchronous Krylov cycle (ops.krylov_steps of BV type b200) against the step-by-step path -----------------------------------
-def _solve_with_async(flag, build, hermitian, nev, ncv, which=None, x0=None):
+def _solve_with_async(flag, build, hermitian, nev, ncv, which=None, x0=None, fuse="1"):
     old, oldf = os.environ.get("B2K_BV_ASYNC"), os.environ.get("B2K_BV_FUSE")
     os.environ["B2K_BV_ASYNC"] = flag               # read when the BV is created
     # the step-by-step path fuses the second pass' dot into the update sweep only once it has seen a refinement (adaptive), the
     # asynchronous cycle always does; B2K_BV_FUSE=1 makes both fuse from the first column on, so that the only thing compared
     # is who takes the decisions (the fused and the separate dot sweep sum in different orders: rounding-level differences)
-    os.environ["B2K_BV_FUSE"] = "1"
+    if fuse is not None:
+        os.environ["B2K_BV_FUSE"] = fuse
+    else:
+        os.environ.pop("B2K_BV_FUSE", None)
     try:
         M = build()
         eps = SL.EPS(M, hermitian=hermitian)
@@ -785,3 +788,32 @@ def test_async_krylov_cycle_hands_a_breakdown_to_the_synchronous_path():
     assert a["reason"] > 0 and a["nconv"] == b["nconv"] >= 2 and a["its"] == b["its"]
     assert a["lam"] == b["lam"]
     assert abs(a["lam"][0][0] - 9.0) < 1e-12 and abs(a["lam"][1][0] - 9.0) < 1e-12      # 9 has multiplicity 800
+
+
+@pytest.mark.parametrize("case", ["lanczos", "arnoldi_markov"])
+def test_async_krylov_cycle_default_schedules_agree_to_rounding(case):
+    """default settings (adaptive fusion): the asynchronous cycle probes with the 2-sweep schedule, switches to the speculative
+    3-sweep one when DGKS refines (Lanczos: every column) and stays on 2 sweeps when it does not (Arnoldi on the Markov matrix);
+    the separate and the fused dot sweep sum in different orders, so the comparison with the step-by-step path is to rounding:
+    same converged count, eigenvalues to 1e-10 relative (the north star's bar), residuals below tol"""
+    if case == "lanczos":
+        args = (lambda: SL.Mat.laplacian(2, 160, 120), True, 6, 28)
+        kw = {}
+    else:
+        from slepc_b200 import matgen
+        m = 80
+        N = matgen.markov_size(m)
+        A = O.markov_model(m)
+        x0 = np.zeros(N); x0[:3] = 1.0
+        args = (lambda: SL.Mat.b200csr(A), False, 6, SL.PETSC_DETERMINE)
+        kw = dict(which=SL.EPS_LARGEST_REAL, x0=x0)
+    a = _solve_with_async("1", *args, fuse=None, **kw)
+    b = _solve_with_async("0", *args, fuse=None, **kw)
+    assert a["reason"] > 0 and b["reason"] > 0 and a["nconv"] >= args[2] and b["nconv"] >= args[2]
+    la = np.array([x[0] for x in a["lam"][:args[2]]]); lb = np.array([x[0] for x in b["lam"][:args[2]]])
+    assert np.allclose(la, lb, rtol=1e-10, atol=0), (la, lb)
+    assert max(a["errs"][:args[2]]) < 5e-8
+    steps = a["counters"][1]
+    assert b["syncs"] - a["syncs"] > 0.5 * steps, (a["syncs"], b["syncs"], steps)
+    if case == "arnoldi_markov":
+        assert a["counters"][0] < 1.2 * steps           # the 2-sweep schedule: about one Gram-Schmidt pass per step, not two
