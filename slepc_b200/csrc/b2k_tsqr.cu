@@ -7,8 +7,7 @@
  * Here the tree has three levels, all Householder (unconditionally stable, unlike the Gram-matrix methods CHOL / SVQB):
  *   1. inside a CTA, a FLAT tree over tiles of 128 rows: [R ; tile] -> [R' ; 0] by k reflectors whose only non-trivial part lies
  *      in the tile (the structure of LAPACK's tpqrt with a rectangular pentagon), so the reflectors are stored IN PLACE of the
- *      tile, plus two scalars (tau, 1/(alpha-beta)) per reflector; every warp keeps its columns of the tile in registers and the
- *      k-1-j inner products of a step are reduced over the lanes by a transposed butterfly (NC/2 + NC/4 + … shuffles, not 5 NC);
+ *      tile, plus two scalars (tau, 1/(alpha-beta)) per reflector;
  *   2. over the CTAs of a GPU: the k x k triangles go to the host (<= 1184 blocks), one LAPACK geqrf/orgqr of the stack;
  *   3. over the GPUs: the same on the gathered per-rank triangles (host/bv.c).
  * Q is formed by the backward kernel: every CTA starts from its k x k block W of the upper levels' orthogonal factor and applies
@@ -29,80 +28,42 @@ __device__ __forceinline__ double ts_warp_sum(double v)
   return v;
 }
 
-/* sum over the 32 lanes of NC values per lane with a transposed butterfly: in round t the lanes exchange HALF of their live values
-   (offset 16 >> t), so NC/2 + NC/4 + … + 1 + (5 - log2 NC) shuffles replace 5 NC.  On return v[0] holds the total of column
-   *cidx (the same in the 32/NC lanes that share it); the order of the additions is fixed. */
-template <int NC>
-__device__ __forceinline__ void ts_reduce_t(double (&v)[NC], int lane, int *cidx)
-{
-  int col = 0;
-#pragma unroll
-  for (int half = NC / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; i++) {
-      const double send = hi ? v[i] : v[i + half], keep = hi ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    if (hi) col += half;
-  }
-#pragma unroll
-  for (int off = 16 / NC; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-  *cidx = col;
-}
-
 template <int KP>
-__host__ __device__ constexpr size_t ts_fwd_smem() { return sizeof(double) * (2 * TS_ROWS + (size_t)KP * KP + 2 * KP + KP); }
+__host__ __device__ constexpr size_t ts_fwd_smem() { return sizeof(double) * ((size_t)KP * TS_ROWS + (size_t)KP * KP + 2 * KP); }
 template <int KP>
-__host__ __device__ constexpr size_t ts_bwd_smem() { return sizeof(double) * ((size_t)KP * TS_ROWS + (size_t)KP * KP + 2 * KP + KP); }
+__host__ __device__ constexpr size_t ts_bwd_smem() { return sizeof(double) * ((size_t)KP * TS_ROWS + (size_t)KP * KP + 2 * KP); }
 
 /* forward: R of the rows [blockIdx.x*rpc, +rpc) into Rblk[blockIdx.x] (k x k column-major, upper triangular); STORE: reflectors
-   over V and (tau, s) into coef[tile][2][k].  Warp w owns columns w, w+8, …: they stay in REGISTERS for the whole tile (4 rows per
-   lane), only the pivot column of a step travels through shared memory (double-buffered: one block barrier per step). */
-#define TS_MINB(KP) ((KP) == 64 ? 2 : ((KP) == 32 ? 3 : 4))     /* resident CTAs per SM the register budget is held to */
+   over V and (tau, s) into coef[tile][2][k] */
 template <int KP, bool STORE>
-__global__ void __launch_bounds__(TS_THREADS, TS_MINB(KP)) k_tsqr_fwd(double *__restrict__ V, int64_t ld, int64_t n, int k, int64_t rpc,
+__global__ void __launch_bounds__(TS_THREADS) k_tsqr_fwd(double *__restrict__ V, int64_t ld, int64_t n, int k, int64_t rpc,
                                                            double *__restrict__ Rblk, double *__restrict__ coef)
 {
   extern __shared__ double ts_sm[];
-  constexpr int NC = KP / TS_WARPS;
-  double *xb = ts_sm;                        /* [2][128] pivot column of the step                                */
-  double *Rs = xb + 2 * TS_ROWS;             /* [KP][KP] strict upper triangle, row j at Rs + j*KP               */
-  double *Rd = Rs + KP * KP;                 /* [2][KP] diagonal, double-buffered by tile parity                 */
-  double *tws = Rd + 2 * KP;                 /* [8 warps][NC] tau*w of the step, broadcast inside a warp         */
+  double *A = ts_sm;                         /* [KP][128] tile, column-major                                   */
+  double *Rs = A + KP * TS_ROWS;             /* [KP][KP] strict upper triangle, row j at Rs + j*KP              */
+  double *Rd = Rs + KP * KP;                 /* [2][KP] diagonal, double-buffered by tile parity                */
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = (int64_t)blockIdx.x * rpc, r1 = min(n, r0 + rpc);
   for (int i = threadIdx.x; i < KP * KP + 2 * KP; i += TS_THREADS) Rs[i] = 0.0;
-  int par = 0, step = 0;
+  int par = 0;
   for (int64_t tr = r0; tr < r1; tr += TS_ROWS) {
-    double a[NC][4];
-#pragma unroll
-    for (int m = 0; m < NC; m++) {
-      const int c = warp + TS_WARPS * m;
+    __syncthreads();
+    for (int c = warp; c < k; c += TS_WARPS) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int64_t r = tr + lane + 32 * i;
-        a[m][i] = (c < k && r < r1) ? V[(int64_t)c * ld + r] : 0.0;
+        A[c * TS_ROWS + lane + 32 * i] = (r < r1) ? V[(int64_t)c * ld + r] : 0.0;
       }
     }
+    __syncthreads();
     const double *Rcur = Rd + par * KP;
     double *Rnew = Rd + (par ^ 1) * KP;
     const int64_t tile = tr / TS_ROWS;
-    for (int j = 0; j < k; j++, step++) {
-      double *xj = xb + (step & 1) * TS_ROWS;               /* alternates across tile boundaries too (k may be odd) */
-      if (warp == (j & (TS_WARPS - 1))) {
-        const int mj = j >> 3;
-#pragma unroll
-        for (int m = 0; m < NC; m++)
-          if (m == mj) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) xj[lane + 32 * i] = a[m][i];
-          }
-      }
-      __syncthreads();                          /* also orders the first step of a tile after the last one of the previous tile */
+    for (int j = 0; j < k; j++) {
       double x[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) x[i] = xj[lane + 32 * i];
+      for (int i = 0; i < 4; i++) x[i] = A[j * TS_ROWS + lane + 32 * i];
       const double ss = ts_warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);   /* same value in every warp */
       const double alpha = Rcur[j];
       double beta = alpha, tau = 0.0, s = 0.0;
@@ -115,38 +76,28 @@ __global__ void __launch_bounds__(TS_THREADS, TS_MINB(KP)) k_tsqr_fwd(double *__
         Rnew[j] = beta;
         if (STORE) { coef[tile * 2 * k + j] = tau; coef[tile * 2 * k + k + j] = s; }
       }
-      if (tau != 0.0 && warp + TS_WARPS * (NC - 1) > j) {     /* this warp still owns a column to the right of the pivot */
-        double dot[NC];
+      if (tau != 0.0) {
+        for (int c = j + 1 + warp; c < k; c += TS_WARPS) {
+          double a[4];
 #pragma unroll
-        for (int m = 0; m < NC; m++) dot[m] = x[0] * a[m][0] + x[1] * a[m][1] + x[2] * a[m][2] + x[3] * a[m][3];
-        int ci;
-        ts_reduce_t<NC>(dot, lane, &ci);
-        const int c = warp + TS_WARPS * ci;
-        double twl = 0.0;
-        if (c > j && c < k) twl = tau * (Rs[j * KP + c] + s * dot[0]);
-        __syncwarp();
-        if ((lane & (32 / NC - 1)) == 0) {
-          if (c > j && c < k) Rs[j * KP + c] -= twl;
-          tws[warp * NC + ci] = twl;
+          for (int i = 0; i < 4; i++) a[i] = A[c * TS_ROWS + lane + 32 * i];
+          const double dot = ts_warp_sum(x[0] * a[0] + x[1] * a[1] + x[2] * a[2] + x[3] * a[3]);
+          const double tw = tau * (Rs[j * KP + c] + s * dot);
+          __syncwarp();
+          if (lane == 0) Rs[j * KP + c] -= tw;
+          const double f = tw * s;
+#pragma unroll
+          for (int i = 0; i < 4; i++) A[c * TS_ROWS + lane + 32 * i] = a[i] - f * x[i];
         }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < NC; m++) {
-          const double f = tws[warp * NC + m] * s;            /* 0 for the columns left of (and at) the pivot: they hold reflectors */
-#pragma unroll
-          for (int i = 0; i < 4; i++) a[m][i] -= f * x[i];
-        }
-        __syncwarp();
       }
+      __syncthreads();
     }
     if (STORE) {
-#pragma unroll
-      for (int m = 0; m < NC; m++) {
-        const int c = warp + TS_WARPS * m;
+      for (int c = warp; c < k; c += TS_WARPS) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int64_t r = tr + lane + 32 * i;
-          if (c < k && r < r1) V[(int64_t)c * ld + r] = a[m][i];
+          if (r < r1) V[(int64_t)c * ld + r] = A[c * TS_ROWS + lane + 32 * i];
         }
       }
     }
@@ -163,21 +114,18 @@ __global__ void __launch_bounds__(TS_THREADS, TS_MINB(KP)) k_tsqr_fwd(double *__
 
 /* backward: rows of CTA b <- Q_b * W_b, Q_b = product of the tiles' reflectors stored by the forward kernel */
 template <int KP>
-__global__ void __launch_bounds__(TS_THREADS, TS_MINB(KP) > 3 ? 3 : TS_MINB(KP)) k_tsqr_bwd(double *__restrict__ V, int64_t ld, int64_t n, int k, int64_t rpc,
+__global__ void __launch_bounds__(TS_THREADS) k_tsqr_bwd(double *__restrict__ V, int64_t ld, int64_t n, int k, int64_t rpc,
                                                            const double *__restrict__ Wblk, const double *__restrict__ coef)
 {
   extern __shared__ double ts_sm[];
   double *X = ts_sm;                         /* [KP][128] reflectors of the tile                               */
   double *Ct = X + KP * TS_ROWS;             /* [KP][KP] top block, column c at Ct + c*KP                        */
   double *tau = Ct + KP * KP, *sc = tau + KP;
-  double *tws = sc + KP;                     /* [8 warps][NC]                                                     */
   constexpr int NC = KP / TS_WARPS;          /* columns a warp carries                                            */
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = (int64_t)blockIdx.x * rpc, r1 = min(n, r0 + rpc);
   if (r0 >= r1) return;
   const double *W = Wblk + (size_t)blockIdx.x * k * k;
-  for (int e = threadIdx.x; e < KP * KP; e += TS_THREADS) Ct[e] = 0.0;
-  __syncthreads();
   for (int e = threadIdx.x; e < k * k; e += TS_THREADS) Ct[(e / k) * KP + (e % k)] = W[e];
   const int64_t ntile = (r1 - r0 + TS_ROWS - 1) / TS_ROWS;
   for (int64_t t = ntile - 1; t >= 0; t--) {
@@ -204,19 +152,23 @@ __global__ void __launch_bounds__(TS_THREADS, TS_MINB(KP) > 3 ? 3 : TS_MINB(KP))
       double dot[NC];
 #pragma unroll
       for (int m = 0; m < NC; m++) dot[m] = x[0] * q[m][0] + x[1] * q[m][1] + x[2] * q[m][2] + x[3] * q[m][3];
-      int ci;
-      ts_reduce_t<NC>(dot, lane, &ci);
-      const int c = warp + TS_WARPS * ci;                      /* c < KP always; columns >= k carry zeros */
-      const double twl = tj * (Ct[c * KP + j] + sj * dot[0]);
-      __syncwarp();
-      if ((lane & (32 / NC - 1)) == 0) {
-        Ct[c * KP + j] -= twl;
-        tws[warp * NC + ci] = twl;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int m = 0; m < NC; m++) dot[m] += __shfl_xor_sync(0xffffffffu, dot[m], o);
+      }
+      double tw[NC];
+#pragma unroll
+      for (int m = 0; m < NC; m++) {
+        const int c = warp + TS_WARPS * m;
+        tw[m] = (c < k) ? tj * (Ct[c * KP + j] + sj * dot[m]) : 0.0;
       }
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < NC; m++) {
-        const double f = tws[warp * NC + m] * sj;
+        const int c = warp + TS_WARPS * m;
+        if (lane == 0 && c < k) Ct[c * KP + j] -= tw[m];
+        const double f = tw[m] * sj;
 #pragma unroll
         for (int i = 0; i < 4; i++) q[m][i] -= f * x[i];
       }
