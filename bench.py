@@ -383,132 +383,141 @@ def run_b200(args, wl):
     # ---------------- e2e leg: host CSR + host start vector in, Ritz vectors out -------------------------------
     e2e = None
     if not args.no_e2e:
-        h = build_host_csr_slab(lib, wl, nx_total, rank, world)
-        def pinned_f64(nelem):                      # the step's host buffers are pinned, like the CSR arrays
-            p = ctypes.c_void_p()
-            assert lib.b2k_host_alloc(ctypes.byref(p), 8 * nelem) == 0
-            return np.frombuffer((ctypes.c_char * (8 * nelem)).from_address(p.value), dtype=np.float64), p
-        v0, v0_p = pinned_f64(h["nloc"])
-        v0[:] = np.sin(0.37 * np.arange(h["row0"], h["row0"] + h["nloc"]) + 0.1) + 0.5
-        out, out_p = pinned_f64(h["nloc"])
-        hb0, db0 = ctypes.c_uint64(), ctypes.c_uint64()
-        lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb0), ctypes.byref(db0))
-        barrier()
-        t0 = time.perf_counter()
-        A = SL.Mat()
-        S.MatCreateB200CSR(h["N"], h["N"], h["row0"], h["row0"] + h["nloc"], h["rowptr"][1], h["colidx"][1], h["val"][1],
-                           h["row0"], h["row0"] + h["nloc"], A.ref)
-        if world > 1:
-            hl = h["halo"]
-            i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
-            rr, rc, sr, sc, si = i32(hl["recvrank"]), i32(hl["recvcount"]), i32(hl["sendrank"]), i32(hl["sendcount"]), i32(hl["sendidx"])
-            pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-            S.MatB200CSRSetHalo(A.h, len(rr), pp(rr), pp(rc), len(sr), pp(sr), pp(sc), pp(si))
-        e2 = SL.EPS(A, hermitian=True)
-        S.EPSSetDimensions(e2.h, wl["nev"], wl["ncv"], SL.PETSC_DETERMINE)
-        S.EPSSetTolerances(e2.h, TOL, 100000000)
-        x0, _ = A.create_vecs()
-        x0.set_values(v0)
-        S.EPSSetInitialSpace(e2.h, 1, (ctypes.c_void_p * 1)(x0.h))
-        ke = 0
-        for _ in range(args.steps):
-            ke += e2.cycles(1)
-        bv2 = e2.bv()
-        steps2 = bv2.counters()[1]
-        checksum = 0.0
-        for j in range(wl["nev"]):                 # device→host read of the result: the nev leading Ritz vectors
-            S.BVGetColumnHost(bv2.h, j, out.ctypes.data_as(ctypes.c_void_p))
-            checksum += float(out[0])
-        barrier()
-        dt = allmax(time.perf_counter() - t0)
-        hb1, db1 = ctypes.c_uint64(), ctypes.c_uint64()
-        lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb1), ctypes.byref(db1))
-        e2e = {"value": rows_global * steps2 / dt, "unit": UNIT, "h2d_bytes_per_step": (hb1.value - hb0.value) / max(ke, 1),
-               "d2h_bytes_per_step": (db1.value - db0.value) / max(ke, 1), "seconds": dt, "steps": ke, "lanczos_steps": steps2,
-               "what": "MatCreateB200CSR(host CSR, pinned) + EPSSetInitialSpace(host vector) + K restart cycles (incl. the first, "
-                       "unrestarted one) + BVGetColumnHost of the nev leading Ritz vectors; wall clock, max over ranks"}
-        e2.destroy()
-        x0.destroy()
-        A.destroy()
-        del v0, out
-        for p in (h["rowptr"][1], h["colidx"][1], h["val"][1], v0_p, out_p):
-            lib.b2k_host_free(p)
-        del h
+        try:
+            h = build_host_csr_slab(lib, wl, nx_total, rank, world)
+            def pinned_f64(nelem):                      # the step's host buffers are pinned, like the CSR arrays
+                p = ctypes.c_void_p()
+                assert lib.b2k_host_alloc(ctypes.byref(p), 8 * nelem) == 0
+                return np.frombuffer((ctypes.c_char * (8 * nelem)).from_address(p.value), dtype=np.float64), p
+            v0, v0_p = pinned_f64(h["nloc"])
+            v0[:] = np.sin(0.37 * np.arange(h["row0"], h["row0"] + h["nloc"]) + 0.1) + 0.5
+            out, out_p = pinned_f64(h["nloc"])
+            hb0, db0 = ctypes.c_uint64(), ctypes.c_uint64()
+            lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb0), ctypes.byref(db0))
+            barrier()
+            t0 = time.perf_counter()
+            A = SL.Mat()
+            S.MatCreateB200CSR(h["N"], h["N"], h["row0"], h["row0"] + h["nloc"], h["rowptr"][1], h["colidx"][1], h["val"][1],
+                               h["row0"], h["row0"] + h["nloc"], A.ref)
+            if world > 1:
+                hl = h["halo"]
+                i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+                rr, rc, sr, sc, si = i32(hl["recvrank"]), i32(hl["recvcount"]), i32(hl["sendrank"]), i32(hl["sendcount"]), i32(hl["sendidx"])
+                pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+                S.MatB200CSRSetHalo(A.h, len(rr), pp(rr), pp(rc), len(sr), pp(sr), pp(sc), pp(si))
+            e2 = SL.EPS(A, hermitian=True)
+            S.EPSSetDimensions(e2.h, wl["nev"], wl["ncv"], SL.PETSC_DETERMINE)
+            S.EPSSetTolerances(e2.h, TOL, 100000000)
+            x0, _ = A.create_vecs()
+            x0.set_values(v0)
+            S.EPSSetInitialSpace(e2.h, 1, (ctypes.c_void_p * 1)(x0.h))
+            ke = 0
+            for _ in range(args.steps):
+                ke += e2.cycles(1)
+            bv2 = e2.bv()
+            steps2 = bv2.counters()[1]
+            checksum = 0.0
+            for j in range(wl["nev"]):                 # device→host read of the result: the nev leading Ritz vectors
+                S.BVGetColumnHost(bv2.h, j, out.ctypes.data_as(ctypes.c_void_p))
+                checksum += float(out[0])
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            hb1, db1 = ctypes.c_uint64(), ctypes.c_uint64()
+            lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb1), ctypes.byref(db1))
+            e2e = {"value": rows_global * steps2 / dt, "unit": UNIT, "h2d_bytes_per_step": (hb1.value - hb0.value) / max(ke, 1),
+                   "d2h_bytes_per_step": (db1.value - db0.value) / max(ke, 1), "seconds": dt, "steps": ke, "lanczos_steps": steps2,
+                   "what": "MatCreateB200CSR(host CSR, pinned) + EPSSetInitialSpace(host vector) + K restart cycles (incl. the first, "
+                           "unrestarted one) + BVGetColumnHost of the nev leading Ritz vectors; wall clock, max over ranks"}
+            e2.destroy()
+            x0.destroy()
+            A.destroy()
+            del v0, out
+            for p in (h["rowptr"][1], h["colidx"][1], h["val"][1], v0_p, out_p):
+                lib.b2k_host_free(p)
+            del h
+        except Exception as ex:                     # noqa: BLE001 — a failed optional leg must not cost the headline line
+            e2e = {"error": (type(ex).__name__ + ": " + str(ex))[:400]}
 
     # ---------------- latency leg: the SAME global 1024^2 problem on every N, solved to convergence ----------------
     lat = None
     if not args.no_latency:
-        g = 1024
-        Mt = SL.Mat.laplacian(2, g, g)
-        et = SL.EPS(Mt, hermitian=True)
-        S.EPSSetDimensions(et.h, 20, 64, SL.PETSC_DETERMINE)
-        S.EPSSetTolerances(et.h, TOL, SL.PETSC_CURRENT)
-        barrier()
-        s0, l0 = syncs(), launches()
-        t0 = time.perf_counter()
-        et.solve()
-        barrier()
-        dt = allmax(time.perf_counter() - t0)
-        nst = et.bv().counters()[1]
-        lat = {"host_syncs_per_lanczos_step": (syncs() - s0) / max(nst, 1), "kernel_launches_per_lanczos_step": (launches() - l0) / max(nst, 1),"workload": "2-D Laplacian 1024x1024 (global, split over the ranks), nev=20 ncv=64: launch/latency-bound regime",
-               "seconds": dt, "restarts": et.its, "nconv": et.nconv, "lanczos_steps": nst, "us_per_lanczos_step": 1e6 * dt / max(nst, 1)}
-        lat["max_rel_residual"] = max(et.error(i) for i in range(et.nconv)) if et.nconv else None
-        et.destroy()
-        Mt.destroy()
+        try:
+            g = 1024
+            Mt = SL.Mat.laplacian(2, g, g)
+            et = SL.EPS(Mt, hermitian=True)
+            S.EPSSetDimensions(et.h, 20, 64, SL.PETSC_DETERMINE)
+            S.EPSSetTolerances(et.h, TOL, SL.PETSC_CURRENT)
+            barrier()
+            s0, l0 = syncs(), launches()
+            t0 = time.perf_counter()
+            et.solve()
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            nst = et.bv().counters()[1]
+            lat = {"host_syncs_per_lanczos_step": (syncs() - s0) / max(nst, 1), "kernel_launches_per_lanczos_step": (launches() - l0) / max(nst, 1),"workload": "2-D Laplacian 1024x1024 (global, split over the ranks), nev=20 ncv=64: launch/latency-bound regime",
+                   "seconds": dt, "restarts": et.its, "nconv": et.nconv, "lanczos_steps": nst, "us_per_lanczos_step": 1e6 * dt / max(nst, 1)}
+            lat["max_rel_residual"] = max(et.error(i) for i in range(et.nconv)) if et.nconv else None
+            et.destroy()
+            Mt.destroy()
+        except Exception as ex:                     # noqa: BLE001 — a failed optional leg must not cost the headline line
+            lat = {"error": (type(ex).__name__ + ": " + str(ex))[:400]}
 
     # ---------------- time-to-solution of the north-star problem, strong-scaled, checked before printing ----------------
     tts = None
     if args.tts != "none":
-        tw = TTS[args.tts]
-        g, dim = tw["g"], tw["dim"]
-        t0 = time.perf_counter()
-        Mt = SL.Mat.laplacian(dim, g, g, g)
-        et = SL.EPS(Mt, hermitian=True)
-        S.EPSSetDimensions(et.h, tw["nev"], tw["ncv"], SL.PETSC_DETERMINE)
-        S.EPSSetTolerances(et.h, TOL, SL.PETSC_CURRENT)
-        barrier()
-        t_build = time.perf_counter() - t0
-        hbm_tts = hbm_used() - hbm0
-        l0 = launches()
-        t0 = time.perf_counter()
-        et.solve()
-        barrier()
-        dt = allmax(time.perf_counter() - t0)
-        hbm_tts = max(hbm_tts, hbm_used() - hbm0)
-        nconv = et.nconv
-        vals = [et.eigenvalue(i)[0] for i in range(nconv)]
-        errs = [et.error(i) for i in range(nconv)]
-        th = 2 - 2 * np.cos(np.arange(max(1, g - 40), g + 1) * np.pi / (g + 1))       # the top 40 1-D values are enough
-        analytic = (th[:, None, None] + th[None, :, None] + th[None, None, :]).ravel()
-        dist_an = float(max(np.min(np.abs(analytic - x)) / abs(x) for x in vals)) if vals else None
-        nst = et.bv().counters()[1]
-        checks = {"nconv_ge_nev": nconv >= tw["nev"], "residuals_lt_5tol": bool(errs) and max(errs) < 5 * TOL,
-                  "values_within_1e-10_of_analytic": dist_an is not None and dist_an < 1e-10, "reason_converged": et.reason > 0}
-        if not all(checks.values()):
-            raise SystemExit(f"bench.py: the {tw['name']} solve on {world} GPU(s) FAILED its checks {checks}: nconv={nconv} "
-                             f"max residual={max(errs) if errs else None} distance to analytic={dist_an}; nothing is printed for a wrong answer")
-        tts = {"workload": tw["name"], "n_gpus": world, "seconds": dt, "seconds_build": t_build, "its": et.its, "nconv": nconv,
-               "lanczos_steps": nst, "ms_per_lanczos_step": 1e3 * dt / max(nst, 1), "max_rel_residual": max(errs),
-               "max_rel_dist_to_analytic": dist_an, "values": vals[:tw["nev"]], "checks": checks, "kernel_launches": launches() - l0,
-               "hbm_bytes_per_gpu": hbm_tts,
-               "timed": "EPSSolve wall clock (first start-vector op to convergence), barrier + device sync on both sides, max over ranks; matrix generation reported separately"}
-        mark = os.path.join(tempfile.gettempdir(), f"b2k_tts_{args.tts}_n1.json")
-        if rank == 0:
-            if world == 1:
-                try:
-                    json.dump({"seconds": dt, "when": time.time()}, open(mark, "w"))
-                except Exception:
-                    pass
-            elif os.path.exists(mark):
-                try:
-                    t1 = json.load(open(mark))
-                    if time.time() - t1["when"] < 6 * 3600:
-                        tts["strong_efficiency"] = t1["seconds"] / (world * dt)
-                        tts["strong_efficiency_from"] = f"N=1 run of this lease ({t1['seconds']:.2f} s, {mark})"
-                except Exception:
-                    pass
-        et.destroy()
-        Mt.destroy()
+        try:
+            tw = TTS[args.tts]
+            g, dim = tw["g"], tw["dim"]
+            t0 = time.perf_counter()
+            Mt = SL.Mat.laplacian(dim, g, g, g)
+            et = SL.EPS(Mt, hermitian=True)
+            S.EPSSetDimensions(et.h, tw["nev"], tw["ncv"], SL.PETSC_DETERMINE)
+            S.EPSSetTolerances(et.h, TOL, SL.PETSC_CURRENT)
+            barrier()
+            t_build = time.perf_counter() - t0
+            hbm_tts = hbm_used() - hbm0
+            l0 = launches()
+            t0 = time.perf_counter()
+            et.solve()
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            hbm_tts = max(hbm_tts, hbm_used() - hbm0)
+            nconv = et.nconv
+            vals = [et.eigenvalue(i)[0] for i in range(nconv)]
+            errs = [et.error(i) for i in range(nconv)]
+            th = 2 - 2 * np.cos(np.arange(max(1, g - 40), g + 1) * np.pi / (g + 1))       # the top 40 1-D values are enough
+            analytic = (th[:, None, None] + th[None, :, None] + th[None, None, :]).ravel()
+            dist_an = float(max(np.min(np.abs(analytic - x)) / abs(x) for x in vals)) if vals else None
+            nst = et.bv().counters()[1]
+            checks = {"nconv_ge_nev": nconv >= tw["nev"], "residuals_lt_5tol": bool(errs) and max(errs) < 5 * TOL,
+                      "values_within_1e-10_of_analytic": dist_an is not None and dist_an < 1e-10, "reason_converged": et.reason > 0}
+            if not all(checks.values()):
+                raise SystemExit(f"bench.py: the {tw['name']} solve on {world} GPU(s) FAILED its checks {checks}: nconv={nconv} "
+                                 f"max residual={max(errs) if errs else None} distance to analytic={dist_an}; nothing is printed for a wrong answer")
+            tts = {"workload": tw["name"], "n_gpus": world, "seconds": dt, "seconds_build": t_build, "its": et.its, "nconv": nconv,
+                   "lanczos_steps": nst, "ms_per_lanczos_step": 1e3 * dt / max(nst, 1), "max_rel_residual": max(errs),
+                   "max_rel_dist_to_analytic": dist_an, "values": vals[:tw["nev"]], "checks": checks, "kernel_launches": launches() - l0,
+                   "hbm_bytes_per_gpu": hbm_tts,
+                   "timed": "EPSSolve wall clock (first start-vector op to convergence), barrier + device sync on both sides, max over ranks; matrix generation reported separately"}
+            mark = os.path.join(tempfile.gettempdir(), f"b2k_tts_{args.tts}_n1.json")
+            if rank == 0:
+                if world == 1:
+                    try:
+                        json.dump({"seconds": dt, "when": time.time()}, open(mark, "w"))
+                    except Exception:
+                        pass
+                elif os.path.exists(mark):
+                    try:
+                        t1 = json.load(open(mark))
+                        if time.time() - t1["when"] < 6 * 3600:
+                            tts["strong_efficiency"] = t1["seconds"] / (world * dt)
+                            tts["strong_efficiency_from"] = f"N=1 run of this lease ({t1['seconds']:.2f} s, {mark})"
+                    except Exception:
+                        pass
+            et.destroy()
+            Mt.destroy()
+        except Exception as ex:                     # noqa: BLE001 — a failed optional leg must not cost the headline line
+            tts = {"error": (type(ex).__name__ + ": " + str(ex))[:400]}
 
     # ---------------- baselines on the same box (rank 0, N=1 only) -------------------------------------------------
     cpu = None
