@@ -396,15 +396,24 @@ def run_b200(args, wl):
             lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb0), ctypes.byref(db0))
             barrier()
             t0 = time.perf_counter()
+            ph = {}
+
+            def phase(name, t_prev):
+                S.B2KDeviceSynchronize()
+                t = time.perf_counter()
+                ph[name] = t - t_prev
+                return t
             A = SL.Mat()
             S.MatCreateB200CSR(h["N"], h["N"], h["row0"], h["row0"] + h["nloc"], h["rowptr"][1], h["colidx"][1], h["val"][1],
                                h["row0"], h["row0"] + h["nloc"], A.ref)
+            tp = phase("matrix_upload_and_sell", t0)
             if world > 1:
                 hl = h["halo"]
                 i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
                 rr, rc, sr, sc, si = i32(hl["recvrank"]), i32(hl["recvcount"]), i32(hl["sendrank"]), i32(hl["sendcount"]), i32(hl["sendidx"])
                 pp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
                 S.MatB200CSRSetHalo(A.h, len(rr), pp(rr), pp(rc), len(sr), pp(sr), pp(sc), pp(si))
+            tp = phase("halo_setup", tp)
             e2 = SL.EPS(A, hermitian=True)
             S.EPSSetDimensions(e2.h, wl["nev"], wl["ncv"], SL.PETSC_DETERMINE)
             S.EPSSetTolerances(e2.h, TOL, 100000000)
@@ -412,20 +421,25 @@ def run_b200(args, wl):
             x0.set_values(v0)
             S.EPSSetInitialSpace(e2.h, 1, (ctypes.c_void_p * 1)(x0.h))
             ke = 0
-            for _ in range(args.steps):
+            for it in range(args.steps):
                 ke += e2.cycles(1)
+                if it == 0:
+                    tp = phase("solver_setup_and_first_unrestarted_cycle", tp)
+            tp = phase("restart_cycles", tp)
             bv2 = e2.bv()
             steps2 = bv2.counters()[1]
             checksum = 0.0
             for j in range(wl["nev"]):                 # device→host read of the result: the nev leading Ritz vectors
                 S.BVGetColumnHost(bv2.h, j, out.ctypes.data_as(ctypes.c_void_p))
                 checksum += float(out[0])
+            tp = phase("ritz_vectors_to_host", tp)
             barrier()
             dt = allmax(time.perf_counter() - t0)
             hb1, db1 = ctypes.c_uint64(), ctypes.c_uint64()
             lib.b2k_ctx_copy_bytes(ctx, ctypes.byref(hb1), ctypes.byref(db1))
             e2e = {"value": rows_global * steps2 / dt, "unit": UNIT, "h2d_bytes_per_step": (hb1.value - hb0.value) / max(ke, 1),
                    "d2h_bytes_per_step": (db1.value - db0.value) / max(ke, 1), "seconds": dt, "steps": ke, "lanczos_steps": steps2,
+                   "phases_s_rank0": {k: round(v, 4) for k, v in ph.items()},
                    "what": "MatCreateB200CSR(host CSR, pinned) + EPSSetInitialSpace(host vector) + K restart cycles (incl. the first, "
                            "unrestarted one) + BVGetColumnHost of the nev leading Ritz vectors; wall clock, max over ranks"}
             e2.destroy()
