@@ -168,6 +168,11 @@ int  b2k_tsqr_backward(b2k_ctx ctx, double *V, int64_t ld, int64_t n, int k, con
    xghost[col-ncols_local] (halo entries received from the neighbouring GPUs).                     */
 int  b2k_csr_create(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t nghost,
                     const int *rowptr_host, const int *colidx_host, const double *val_host, b2k_csr *A);
+/* rows with GLOBAL column indices in [0, ncols_global), owned columns [cstart, cend): the local numbering [owned | ghosts] is built
+   in HBM (off-range columns selected, sorted, made unique and looked up on the device — MPIAIJ's garray, MatSetUpMultiply_MPIAIJ);
+   *ghosts_host (malloc'ed here, freed by the caller; NULL when nghost = 0) = global index of every ghost column, ascending     */
+int  b2k_csr_create_global(b2k_ctx ctx, int64_t nrows, int64_t ncols_global, int64_t cstart, int64_t cend, const int *rowptr_host,
+                           const int *colidx_host, const double *val_host, b2k_csr *A, int64_t *nghost, int **ghosts_host);
 /* same, adopting arrays that already live in HBM (device generators)                              */
 int  b2k_csr_adopt(b2k_ctx ctx, int64_t nrows, int64_t ncols_local, int64_t nghost, int64_t nnz,
                    int *rowptr, int *colidx, double *val, b2k_csr *A);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b2k_spmv_set_sell": [c_int],
     "b2k_vq_set_tma": [c_int],
     "b2k_csr_create": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
+    "b2k_csr_create_global": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_vp)],
     "b2k_csr_adopt": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)],
     "b2k_csr_destroy": [c_vp, c_vp],
     "b2k_csr_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],

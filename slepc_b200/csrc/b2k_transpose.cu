@@ -14,6 +14,7 @@
  * code outside the per-step path, like the host LAPACK of the projected problem.
  */
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include "b2k_internal.h"
 
 /* idx[k] = k */
@@ -117,5 +118,131 @@ extern "C" int b2k_csr_transpose_split(b2k_ctx ctx, b2k_csr A, b2k_csr *ATown, b
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(keys); cudaFree(perm_in); cudaFree(perm); cudaFree(trp_all); cudaFree(tmp);
   b2k_csr_release_arrays(A);
+  return rc;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Local column numbering built in HBM.  A row block arrives with GLOBAL column indices (what MatMPIAIJ's users hand over); the
+ * product kernels want [owned | ghosts] numbering with the ghosts = the sorted distinct off-range columns (MPIAIJ's garray,
+ * MatSetUpMultiply_MPIAIJ).  Round 1 did this on the host: two passes over the entries plus a remapped copy, 0.3 s per GPU for
+ * the 8.4e7 entries of C2 — the largest item of the end-to-end leg after the solve itself (bench.py phases).  Here the
+ * arrays are uploaded as they are and the off-range columns are selected, sorted, made unique and looked up on the device.
+ * ---------------------------------------------------------------------------------------------------------------------------- */
+struct tr_offrange {
+  int c0, c1;
+  __host__ __device__ bool operator()(const int &c) const { return c < c0 || c >= c1; }
+};
+
+__global__ void __launch_bounds__(256) k_col_minmax(const int *__restrict__ col, int64_t nnz, int *__restrict__ mm)
+{
+  int lo = 2147483647, hi = -2147483647 - 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) { const int c = col[k]; lo = min(lo, c); hi = max(hi, c); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+__global__ void __launch_bounds__(256) k_col_localize(int *__restrict__ col, int64_t nnz, int c0, int c1, const int *__restrict__ ghosts, int ng)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int ncl = c1 - c0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+    const int c = col[k];
+    if (c >= c0 && c < c1) { col[k] = c - c0; continue; }
+    int lo = 0, hi = ng - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ghosts[mid] < c) lo = mid + 1; else hi = mid; }
+    col[k] = ncl + lo;
+  }
+}
+
+/* rows of a row block with GLOBAL column indices in [0, ncols_global); owned columns [cstart, cend).  On return *A multiplies
+   [x_owned ; x_ghost], *nghost / *ghosts_host (malloc'ed by this call, the caller frees it; NULL when there are none) list the
+   global indices of the ghost columns in local order (ascending). */
+extern "C" int b2k_csr_create_global(b2k_ctx ctx, int64_t nrows, int64_t ncols_global, int64_t cstart, int64_t cend, const int *rowptr_host,
+                                     const int *colidx_host, const double *val_host, b2k_csr *A, int64_t *nghost, int **ghosts_host)
+{
+  ARGCHK(ctx && A && nghost && ghosts_host, "null argument");
+  ARGCHK(nrows >= 0 && nrows < 2147483647LL && ncols_global >= 0 && ncols_global < 2147483647LL, "sizes must fit int32");
+  ARGCHK(cstart >= 0 && cend >= cstart && cend <= ncols_global, "owned column range outside the matrix");
+  CK(cudaSetDevice(ctx->device));
+  *A = NULL; *nghost = 0; *ghosts_host = NULL;
+  const int64_t nnz = nrows ? rowptr_host[nrows] : 0;
+  const size_t ne = (size_t)(nnz ? nnz : 1);
+  int *rp = NULL, *ci = NULL, *off = NULL, *srt = NULL, *cnt = NULL;
+  double *va = NULL;
+  void *tmp = NULL;
+  CK(cudaMalloc(&rp, sizeof(int) * (size_t)(nrows + 1)));
+  CK(cudaMalloc(&ci, sizeof(int) * ne));
+  CK(cudaMalloc(&va, sizeof(double) * ne));
+  CK(cudaMalloc(&cnt, sizeof(int) * 4));
+  CK(cudaMemcpyAsync(rp, rowptr_host, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    CK(cudaMemcpyAsync(ci, colidx_host, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(va, val_host, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->h2d_bytes += sizeof(int) * (size_t)(nrows + 1) + (sizeof(int) + sizeof(double)) * (size_t)nnz;
+  int hc[4] = {2147483647, -2147483647 - 1, 0, 0};         /* min, max, off-range entries, distinct ghosts */
+  CK(cudaMemcpyAsync(cnt, hc, sizeof(hc), cudaMemcpyHostToDevice, ctx->stream));
+  int ng = 0;
+  if (nnz) {
+    k_col_minmax<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ci, nnz, cnt);
+    CKLAUNCH(ctx);
+    const bool all_owned = (cstart == 0 && cend == ncols_global);
+    if (!all_owned) {
+      size_t tb = 0, tb2 = 0, tb3 = 0;
+      const tr_offrange pred = {(int)cstart, (int)cend};
+      CK(cudaMalloc(&off, sizeof(int) * ne));
+      CK(cub::DeviceSelect::If(NULL, tb, ci, off, cnt + 2, (int)nnz, pred, ctx->stream));
+      int end_bit = 1;
+      while (end_bit < 31 && ((int64_t)1 << end_bit) < ncols_global) end_bit++;
+      CK(cub::DeviceRadixSort::SortKeys(NULL, tb2, off, off, (int)nnz, 0, end_bit, ctx->stream));
+      CK(cub::DeviceSelect::Unique(NULL, tb3, off, off, cnt + 3, (int)nnz, ctx->stream));
+      if (tb2 > tb) tb = tb2;
+      if (tb3 > tb) tb = tb3;
+      CK(cudaMalloc(&tmp, tb ? tb : 1));
+      CK(cub::DeviceSelect::If(tmp, tb, ci, off, cnt + 2, (int)nnz, pred, ctx->stream));
+      CK(cudaMemcpyAsync(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->syncs++;
+      const int noff = hc[2];
+      if (noff > 0) {
+        CK(cudaMalloc(&srt, sizeof(int) * (size_t)noff));
+        CK(cub::DeviceRadixSort::SortKeys(tmp, tb, off, srt, noff, 0, end_bit, ctx->stream));
+        CK(cub::DeviceSelect::Unique(tmp, tb, srt, off, cnt + 3, noff, ctx->stream));   /* off now holds the distinct ghosts, ascending */
+        CK(cudaMemcpyAsync(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->syncs++;
+        ng = hc[3];
+      }
+    } else {
+      CK(cudaMemcpyAsync(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->syncs++;
+    }
+    if (hc[0] < 0 || (int64_t)hc[1] >= ncols_global) {
+      cudaFree(rp); cudaFree(ci); cudaFree(va); cudaFree(cnt); cudaFree(off); cudaFree(srt); cudaFree(tmp);
+      b2k_set_error("column index %d outside [0,%lld)", hc[0] < 0 ? hc[0] : hc[1], (long long)ncols_global);
+      return B2K_ERR_ARG;
+    }
+    if (!all_owned) {
+      k_col_localize<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ci, nnz, (int)cstart, (int)cend, off, ng);
+      CKLAUNCH(ctx);
+      if (ng > 0) {
+        int *g = (int *)malloc(sizeof(int) * (size_t)ng);
+        if (!g) return B2K_ERR_MEM;
+        CK(cudaMemcpyAsync(g, off, sizeof(int) * (size_t)ng, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->d2h_bytes += sizeof(int) * (size_t)ng;
+        *ghosts_host = g;
+      }
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(cnt); cudaFree(off); cudaFree(srt); cudaFree(tmp);
+  *nghost = ng;
+  const int rc = b2k_csr_adopt(ctx, nrows, cend - cstart, ng, nnz, rp, ci, va, A);   /* takes the three arrays; builds the SELL copy */
+  if (rc && *ghosts_host) { free(*ghosts_host); *ghosts_host = NULL; }
   return rc;
 }

@@ -258,8 +258,6 @@ static PetscErrorCode MatSetUp_B200CSR(Mat A, PetscInt M, PetscInt N, PetscInt r
   return PETSC_SUCCESS;
 }
 
-static int cmp_int(const void *x, const void *y) { const PetscInt a = *(const PetscInt *)x, b = *(const PetscInt *)y; return (a > b) - (a < b); }
-
 PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscInt rend, const PetscInt *rowptr, const PetscInt *colidx,
                                 const PetscScalar *val, PetscInt cstart, PetscInt cend, Mat *out)
 {
@@ -268,64 +266,24 @@ PetscErrorCode MatCreateB200CSR(PetscInt M, PetscInt N, PetscInt rstart, PetscIn
   PetscCheck(rstart >= 0 && rend >= rstart && rend <= M, PETSC_ERR_ARG_OUTOFRANGE, "row range [%d,%d) outside [0,%d)", rstart, rend, M);
   PetscCheck(cstart >= 0 && cend >= cstart && cend <= N, PETSC_ERR_ARG_OUTOFRANGE, "column range [%d,%d) outside [0,%d)", cstart, cend, N);
   PetscCheck(rowptr && (rend == rstart || rowptr[0] == 0), PETSC_ERR_ARG_WRONG, "rowptr[0] must be 0");
-  const PetscInt m = rend - rstart, ncl = cend - cstart;
+  const PetscInt m = rend - rstart;
   const PetscInt nnz = m ? rowptr[m] : 0;
   Mat A;
   Mat_B200CSR *a;
   PetscCall(MatCreate_Private(&A));
   PetscCall(MatSetUp_B200CSR(A, M, N, rstart, rend, cstart, cend, &a));
   a->nnz = nnz;
-  /* ghosts = sorted unique off-range columns; local numbering = [owned | ghosts] like MatMPIAIJ's garray */
-  PetscInt noff = 0;
-  for (PetscInt k = 0; k < nnz; k++) {
-    PetscCheck(colidx[k] >= 0 && colidx[k] < N, PETSC_ERR_ARG_OUTOFRANGE, "column index %d outside [0,%d)", colidx[k], N);
-    if (colidx[k] < cstart || colidx[k] >= cend) noff++;
+  /* ghosts = sorted unique off-range columns; local numbering = [owned | ghosts] like MatMPIAIJ's garray (MatSetUpMultiply_MPIAIJ).
+     Built in HBM from the arrays as they are: the host does not walk the entries (b2k_csr_create_global) */
+  int64_t ng = 0;
+  int *gh = NULL;
+  const int rc = b2k_csr_create_global(ctx, m, N, cstart, cend, rowptr, colidx, val, &a->A, &ng, &gh);
+  if (rc) {
+    MatDestroy(&A);
+    SETERRQ(rc == B2K_ERR_ARG ? PETSC_ERR_ARG_OUTOFRANGE : PETSC_ERR_GPU, "b2k_csr_create_global failed (%d): %s", rc, b2k_last_error());
   }
-  if (!noff && cstart == 0) {                     /* all columns owned and already locally numbered: upload as is */
-    int rc0 = b2k_csr_create(ctx, m, ncl, 0, rowptr, colidx, val, &a->A);
-    if (rc0) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_create failed (%d): %s", rc0, b2k_last_error()); }
-    *out = A;
-    return PETSC_SUCCESS;
-  }
-  PetscInt *loc = (PetscInt *)malloc(sizeof(PetscInt) * ((size_t)nnz + 1));
-  PetscCheck(loc, PETSC_ERR_MEM, "out of memory");
-  PetscInt *map = NULL;                           /* global column -> ghost slot, when an N-long table is affordable */
-  if (noff && (int64_t)N <= 536870912LL && (int64_t)N <= 8 * (int64_t)noff + 1048576) {
-    /* O(nnz + N): mark the off-range columns, enumerate them in order (= sorted unique), keep the inverse table */
-    map = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)N);
-    PetscCheck(map, PETSC_ERR_MEM, "out of memory");
-    memset(map, 0xff, sizeof(PetscInt) * (size_t)N);
-    for (PetscInt k = 0; k < nnz; k++) if (colidx[k] < cstart || colidx[k] >= cend) map[colidx[k]] = 0;
-    PetscInt nu = 0;
-    for (PetscInt cg = 0; cg < N; cg++) if (map[cg] == 0) nu++;
-    PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)(nu ? nu : 1));
-    PetscCheck(g, PETSC_ERR_MEM, "out of memory");
-    nu = 0;
-    for (PetscInt cg = 0; cg < N; cg++) if (map[cg] == 0) { map[cg] = nu; g[nu++] = cg; }
-    a->ghosts = g; a->nghost = nu;
-  } else if (noff) {
-    PetscInt *g = (PetscInt *)malloc(sizeof(PetscInt) * (size_t)noff), ng = 0;
-    PetscCheck(g, PETSC_ERR_MEM, "out of memory");
-    for (PetscInt k = 0; k < nnz; k++) if (colidx[k] < cstart || colidx[k] >= cend) g[ng++] = colidx[k];
-    qsort(g, (size_t)ng, sizeof(PetscInt), cmp_int);
-    PetscInt nu = 0;
-    for (PetscInt i = 0; i < ng; i++) if (i == 0 || g[i] != g[i - 1]) g[nu++] = g[i];
-    a->ghosts = g; a->nghost = nu;
-  }
-  for (PetscInt k = 0; k < nnz; k++) {
-    const PetscInt cg = colidx[k];
-    if (cg >= cstart && cg < cend) loc[k] = cg - cstart;
-    else if (map) loc[k] = ncl + map[cg];
-    else {
-      PetscInt lo = 0, hi = a->nghost - 1;
-      while (lo < hi) { const PetscInt mid = (lo + hi) / 2; if (a->ghosts[mid] < cg) lo = mid + 1; else hi = mid; }
-      loc[k] = ncl + lo;
-    }
-  }
-  free(map);
-  int rc = b2k_csr_create(ctx, m, ncl, a->nghost, rowptr, loc, val, &a->A);
-  free(loc);
-  if (rc) { MatDestroy(&A); SETERRQ(PETSC_ERR_GPU, "b2k_csr_create failed (%d): %s", rc, b2k_last_error()); }
+  a->nghost = (PetscInt)ng;
+  a->ghosts = gh;
   if (a->nghost) B2KCall(b2k_malloc(ctx, (void **)&a->xghost, sizeof(double) * (size_t)a->nghost));
   *out = A;
   return PETSC_SUCCESS;

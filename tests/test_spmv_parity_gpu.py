@@ -431,3 +431,64 @@ def test_device_transpose_matches_scipy_exactly(ctx, case):
     for hh in (hown, hgh, h):
         if hh:
             _check(ctx.lib.b2k_csr_destroy(ctx.h, hh))
+
+
+# ---- local column numbering built in HBM (b2k_csr_create_global): what MatCreateB200CSR does with a row block on > 1 rank ----
+@pytest.mark.parametrize("case", ["middle_block", "first_block", "all_owned", "no_offrange_entries", "empty"])
+def test_global_columns_localized_on_the_device(ctx, case):
+    """rows with GLOBAL column indices: the ghost list (sorted distinct off-range columns, MPIAIJ's garray) and the local
+    numbering [owned | ghosts] come from the device select / sort / unique / lookup; checked against numpy and through a product"""
+    import scipy.sparse as sp
+    from slepc_b200 import matgen
+    rng = np.random.default_rng(33)
+    M, N = 200003, 70001
+    if case == "empty":
+        A = sp.csr_matrix((50, N))
+        c0, c1 = 100, 900
+    else:
+        rp, ci, va = matgen.random_sparse_rows(M, N, 9, seed=4)
+        A = sp.csr_matrix((va, ci, rp), shape=(M, N))
+        c0, c1 = {"middle_block": (20000, 45000), "first_block": (0, 30000), "all_owned": (0, N), "no_offrange_entries": (0, N)}[case]
+        if case == "no_offrange_entries":
+            A = A[:, :40000].tocsr()                 # entries only in [0, 40000), owned range declared as [0, 50000) of 70001
+            A = sp.csr_matrix((A.data, A.indices, A.indptr), shape=(M, N))
+            c0, c1 = 0, 50000
+    A.sort_indices()
+    nr = A.shape[0]
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32); va = np.ascontiguousarray(A.data)
+    h, ng, gp = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
+    _check(ctx.lib.b2k_csr_create_global(ctx.h, nr, N, c0, c1, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h), ctypes.byref(ng), ctypes.byref(gp)))
+    cols = np.unique(A.indices)
+    ghosts_ref = cols[(cols < c0) | (cols >= c1)]
+    assert ng.value == len(ghosts_ref)
+    ghosts = np.ctypeslib.as_array(ctypes.cast(gp, ctypes.POINTER(ctypes.c_int)), shape=(ng.value,)).copy() if ng.value else np.zeros(0, np.int32)
+    assert np.array_equal(ghosts, ghosts_ref)
+    x = rng.standard_normal(N)
+    dx = ctx.to_device(np.ascontiguousarray(x[c0:c1]))
+    dg = ctx.to_device(np.ascontiguousarray(x[ghosts])) if ng.value else None
+    dy = ctx.empty(max(nr, 1))
+    _check(ctx.lib.b2k_csr_spmv(ctx.h, h, dx.ptr, dg.ptr if dg else None, dy.ptr))
+    ctx.sync()
+    y = dy.to_host()[:nr]
+    tol = 1e-13 * np.abs(x).max() * max(int(np.diff(A.indptr).max()), 1) * max(np.abs(A.data).max() if A.nnz else 1.0, 1.0)
+    assert np.abs(y - A @ x).max() <= tol
+    # the local numbering itself: owned columns first, then the ghosts in ascending global order
+    lrp, lci, lva, shape = _csr_to_host(ctx, h)
+    loc2glob = np.concatenate([np.arange(c0, c1), ghosts_ref])
+    assert np.array_equal(lrp, A.indptr) and np.array_equal(loc2glob[lci], A.indices) and np.array_equal(lva, A.data)
+    for d in (dx, dg, dy):
+        if d is not None:
+            d.free()
+    _check(ctx.lib.b2k_csr_destroy(ctx.h, h))
+    if gp:
+        libc = ctypes.CDLL(None)
+        libc.free.argtypes = [ctypes.c_void_p]
+        libc.free(gp)
+
+
+def test_global_columns_out_of_range_is_an_error(ctx):
+    from slepc_b200._b2k import B2KError
+    rp = np.array([0, 2, 3], dtype=np.int32); ci = np.array([0, 7, 12], dtype=np.int32); va = np.ones(3)
+    h, ng, gp = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
+    with pytest.raises(B2KError):
+        _check(ctx.lib.b2k_csr_create_global(ctx.h, 2, 10, 2, 6, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, ctypes.byref(h), ctypes.byref(ng), ctypes.byref(gp)))
