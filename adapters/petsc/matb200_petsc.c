@@ -5,8 +5,9 @@
  *   SVDTwoSideLanczos → MatMult(A|AT)       src/svd/impls/lanczos/gklanczos.c:67,80,90,103
  * and only needs MATOP_MULT (+ MATOP_MULT_TRANSPOSE for an implicit transpose, svdsetup.c:273-279) and CUDA vectors from
  * MatCreateVecs (stsolve.c:349-353, BVSetSizesFromVec): a MatShell, the pattern of src/eps/tutorials/ex3.c:46-49,140-168.
- * The PETSc-typed twin of slepc_b200/host/matb200.c: the local rows go to HBM as CSR → SELL-32 (b2k_csr_create), the halo
- * moves GPU-to-GPU (NVLink peer memory, else ncclSend/ncclRecv), the product is k_spmv_sell_pipe.
+ * The PETSc-typed twin of slepc_b200/host/matb200.c: the local rows go to HBM with their global column indices, the local
+ * numbering and the SELL-32 copy are built there (b2k_csr_create_global), the halo moves GPU-to-GPU in both directions (NVLink
+ * peer memory, else ncclSend/ncclRecv), the products are k_spmv_sell_pipe on A and on the local transpose built in HBM.
  * Type-checked against the reference's headers with the stand-in PETSc declarations of adapters/petsc/stub/ (no PETSc here).
  */
 #include <slepcsys.h>
@@ -19,6 +20,10 @@ typedef struct {
   b2k_csr   A;
   b2k_comm  comm;
   b2k_halo  halo;            /* forward halo over peer memory (NULL: single rank or no mailboxes)   */
+  b2k_halo  halo_rev;        /* the same plan with the roles exchanged: reverse halo of MatMultTranspose */
+  b2k_csr   ATown, ATgh;     /* local transpose built in HBM on first use (b2k_csr_transpose_split)  */
+  double   *zghost, *rbuf;   /* ghost-column contributions of y = A^T x (send) / received ones (NCCL path) */
+  PetscInt  n;               /* owned columns                                                        */
   PetscInt  nghost, *ghosts; /* sorted global columns outside the owned range, local numbering [owned | ghosts] */
   double   *xghost;          /* NCCL path: device ghost values                                      */
   PetscInt  nrecv, nsend, *recvrank, *recvcount, *sendrank, *sendcount, nsendtot;
@@ -54,6 +59,67 @@ static PetscErrorCode MatMult_B200(Mat S, Vec x, Vec y)
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+/* y = A^T x for the implicit transpose of SVDSetUp (svdsetup.c:273-279; reached from gklanczos.c:80,103) — PETSc's
+   MatMultTranspose_MPIAIJ: local transpose products, then the ghost-column contributions travel to their owners and are added
+   in the order of the send list (deterministic).  The PETSc-typed twin of MatMultTranspose_B200CSR in host/matb200.c. */
+static PetscErrorCode MatMultTranspose_B200(Mat S, Vec x, Vec y)
+{
+  Mat_B200          *a;
+  const PetscScalar *px;
+  PetscScalar       *py;
+  b2k_ctx            ctx = B2KPetscContext();
+
+  PetscFunctionBegin;
+  PetscCall(MatShellGetContext(S, &a));
+  if (!a->ATown) {
+    B2KCall(b2k_csr_transpose_split(ctx, a->A, &a->ATown, a->nghost ? &a->ATgh : NULL));
+    if (a->nghost) B2KCall(b2k_malloc(ctx, (void **)&a->zghost, sizeof(double) * (size_t)a->nghost));
+  }
+  PetscCall(VecCUDAGetArrayRead(x, &px));
+  PetscCall(VecCUDAGetArrayWrite(y, &py));
+  B2KCall(b2k_csr_spmv(ctx, a->ATown, px, NULL, py));
+  if (a->nghost) B2KCall(b2k_csr_spmv(ctx, a->ATgh, px, NULL, a->zghost));
+  if (a->halo) {                                                  /* every rank of the communicator takes part */
+    const double *rb = NULL;
+    PetscInt      so = 0;
+    if (!a->halo_rev) {
+      int     rr[8], rc[8], sr[8], sc[8];
+      int64_t off[8] = {0}, roff = 0;
+      for (PetscInt p = 0; p < a->nrecv; p++) { sr[p] = (int)a->recvrank[p]; sc[p] = (int)a->recvcount[p]; off[p] = roff; roff += a->recvcount[p]; }
+      for (PetscInt q = 0; q < a->nsend; q++) { rr[q] = (int)a->sendrank[q]; rc[q] = (int)a->sendcount[q]; }
+      B2KCall(b2k_halo_create(a->comm, (int)a->nsend, rr, rc, (int)a->nrecv, sr, sc, NULL, off, &a->halo_rev));
+    }
+    B2KCall(b2k_halo_exchange(a->halo_rev, a->zghost, &rb));
+    for (PetscInt q = 0; q < a->nsend; q++) { B2KCall(b2k_scatter_add(ctx, py, a->d_sendidx + so, rb + so, a->sendcount[q])); so += a->sendcount[q]; }
+  } else if (a->nrecv || a->nsend) {                             /* grouped ncclSend / ncclRecv, the plan run backwards */
+    PetscInt soff = 0, roff = 0;
+    if (a->nsendtot && !a->rbuf) B2KCall(b2k_malloc(ctx, (void **)&a->rbuf, sizeof(double) * (size_t)a->nsendtot));
+    B2KCall(b2k_comm_group_start(a->comm));
+    for (PetscInt p = 0; p < a->nrecv; p++) { B2KCall(b2k_comm_sendrecv(a->comm, a->zghost + roff, a->recvcount[p], (int)a->recvrank[p], NULL, 0, 0)); roff += a->recvcount[p]; }
+    for (PetscInt q = 0; q < a->nsend; q++) { B2KCall(b2k_comm_sendrecv(a->comm, NULL, 0, 0, a->rbuf + soff, a->sendcount[q], (int)a->sendrank[q])); soff += a->sendcount[q]; }
+    B2KCall(b2k_comm_group_end(a->comm));
+    soff = 0;
+    for (PetscInt q = 0; q < a->nsend; q++) { B2KCall(b2k_scatter_add(ctx, py, a->d_sendidx + soff, a->rbuf + soff, a->sendcount[q])); soff += a->sendcount[q]; }
+  }
+  PetscCall(VecCUDARestoreArrayWrite(y, &py));
+  PetscCall(VecCUDARestoreArrayRead(x, &px));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+/* MatGetDiagonal: the Jacobi preconditioner of a KSP behind STMatSolve (stsles.c:166-200) */
+static PetscErrorCode MatGetDiagonal_B200(Mat S, Vec d)
+{
+  Mat_B200    *a;
+  PetscScalar *pd;
+
+  PetscFunctionBegin;
+  PetscCall(MatShellGetContext(S, &a));
+  PetscCall(VecCUDAGetArrayWrite(d, &pd));
+  B2KCall(b2k_csr_get_diagonal(B2KPetscContext(), a->A, 0, pd));
+  PetscCall(VecCUDARestoreArrayWrite(d, &pd));
+  PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 static PetscErrorCode MatDestroy_B200(Mat S)
 {
   Mat_B200 *a;
@@ -61,18 +127,21 @@ static PetscErrorCode MatDestroy_B200(Mat S)
 
   PetscFunctionBegin;
   PetscCall(MatShellGetContext(S, &a));
+  if (a->halo_rev) B2KCall(b2k_halo_destroy(a->halo_rev));       /* collective */
   if (a->halo) B2KCall(b2k_halo_destroy(a->halo));               /* collective */
+  B2KCall(b2k_csr_destroy(ctx, a->ATown));
+  B2KCall(b2k_csr_destroy(ctx, a->ATgh));
+  B2KCall(b2k_free(ctx, a->zghost));
+  B2KCall(b2k_free(ctx, a->rbuf));
   B2KCall(b2k_csr_destroy(ctx, a->A));
   B2KCall(b2k_free(ctx, a->xghost));
   B2KCall(b2k_free(ctx, a->d_sendidx));
   B2KCall(b2k_free(ctx, a->sendbuf));
-  PetscCall(PetscFree(a->ghosts));
+  free(a->ghosts);                                               /* malloc'ed by b2k_csr_create_global */
   PetscCall(PetscFree(a->recvrank)); PetscCall(PetscFree(a->recvcount)); PetscCall(PetscFree(a->sendrank)); PetscCall(PetscFree(a->sendcount));
   PetscCall(PetscFree(a));
   PetscFunctionReturn(PETSC_SUCCESS);
 }
-
-static int cmp_int(const void *x, const void *y) { const PetscInt a = *(const PetscInt *)x, b = *(const PetscInt *)y; return (a > b) - (a < b); }
 
 /* the halo plan: who needs which of my entries (what MatSetUpMultiply_MPIAIJ / VecScatterCreate work out): every rank publishes
    the sorted list of ghost columns it needs from each owner; the counts travel with MPI_Allreduce-free point-to-point exchanges
@@ -122,7 +191,7 @@ PetscErrorCode MatCreateB200FromMat(Mat Ain, Mat *Aout)
 {
   MPI_Comm     comm;
   Mat_B200    *a;
-  PetscInt     M, N, m, n, rstart, rend, cstart, cend, nnz = 0, noff = 0, *rowptr, *colloc, *colstarts;
+  PetscInt     M, N, m, n, rstart, rend, cstart, cend, nnz = 0, *rowptr, *colglob, *colstarts;
   PetscScalar *val;
   int          size, rank;
   b2k_ctx      ctx;
@@ -139,42 +208,36 @@ PetscErrorCode MatCreateB200FromMat(Mat Ain, Mat *Aout)
   PetscCall(MatGetOwnershipRangeColumn(Ain, &cstart, &cend));
   PetscCall(PetscNew(&a));
   PetscCall(B2KPetscCommGet(comm, &a->comm));
-  /* pass 1: sizes; pass 2: rows with local column numbering [owned | ghosts] */
+  a->n = n;
+  /* the local rows with their GLOBAL column indices go to HBM as they are; the [owned | ghosts] numbering and the ghost list
+     (MPIAIJ's garray, MatSetUpMultiply_MPIAIJ) are built on the device (b2k_csr_create_global) */
   PetscCall(PetscMalloc1(m + 1, &rowptr));
   rowptr[0] = 0;
   for (PetscInt r = 0; r < m; r++) {
-    PetscInt           nc;
-    const PetscInt    *cols;
-    PetscCall(MatGetRow(Ain, rstart + r, &nc, &cols, NULL));
-    for (PetscInt k = 0; k < nc; k++) if (cols[k] < cstart || cols[k] >= cend) noff++;
+    PetscInt nc;
+    PetscCall(MatGetRow(Ain, rstart + r, &nc, NULL, NULL));
     nnz += nc;
     rowptr[r + 1] = nnz;
-    PetscCall(MatRestoreRow(Ain, rstart + r, &nc, &cols, NULL));
+    PetscCall(MatRestoreRow(Ain, rstart + r, &nc, NULL, NULL));
   }
-  PetscCall(PetscMalloc1(nnz + 1, &colloc));
+  PetscCall(PetscMalloc1(nnz + 1, &colglob));
   PetscCall(PetscMalloc1(nnz + 1, &val));
-  PetscCall(PetscMalloc1(noff + 1, &a->ghosts));
-  for (PetscInt r = 0, g = 0; r < m; r++) {
+  for (PetscInt r = 0; r < m; r++) {
     PetscInt           nc;
     const PetscInt    *cols;
     const PetscScalar *v;
     PetscCall(MatGetRow(Ain, rstart + r, &nc, &cols, &v));
-    for (PetscInt k = 0; k < nc; k++) { if (cols[k] < cstart || cols[k] >= cend) a->ghosts[g++] = cols[k]; val[rowptr[r] + k] = v[k]; colloc[rowptr[r] + k] = cols[k]; }
+    for (PetscInt k = 0; k < nc; k++) { val[rowptr[r] + k] = v[k]; colglob[rowptr[r] + k] = cols[k]; }
     PetscCall(MatRestoreRow(Ain, rstart + r, &nc, &cols, &v));
   }
-  qsort(a->ghosts, (size_t)noff, sizeof(PetscInt), cmp_int);
-  for (PetscInt i = 0; i < noff; i++) if (i == 0 || a->ghosts[i] != a->ghosts[i - 1]) a->ghosts[a->nghost++] = a->ghosts[i];
-  for (PetscInt k = 0; k < nnz; k++) {
-    const PetscInt cg = colloc[k];
-    if (cg >= cstart && cg < cend) colloc[k] = cg - cstart;
-    else {
-      PetscInt lo = 0, hi = a->nghost - 1;
-      while (lo < hi) { const PetscInt mid = (lo + hi) / 2; if (a->ghosts[mid] < cg) lo = mid + 1; else hi = mid; }
-      colloc[k] = n + lo;
-    }
+  {
+    int64_t ng = 0;
+    int    *gh = NULL;
+    B2KCall(b2k_csr_create_global(ctx, m, N, cstart, cend, rowptr, colglob, val, &a->A, &ng, &gh));
+    a->nghost = (PetscInt)ng;
+    a->ghosts = gh;                                              /* PetscInt is int in the default build */
   }
-  B2KCall(b2k_csr_create(ctx, m, n, a->nghost, rowptr, colloc, val, &a->A));
-  PetscCall(PetscFree(rowptr)); PetscCall(PetscFree(colloc)); PetscCall(PetscFree(val));
+  PetscCall(PetscFree(rowptr)); PetscCall(PetscFree(colglob)); PetscCall(PetscFree(val));
   if (size > 1) {
     PetscCall(PetscMalloc1(size + 1, &colstarts));
     PetscCallMPI(MPI_Allgather(&cstart, 1, MPIU_INT, colstarts, 1, MPIU_INT, comm));
@@ -192,6 +255,8 @@ PetscErrorCode MatCreateB200FromMat(Mat Ain, Mat *Aout)
   }
   PetscCall(MatCreateShell(comm, m, n, M, N, (void *)a, Aout));
   PetscCall(MatShellSetOperation(*Aout, MATOP_MULT, (void (*)(void))MatMult_B200));
+  PetscCall(MatShellSetOperation(*Aout, MATOP_MULT_TRANSPOSE, (void (*)(void))MatMultTranspose_B200));   /* no MATOP_TRANSPOSE: SVDSetUp goes implicit */
+  if (M == N && rstart == cstart && rend == cend) PetscCall(MatShellSetOperation(*Aout, MATOP_GET_DIAGONAL, (void (*)(void))MatGetDiagonal_B200));
   PetscCall(MatShellSetOperation(*Aout, MATOP_DESTROY, (void (*)(void))MatDestroy_B200));
   PetscCall(MatShellSetVecType(*Aout, VECCUDA));                 /* MatCreateVecs hands SLEPc CUDA vectors: stsolve.c:349-353 */
   PetscFunctionReturn(PETSC_SUCCESS);
