@@ -74,7 +74,7 @@ int  b2k_ctx_copy_bytes(b2k_ctx ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 #define B2K_PROF_MULTVEC  1   /* k_gs_tma<.,0,.> / k_gs_rt / k_multvec: y = beta y + alpha V q (+ norm) */
 #define B2K_PROF_GSFUSED  2   /* k_gs_tma<.,1,1>: update + next pass' V^T w + norm, V read once     */
 #define B2K_PROF_SPMV     3   /* k_spmv_sell_pipe / k_spmv_sell / k_spmv_csr_stream                */
-#define B2K_PROF_GEMM     4   /* k_vq_tma / k_vq / k_gemm_ts: V Q (restart); k_gram: Y^T X         */
+#define B2K_PROF_GEMM     4   /* k_vq_tma / k_vq: V Q (restart); k_gram_tma: Y^T X; k_tsqr_*        */
 #define B2K_PROF_ELEMWISE 5   /* scale / copy / axpby / fill                                      */
 #define B2K_PROF_NCLASS   6
 int  b2k_prof_enable(b2k_ctx ctx, int on);               /* on: start a fresh recording            */

@@ -54,7 +54,7 @@ __device__ __forceinline__ void gr_dmma(double &d0, double &d1, double a, double
 
 /* one 64-row tile for a warp that owns nb <= NBP blocks: RS = 8 / NBP row splits give every warp 8 independent DMMA chains
    (accumulator u*RS + sp), so narrow results (few blocks per warp) are not bound by the latency of a single dependent chain —
-   measured before the split: 32 x 32 took as long as 64 x 64 (profiles/r02_kernels.md) */
+   measured before the split: 32 x 32 took as long as 64 x 64 (profiles/r02/r02e_kbench2.jsonl vs r02f_kbench2.jsonl) */
 template <int NBP>
 __device__ __forceinline__ void gr_tile(const double *__restrict__ ap, const double *__restrict__ bp, int G, int nb, double (&c0)[8], double (&c1)[8])
 {

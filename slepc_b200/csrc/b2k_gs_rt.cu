@@ -6,7 +6,7 @@
  *       cout[0:k] = V(:,0:k)^T w_new                         (dot sweep of the next DGKS pass, bvorthog.c:100)
  *       cout[k]   = ||w_new||^2                              (explicit norm, bvorthog.c:126)
  *
- * Why registers and not shared memory / TMA staging: the TMA-staged variant (b2k_gs_fused.cu, one 1 KB bulk
+ * Why registers and not shared memory / TMA staging: the first TMA-staged variant (round 1, since removed: one 1 KB bulk
  * copy per column per 128-row tile) is bound by the per-copy issue rate of the bulk-copy engine — ncu shows
  * 40 % of the warp samples spinning on the `full` mbarrier and 50 % DRAM utilisation (profiles/r01_ncu_summary.md).
  * Here a CTA of 4 warps owns a 64-row tile; warp g holds columns [g*kq,(g+1)*kq) of the tile in REGISTERS

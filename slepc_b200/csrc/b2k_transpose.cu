@@ -15,6 +15,7 @@
  */
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <time.h>
 #include "b2k_internal.h"
 
 /* idx[k] = k */
@@ -168,6 +169,18 @@ extern "C" int b2k_csr_create_global(b2k_ctx ctx, int64_t nrows, int64_t ncols_g
   ARGCHK(cstart >= 0 && cend >= cstart && cend <= ncols_global, "owned column range outside the matrix");
   CK(cudaSetDevice(ctx->device));
   *A = NULL; *nghost = 0; *ghosts_host = NULL;
+  const char *tdbg = getenv("B2K_TIMING");                 /* B2K_TIMING=1: wall-clock of the set-up phases on stderr */
+  struct timespec ts0, ts1;
+  if (tdbg) clock_gettime(CLOCK_MONOTONIC, &ts0);
+#define TR_TICK(what)                                                                                                              \
+  do {                                                                                                                             \
+    if (tdbg) {                                                                                                                    \
+      cudaStreamSynchronize(ctx->stream);                                                                                          \
+      clock_gettime(CLOCK_MONOTONIC, &ts1);                                                                                        \
+      fprintf(stderr, "[b2k_csr_create_global] %-28s %8.2f ms\n", what, 1e3 * (ts1.tv_sec - ts0.tv_sec) + 1e-6 * (ts1.tv_nsec - ts0.tv_nsec)); \
+      ts0 = ts1;                                                                                                                   \
+    }                                                                                                                              \
+  } while (0)
   const int64_t nnz = nrows ? rowptr_host[nrows] : 0;
   const size_t ne = (size_t)(nnz ? nnz : 1);
   int *rp = NULL, *ci = NULL, *off = NULL, *srt = NULL, *cnt = NULL;
@@ -183,6 +196,7 @@ extern "C" int b2k_csr_create_global(b2k_ctx ctx, int64_t nrows, int64_t ncols_g
     CK(cudaMemcpyAsync(va, val_host, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
   }
   ctx->h2d_bytes += sizeof(int) * (size_t)(nrows + 1) + (sizeof(int) + sizeof(double)) * (size_t)nnz;
+  TR_TICK("cudaMalloc + upload");
   int hc[4] = {2147483647, -2147483647 - 1, 0, 0};         /* min, max, off-range entries, distinct ghosts */
   CK(cudaMemcpyAsync(cnt, hc, sizeof(hc), cudaMemcpyHostToDevice, ctx->stream));
   int ng = 0;
@@ -242,7 +256,10 @@ extern "C" int b2k_csr_create_global(b2k_ctx ctx, int64_t nrows, int64_t ncols_g
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(cnt); cudaFree(off); cudaFree(srt); cudaFree(tmp);
   *nghost = ng;
+  TR_TICK("range check + local numbering");
   const int rc = b2k_csr_adopt(ctx, nrows, cend - cstart, ng, nnz, rp, ci, va, A);   /* takes the three arrays; builds the SELL copy */
+  TR_TICK("row blocks + SELL copy");
+#undef TR_TICK
   if (rc && *ghosts_host) { free(*ghosts_host); *ghosts_host = NULL; }
   return rc;
 }
