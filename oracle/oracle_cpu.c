@@ -334,6 +334,45 @@ static PetscErrorCode BVSetRandomColumn_CPU(BV bv, PetscInt j)
   for (PetscInt i = 0; i < bv->n; i++) x[i] = B2KHashUniform((uint64_t)(bv->row0 + i), bv->rng_seed + (uint64_t)j);
   return PETSC_SUCCESS;
 }
+/* TEST DOUBLE of the krylov_steps slot (the device type enqueues a whole restart cycle and may stop early at a step it cannot
+   finish on its own: tests/test_host_cpu.py drives the front-end's resume logic of BVKrylovLoop_Private with it).  Active only
+   when ORACLE_KRYLOV_STEPS is set to a comma-separated pattern: the i-th call completes min(pattern[i mod len], m-k) steps with
+   the step-by-step arithmetic and reports where it stopped; 0 = declines; a negative entry -s completes s steps and then runs
+   ONE MORE step that it disowns (its column is left modified, as after a device-side breakdown: the loop must redo it). */
+static PetscErrorCode BVKrylovSteps_CPU(BV V, Mat A, PetscInt k, PetscInt m, PetscInt *jnext, PetscReal *beta)
+{
+  static int ncall = 0;
+  const char *pat = getenv("ORACLE_KRYLOV_STEPS");
+  *jnext = k;
+  if (!pat || !*pat) return PETSC_SUCCESS;
+  int vals[64], nv = 0;
+  for (const char *p = pat; *p && nv < 64;) { vals[nv++] = atoi(p); while (*p && *p != ',') p++; if (*p == ',') p++; }
+  if (!nv) return PETSC_SUCCESS;
+  const int want = vals[ncall++ % nv];
+  PetscInt todo = want < 0 ? -want : want;
+  if (todo > m - k) todo = m - k;
+  PetscErrorCode (*self)(BV, Mat, PetscInt, PetscInt, PetscInt *, PetscReal *) = V->ops.krylov_steps;
+  V->ops.krylov_steps = NULL;                      /* the public calls below must not come back here */
+  PetscErrorCode ierr = PETSC_SUCCESS;
+  PetscInt j = k;
+  for (; !ierr && j < k + todo; j++) {
+    PetscBool lindep = PETSC_FALSE;
+    PetscReal b = 0.0;
+    ierr = BVMatMultColumn(V, A, j);
+    if (!ierr) ierr = BVOrthonormalizeColumn(V, j + 1, PETSC_FALSE, &b, &lindep);
+    if (!ierr && lindep) break;                    /* a breakdown is the loop's business: this step is not reported as done */
+    if (!ierr) *beta = b;
+  }
+  if (!ierr && want < 0 && j == k + todo && j < m) {   /* one disowned step: column j+1 and its coefficients are garbage afterwards */
+    ierr = BVMatMultColumn(V, A, j);
+    if (!ierr) ierr = V->ops.scale(V, j + 1, 3.0);
+  }
+  V->ops.krylov_steps = self;
+  PetscCall(ierr);
+  *jnext = j;
+  return PETSC_SUCCESS;
+}
+
 /* local Householder QR of the active columns with LAPACK, as BVOrthogonalize_LAPACK_TSQR does on the raw array (bvlapack.c:378-396):
    geqrf -> R; with wantq the factored copy is kept and tsqr_formq applies it to [W ; 0] (ormqr) */
 static PetscErrorCode BVTSQRFactor_CPU(BV bv, PetscBool wantq, PetscScalar *R)
@@ -410,6 +449,7 @@ PetscErrorCode BVCreate_OracleCPU(BV bv)
   bv->ops.setrandomcolumn = BVSetRandomColumn_CPU;
   bv->ops.tsqr_factor = BVTSQRFactor_CPU;
   bv->ops.tsqr_formq = BVTSQRFormQ_CPU;
+  if (getenv("ORACLE_KRYLOV_STEPS")) bv->ops.krylov_steps = BVKrylovSteps_CPU;     /* test double, see above */
   return PETSC_SUCCESS;
 }
 

@@ -6,6 +6,7 @@ The product's own BV type needs a GPU and is covered by tests/test_slepc_gpu.py 
 driver is what is under test, the arithmetic comes from oracle/oracle_cpu.c.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -412,3 +413,61 @@ def test_bv_set_matrix_inner_product():
         Q = X.to_numpy()
         assert np.linalg.norm(Q.T @ (B @ Q) - np.eye(k)) < 1e-13
     X.destroy()
+
+
+# ---- BVKrylovLoop_Private with a type that runs stretches of the recurrence on its own (ops.krylov_steps) ---------------------------
+def _solve_with_krylov_steps(pattern, kind):
+    """the CPU plug-in's test double of the krylov_steps slot (oracle_cpu.c BVKrylovSteps_CPU): completes pattern[i] steps on its
+    i-th call, declines on 0, and on a negative entry leaves one more step half done (what a device-side breakdown looks like)"""
+    import scipy.sparse as sp
+    old = os.environ.get("ORACLE_KRYLOV_STEPS")
+    if pattern is None:
+        os.environ.pop("ORACLE_KRYLOV_STEPS", None)
+    else:
+        os.environ["ORACLE_KRYLOV_STEPS"] = pattern
+    try:
+        x0 = None
+        if kind == "lanczos":
+            A, herm, nev, ncv, which = O.laplacian_2d(30), True, 4, 16, None
+        elif kind == "arnoldi":
+            A, herm, nev, ncv, which = O.markov_model(25), False, 4, 14, SL.EPS_LARGEST_REAL
+            x0 = np.zeros(A.shape[0]); x0[:3] = 1.0
+        else:                                           # exact breakdown at the very first step: start vector = eigenvector
+            n = 400
+            A, herm, nev, ncv, which = sp.diags(np.repeat([1.0, 2.0, 3.5, 5.0, 9.0], n // 5)).tocsr(), True, 2, 12, None
+            x0 = np.zeros(n); x0[0] = 1.0
+        M = CP.mat_csr(A)
+        eps = SL.EPS(M, hermitian=herm)
+        CP.use_cpu_bv(eps)
+        if which is not None:
+            S.EPSSetWhichEigenpairs(eps.h, which)
+        S.EPSSetDimensions(eps.h, nev, ncv, SL.PETSC_DETERMINE)
+        keep = None
+        if x0 is not None:
+            keep, _ = M.create_vecs()
+            keep.set_values(x0)
+            S.EPSSetInitialSpace(eps.h, 1, (ctypes.c_void_p * 1)(keep.h))
+        eps.solve()
+        out = dict(its=eps.its, nconv=eps.nconv, reason=eps.reason, lam=[eps.eigenvalue(i) for i in range(eps.nconv)],
+                   errs=[eps.error(i) for i in range(eps.nconv)], passes=eps.bv().counters()[0])
+        for o in (eps, M) + ((keep,) if keep is not None else ()):
+            o.destroy()
+        return out
+    finally:
+        if old is None:
+            os.environ.pop("ORACLE_KRYLOV_STEPS", None)
+        else:
+            os.environ["ORACLE_KRYLOV_STEPS"] = old
+
+
+@pytest.mark.parametrize("kind", ["lanczos", "arnoldi", "breakdown"])
+@pytest.mark.parametrize("pattern", ["1000", "3", "1,0,2", "-2,5", "0,0,7", "-1"])
+def test_krylov_loop_resumes_after_a_type_run_stretch(kind, pattern):
+    """whatever part of a cycle the BV type completes on its own (all of it, a few steps, nothing, or a stretch that ends in a step
+    it disowns), BVMatLanczos / BVMatArnoldi finish the cycle step by step and ask again: iteration counts, converged pairs and
+    eigenvalues are bit-identical to the plain loop of bvkrylov.c:56-226"""
+    ref = _solve_with_krylov_steps(None, kind)
+    got = _solve_with_krylov_steps(pattern, kind)
+    assert ref["reason"] > 0 and ref["nconv"] >= 2
+    assert (got["its"], got["nconv"], got["reason"]) == (ref["its"], ref["nconv"], ref["reason"])
+    assert got["lam"] == ref["lam"] and got["errs"] == ref["errs"]
