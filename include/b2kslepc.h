@@ -240,6 +240,13 @@ PetscErrorCode BVDotVecEnd(BV X, Vec y, PetscScalar *m);                        
 PetscErrorCode BVDotColumnBegin(BV X, PetscInt j, PetscScalar *m);                      /* bvglobal.c:350 */
 PetscErrorCode BVDotColumnEnd(BV X, PetscInt j, PetscScalar *m);                        /* bvglobal.c:410 */
 PetscErrorCode BVNormColumnBegin(BV bv, PetscInt j, NormType type, PetscReal *val);     /* bvglobal.c:703 */
+PetscErrorCode BVNormVecBegin(BV bv, Vec v, NormType type, PetscReal *val);             /* bvglobal.c:575 (= VecNormBegin)      */
+PetscErrorCode BVNormVecEnd(BV bv, Vec v, NormType type, PetscReal *val);               /* bvglobal.c:616                       */
+/* PETSc's split-phase Vec reductions as bv/tests/test10.c uses them: stand-ins that evaluate at Begin (see host/bv.c) */
+PetscErrorCode VecDotBegin(Vec x, Vec y, PetscScalar *val);
+PetscErrorCode VecDotEnd(Vec x, Vec y, PetscScalar *val);
+PetscErrorCode VecNormBegin(Vec x, NormType type, PetscReal *val);
+PetscErrorCode VecNormEnd(Vec x, NormType type, PetscReal *val);
 PetscErrorCode BVNormColumnEnd(BV bv, PetscInt j, NormType type, PetscReal *val);       /* bvglobal.c:760 */
 PetscErrorCode BVMatMult(BV V, Mat A, BV Y);                                            /* bvops.c:767 */
 PetscErrorCode BVMatMultColumn(BV V, Mat A, PetscInt j);                                /* bvops.c:862 */

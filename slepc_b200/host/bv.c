@@ -685,6 +685,45 @@ PetscErrorCode BVNormColumnEnd(BV bv, PetscInt j, NormType type, PetscReal *val)
   return PETSC_SUCCESS;
 }
 
+/* BVNormVecBegin / BVNormVecEnd (bvglobal.c:575-636) are VecNormBegin / VecNormEnd for the standard inner product, i.e. PETSc's
+   split-phase Vec reductions, and bv/tests/test10.c pairs them with VecDotBegin / VecDotEnd.  PETSc is not here, so the four Vec
+   entry points are stand-ins that evaluate at Begin (the complete, reduced value) and hand the number out at End in FIFO order —
+   what PETSc itself does when split reductions are switched off; the BV-level pairs above are the ones that really merge. */
+#define B2K_EAGER_MAX 64
+static struct { double v[B2K_EAGER_MAX]; void *owner[B2K_EAGER_MAX]; int head, tail; } g_eager;
+static PetscErrorCode EagerPush_Private(void *owner, double v)
+{
+  PetscCheck(g_eager.tail - g_eager.head < B2K_EAGER_MAX, PETSC_ERR_ARG_SIZ, "too many outstanding split reductions");
+  g_eager.owner[g_eager.tail % B2K_EAGER_MAX] = owner; g_eager.v[g_eager.tail++ % B2K_EAGER_MAX] = v;
+  return PETSC_SUCCESS;
+}
+static PetscErrorCode EagerPop_Private(void *owner, double *v)
+{
+  PetscCheck(g_eager.head < g_eager.tail, PETSC_ERR_ARG_WRONGSTATE, "Called xxxEnd() more times than xxxBegin()");
+  PetscCheck(g_eager.owner[g_eager.head % B2K_EAGER_MAX] == owner, PETSC_ERR_ARG_WRONGSTATE, "Called xxxEnd() in a different order or on a different object than xxxBegin()");
+  *v = g_eager.v[g_eager.head++ % B2K_EAGER_MAX];
+  return PETSC_SUCCESS;
+}
+PetscErrorCode VecDotBegin(Vec x, Vec y, PetscScalar *val) { PetscScalar d; (void)val; PetscCall(VecDot(x, y, &d)); return EagerPush_Private((void *)x, d); }
+PetscErrorCode VecDotEnd(Vec x, Vec y, PetscScalar *val) { (void)y; return EagerPop_Private((void *)x, val); }
+PetscErrorCode VecNormBegin(Vec x, NormType type, PetscReal *val) { PetscReal d; (void)val; PetscCall(VecNorm(x, type, &d)); return EagerPush_Private((void *)x, d); }
+PetscErrorCode VecNormEnd(Vec x, NormType type, PetscReal *val) { (void)type; return EagerPop_Private((void *)x, val); }
+
+PetscErrorCode BVNormVecBegin(BV bv, Vec v, NormType type, PetscReal *val)
+{
+  BVCheckSizes(bv);
+  PetscCheck(v, PETSC_ERR_ARG_NULL, "null vector");
+  PetscCheck(!bv->matrix, PETSC_ERR_SUP, "split-phase reductions with a non-standard inner product are not available");
+  PetscCall(VecNormBegin(v, type, val));           /* bvglobal.c:602 */
+  return PETSC_SUCCESS;
+}
+PetscErrorCode BVNormVecEnd(BV bv, Vec v, NormType type, PetscReal *val)
+{
+  BVCheckSizes(bv);
+  PetscCall(VecNormEnd(v, type, val));             /* bvglobal.c:634 */
+  return PETSC_SUCCESS;
+}
+
 PetscErrorCode BVNorm(BV bv, NormType type, PetscReal *val)
 {
   BVCheckSizes(bv);

@@ -282,6 +282,104 @@ def scenario_test13(make_bv):
     X.destroy()
 
 
+def scenario_test10(make_bv, n=10, k=5):
+    """bv/tests/test10.c:51-111 (output/test10_1.out: `0.`): the split-phase operations — VecDotBegin/End, BVDotVecBegin/End,
+    BVDotColumnBegin/End, VecNormBegin/End, BVNormVecBegin/End, BVNormColumnBegin/End, posted together and collected in the
+    reference's order — give exactly what the regular operations give (the test prints the 1-norm of the difference: 0)"""
+    X = make_bv(n, k)
+    fill_test1(X, k, n)                                   # the same fill as test1 (test10.c:44-54)
+    v = ctypes.c_void_p()
+    S.BVCreateVec(X.h, ctypes.byref(v))
+    S.VecSet(v, 1.0)
+    z, zs = np.zeros(k + 6), np.zeros(k + 6)
+
+    def dptr(a, off):
+        return ctypes.cast(a.ctypes.data + 8 * off, ctypes.POINTER(ctypes.c_double))
+    nrm = c_dbl()
+    # regular operations
+    w = ctypes.c_void_p()
+    S.BVGetColumn(X.h, 0, ctypes.byref(w)); S.VecDot(w, v, dptr(z, 0)); S.BVRestoreColumn(X.h, 0, ctypes.byref(w))
+    S.BVDotVec(X.h, v, dptr(z, 1))
+    S.BVDotColumn(X.h, 2, dptr(z, 1 + k))
+    S.BVGetColumn(X.h, 1, ctypes.byref(w)); S.VecNorm(w, SL.NORM_2, ctypes.byref(nrm)); S.BVRestoreColumn(X.h, 1, ctypes.byref(w))
+    z[k + 3] = nrm.value
+    S.BVNormVec(X.h, v, SL.NORM_2, ctypes.byref(nrm)); z[k + 4] = nrm.value
+    S.BVNormColumn(X.h, 0, SL.NORM_2, ctypes.byref(nrm)); z[k + 5] = nrm.value
+    # split operations, posted and collected as test10.c:82-104 does
+    S.BVGetColumn(X.h, 0, ctypes.byref(w))
+    S.VecDotBegin(w, v, dptr(zs, 0))
+    S.BVDotVecBegin(X.h, v, dptr(zs, 1))
+    S.BVDotColumnBegin(X.h, 2, dptr(zs, 1 + k))
+    S.VecDotEnd(w, v, dptr(zs, 0))
+    S.BVRestoreColumn(X.h, 0, ctypes.byref(w))
+    S.BVDotVecEnd(X.h, v, dptr(zs, 1))
+    S.BVDotColumnEnd(X.h, 2, dptr(zs, 1 + k))
+    y = ctypes.c_void_p()
+    S.BVGetColumn(X.h, 1, ctypes.byref(y))
+    S.VecNormBegin(y, SL.NORM_2, ctypes.byref(nrm))
+    S.BVNormVecBegin(X.h, v, SL.NORM_2, ctypes.byref(nrm))
+    S.BVNormColumnBegin(X.h, 0, SL.NORM_2, ctypes.byref(nrm))
+    S.VecNormEnd(y, SL.NORM_2, ctypes.byref(nrm)); zs[k + 3] = nrm.value
+    S.BVRestoreColumn(X.h, 1, ctypes.byref(y))
+    S.BVNormVecEnd(X.h, v, SL.NORM_2, ctypes.byref(nrm)); zs[k + 4] = nrm.value
+    S.BVNormColumnEnd(X.h, 0, SL.NORM_2, ctypes.byref(nrm)); zs[k + 5] = nrm.value
+    assert np.abs(z - zs).sum() == 0.0, (z, zs)           # the reference prints "0."
+    # and the numbers themselves (numpy on the same fill)
+    A = X.to_numpy()
+    one = np.ones(n)
+    ref = np.concatenate([[A[:, 0] @ one], A.T @ one, A[:, :2].T @ A[:, 2], [np.linalg.norm(A[:, 1]), np.sqrt(n), np.linalg.norm(A[:, 0])]])
+    assert np.allclose(z, ref, rtol=1e-14, atol=1e-14), (z, ref)
+    S.VecDestroy(ctypes.byref(v))
+    X.destroy()
+
+
+def scenario_test18(make_bv, make_mat, n=250, l=6, k=15):
+    """bv/tests/test18.c (output/test18_1.out, args -n 250 -l 6 -k 15): BVNormalize of the active columns — plain 2-norms, B-norms
+    with the tridiagonal inner-product matrix of :98-109, and conjugate pairs (eigi != 0: the two columns of a pair are scaled
+    by the norm of the complex vector, :128-166); each deviation from 1 below the reference's 100 eps"""
+    import scipy.sparse as sp
+    X0 = np.zeros((n, k))
+    for j in range(k):
+        for i in range(n // 2 + 1):
+            if i + j < n:
+                X0[i + j, j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
+    X, Y, Z = make_bv(n, k), make_bv(n, k), make_bv(n, k)
+    for W in (X, Y, Z):
+        W.from_numpy(X0)
+        W.set_active(l, k)
+    S.BVNormalize(X.h, None)
+    assert max(abs(norm_column(X, j) - 1.0) for j in range(l, k)) < 100 * EPS
+    assert np.array_equal(X.to_numpy()[:, :l], X0[:, :l])                   # the leading columns are not touched
+    B = make_mat(sp.diags([np.full(n - 1, -1.0), np.full(n, 2.0), np.full(n - 1, -1.0)], [-1, 0, 1], format="csr"))
+    S.BVSetMatrix(Y.h, B.h, 0)
+    S.BVNormalize(Y.h, None)
+    assert max(abs(norm_column(Y, j) - 1.0) for j in range(l, k)) < 100 * EPS          # B-norms (BVNormColumn with a matrix)
+    Yn = Y.to_numpy()
+    Bd = sp.diags([np.full(n - 1, -1.0), np.full(n, 2.0), np.full(n - 1, -1.0)], [-1, 0, 1]).toarray()
+    assert max(abs(np.sqrt(Yn[:, j] @ Bd @ Yn[:, j]) - 1.0) for j in range(l, k)) < 100 * EPS
+    eigi = np.zeros(k)
+    rng = np.random.default_rng(18)
+    for j in range(l + 1, k - 1, 5):
+        a = rng.uniform(0.1, 1.0)
+        eigi[j], eigi[j + 1] = a, -a
+    S.BVNormalize(Z.h, eigi.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    Zn = Z.to_numpy()
+    j, err = l, 0.0
+    while j < k:
+        if eigi[j] != 0.0:
+            nr = np.hypot(np.linalg.norm(Zn[:, j]), np.linalg.norm(Zn[:, j + 1]))
+            nr0 = np.hypot(np.linalg.norm(X0[:, j]), np.linalg.norm(X0[:, j + 1]))          # both columns of a pair by the same factor
+            assert np.allclose(Zn[:, j], X0[:, j] / nr0, rtol=1e-14, atol=0) and np.allclose(Zn[:, j + 1], X0[:, j + 1] / nr0, rtol=1e-14, atol=0)
+            j += 1
+        else:
+            nr = np.linalg.norm(Zn[:, j])
+        err = max(err, abs(nr - 1.0))
+        j += 1
+    assert err < 100 * EPS
+    for o in (X, Y, Z, B):
+        o.destroy()
+
+
 def scenario_errors(make_bv):
     """error behaviour of the front-end (same checks and messages as bvops.c / bvbasic.c)"""
     X, Y = make_bv(10, 5), make_bv(10, 3)

@@ -126,6 +126,52 @@ def main():
         norms_o = [Xo.orthonormalize_column(j)[0] for j in range(k)]
         res.update(orth=float(np.linalg.norm(Q.T @ Q - np.eye(k))), dq=float(np.abs(Q - Xo.V).max()),
                    dn=float(np.abs(np.array(norms) - np.array(norms_o)).max()))
+    elif case == "bvsplit":
+        # bv/tests/test10.c (its test list runs it on 2 ranks): split-phase operations posted together give exactly what the
+        # regular, individually reduced ones give; the merged reduction of the BV-level pairs is ONE callback all-reduce
+        n, k = 10, 5
+        rs, re = CP.split_rows(n, size)[rank]
+        Aglob = np.zeros((n, k))
+        for j in range(k):
+            for i in range(4):
+                if i + j < n:
+                    Aglob[i + j, j] = 3 * i + j - 2
+        X = CP.bv_cpu(re - rs, k, N=n, rstart=rs)
+        X.from_numpy(Aglob[rs:re])
+        v = ctypes.c_void_p()
+        S.BVCreateVec(X.h, ctypes.byref(v))
+        S.VecSet(v, 1.0)
+        z, zs = np.zeros(k + 6), np.zeros(k + 6)
+        dptr = lambda a, off: ctypes.cast(a.ctypes.data + 8 * off, ctypes.POINTER(ctypes.c_double))
+        nrm, w = ctypes.c_double(), ctypes.c_void_p()
+        S.BVGetColumn(X.h, 0, ctypes.byref(w)); S.VecDot(w, v, dptr(z, 0)); S.BVRestoreColumn(X.h, 0, ctypes.byref(w))
+        S.BVDotVec(X.h, v, dptr(z, 1))
+        S.BVDotColumn(X.h, 2, dptr(z, 1 + k))
+        S.BVGetColumn(X.h, 1, ctypes.byref(w)); S.VecNorm(w, SL.NORM_2, ctypes.byref(nrm)); S.BVRestoreColumn(X.h, 1, ctypes.byref(w))
+        z[k + 3] = nrm.value
+        S.BVNormVec(X.h, v, SL.NORM_2, ctypes.byref(nrm)); z[k + 4] = nrm.value
+        S.BVNormColumn(X.h, 0, SL.NORM_2, ctypes.byref(nrm)); z[k + 5] = nrm.value
+        S.BVGetColumn(X.h, 0, ctypes.byref(w))
+        S.VecDotBegin(w, v, dptr(zs, 0))
+        S.BVDotVecBegin(X.h, v, dptr(zs, 1))
+        S.BVDotColumnBegin(X.h, 2, dptr(zs, 1 + k))
+        S.VecDotEnd(w, v, dptr(zs, 0))
+        S.BVRestoreColumn(X.h, 0, ctypes.byref(w))
+        S.BVDotVecEnd(X.h, v, dptr(zs, 1))
+        S.BVDotColumnEnd(X.h, 2, dptr(zs, 1 + k))
+        S.BVGetColumn(X.h, 1, ctypes.byref(w))
+        S.VecNormBegin(w, SL.NORM_2, ctypes.byref(nrm))
+        S.BVNormVecBegin(X.h, v, SL.NORM_2, ctypes.byref(nrm))
+        S.BVNormColumnBegin(X.h, 0, SL.NORM_2, ctypes.byref(nrm))
+        S.VecNormEnd(w, SL.NORM_2, ctypes.byref(nrm)); zs[k + 3] = nrm.value
+        S.BVRestoreColumn(X.h, 1, ctypes.byref(w))
+        S.BVNormVecEnd(X.h, v, SL.NORM_2, ctypes.byref(nrm)); zs[k + 4] = nrm.value
+        S.BVNormColumnEnd(X.h, 0, SL.NORM_2, ctypes.byref(nrm)); zs[k + 5] = nrm.value
+        one = np.ones(n)
+        ref = np.concatenate([[Aglob[:, 0] @ one], Aglob.T @ one, Aglob[:, :2].T @ Aglob[:, 2],
+                              [np.linalg.norm(Aglob[:, 1]), np.sqrt(n), np.linalg.norm(Aglob[:, 0])]])
+        res.update(diff=float(np.abs(z - zs).sum()), err=float(np.abs(z - ref).max()))
+        S.VecDestroy(ctypes.byref(v))
     elif case in ("bvchol", "bvsvqb", "bvtsqr", "bvtsqrchol"):
         # BVOrthogonalize CHOL / SVQB (bvorthog.c:586-675) on a split basis with 2 leading columns: the Gram matrix is
         # globally reduced by BVDot, the k x k factorisation is replicated, BVMult/BVMultInPlace are local

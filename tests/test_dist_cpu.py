@@ -51,6 +51,13 @@ def test_bv_orthonormalize_split_rows(world, tmp_path):
 
 
 @pytest.mark.parametrize("world", [2, 3])
+def test_bv_test10_split_reductions_split_rows(world, tmp_path):
+    """bv/tests/test10.c on 2 ranks (its own test list) and on 3: the reference prints `0.` for the difference"""
+    r = run_case("bvsplit", world, tmp_path)
+    assert r["diff"] < 1e-14 and r["err"] < 1e-13, r
+
+
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("case", ["bvchol", "bvsvqb", "bvtsqr", "bvtsqrchol"])
 def test_bv_block_orthogonalize_split_rows(case, world, tmp_path):
     if world == 3 and case in ("bvchol", "bvsvqb"):

@@ -69,6 +69,14 @@ def test_bv_test13():
     SC.scenario_test13(make_bv)
 
 
+def test_bv_test10_split_reductions():
+    SC.scenario_test10(make_bv)
+
+
+def test_bv_test18_normalize():
+    SC.scenario_test18(make_bv, CP.mat_csr)
+
+
 def test_bv_errors():
     SC.scenario_errors(make_bv)
 
