@@ -1260,10 +1260,10 @@ static PetscErrorCode BVOrthogonalize_GS(BV V, Mat R)
   const PetscInt lsave = V->l, ksave = V->k;
   for (PetscInt j = lsave; j < ksave; j++) {
     PetscReal norm;
-    PetscBool lindep;
     V->l = lsave; V->k = ksave;
-    PetscCall(BVOrthogonalizeColumn(V, j, NULL, &norm, &lindep));
-    PetscCheck(norm != 0.0 && !lindep, PETSC_ERR_CONV_FAILED, "Breakdown in the Gram-Schmidt block orthogonalization: column %d is linearly dependent", j);
+    PetscCall(BVOrthogonalizeColumn(V, j, NULL, &norm, NULL));       /* the reference does not ask for lindep here (bvorthog.c:531-538): a
+                                                                         dependent column is reduced to noise and normalised, bv/tests/test12.c */
+    PetscCheck(norm != 0.0, PETSC_ERR_CONV_FAILED, "Breakdown in BVOrthogonalize due to a linearly dependent column");
     PetscCall(V->ops.scale(V, j, 1.0 / norm));
     if (r) {
       for (PetscInt i = 0; i < j; i++) r[i + (size_t)j * ldr] = BV_BUF(V, V->nc + i, j);

@@ -333,6 +333,40 @@ def scenario_test10(make_bv, n=10, k=5):
     X.destroy()
 
 
+def scenario_test12(make_bv, n=20, k=8):
+    """bv/tests/test12.c (output/test12_1.out, -bv_orthog_block gs): block orthogonalisation of a RANK-DEFICIENT basis — column k/2
+    depends on columns 0 and 1, column k-1 on columns 1 and k/2+1.  BVOrthogonalize_GS (bvorthog.c:506-550) does not ask for
+    the linear-dependence flag: the dependent column is reduced to rounding noise, re-orthogonalised by the DGKS passes and
+    normalised, R(j,j) is tiny, and both checks hold at the reference's 100 eps"""
+    def col(j):
+        c = np.zeros(n)
+        for i in range(n // 2 + 1):
+            if i + j < n:
+                c[i + j] = (3.0 * i + j - 2) / (2 * (i + j + 1))
+        return c
+    X0 = np.zeros((n, k))
+    for j in range(k // 2):
+        X0[:, j] = col(j)
+    j = k // 2
+    X0[:, j] = X0[:, 0] + 0.5 * X0[:, 1]
+    for j in range(k // 2 + 1, k - 1):
+        X0[:, j] = col(j)
+    X0[:, k - 1] = X0[:, 1] - 1.2 * X0[:, k // 2 + 1]
+    X = make_bv(n, k)
+    X.from_numpy(X0)
+    S.BVSetOrthogonalization(X.h, SL.BV_ORTHOG_CGS, SL.BV_ORTHOG_REFINE_IFNEEDED, 0.7071, SL.BV_ORTHOG_BLOCK_GS)
+    R = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVOrthogonalize(X.h, R.h)
+    M = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVDot(X.h, X.h, M.h)
+    assert np.abs(M.dense_array() - np.eye(k)).sum(axis=0).max() < 100 * EPS          # MatNorm(M - I, NORM_1): level of orthogonality
+    assert np.linalg.norm(X0 - X.to_numpy() @ R.dense_array()) < 100 * EPS             # residual ||X - QR||_F
+    Rm = R.dense_array()
+    assert abs(Rm[k // 2, k // 2]) < 1e-13 and abs(Rm[k - 1, k - 1]) < 1e-13          # the two dependent columns
+    for o in (X, R, M):
+        o.destroy()
+
+
 def scenario_test18(make_bv, make_mat, n=250, l=6, k=15):
     """bv/tests/test18.c (output/test18_1.out, args -n 250 -l 6 -k 15): BVNormalize of the active columns — plain 2-norms, B-norms
     with the tridiagonal inner-product matrix of :98-109, and conjugate pairs (eigi != 0: the two columns of a pair are scaled

@@ -73,6 +73,10 @@ def test_bv_test10_split_reductions():
     SC.scenario_test10(make_bv)
 
 
+def test_bv_test12_rank_deficient_block_gs():
+    SC.scenario_test12(make_bv)
+
+
 def test_bv_test18_normalize():
     SC.scenario_test18(make_bv, CP.mat_csr)
 
