@@ -20,6 +20,9 @@ FILES = {
     "sys/classes/bv/tests/output/test13_1.out": ("sys/classes/bv/tests/test13.c", "n=10 k=5"),
     "eps/tests/output/test4_1.out": ("eps/tests/test4.c", "1-D Laplacian n=30 nev=4 -eps_type krylovschur"),
     "eps/tests/output/test2_1.out": ("eps/tests/test2.c", "1-D Laplacian n=30 nev=4: largest / smallest / interior(target 2.1, sinvert)"),
+    "eps/tests/output/test1_1.out": ("eps/tests/test1.c", "GHEP: 2-D Laplacian 18x18, B = diag(2/log(i+2)), nev=4 (B-orthonormal eigenvectors)"),
+    "eps/tests/output/test6_1.out": ("eps/tests/test6.c", "diagonal matrix 1..30, nev=4"),
+    "eps/tutorials/output/ex13_1.out": ("eps/tutorials/ex13.c", "GHEP sinvert: 2-D Laplacian 10x10, B = 4 I, nev=4 ncv=22 tol=1e-5"),
     "eps/tutorials/output/ex2_1.out": ("eps/tutorials/ex2.c", "2-D Laplacian n=72 nev=4"),
     "eps/tutorials/output/ex5_1.out": ("eps/tutorials/ex5.c", "Markov m=15 nev=4 -eps_largest_real"),
     "svd/tests/output/test3_1.out": ("svd/tests/test3.c", "Grcar-like 35x30 nsv=4 trlanczos"),

@@ -127,3 +127,44 @@ def test_bv_norm_goldens():
     assert len(gold) == k - 1
     for x, g in zip(z, gold):
         assert f"{abs(x):g}" == f"{abs(g):g}"
+
+
+def test_eps_test1_ghep_b_orthonormality():
+    """eps/tests/test1.c (-n 18 -eps_nev 4, krylovschur): A x = k B x with the 5-point Laplacian and B = diag(2/log(i+2)), largest
+    eigenvalues with the default STSHIFT (B^-1 A through the ST), B-inner product in the basis; the reference then checks that the
+    eigenvectors are B-orthonormal to 10 tol (VecCheckOrthonormality, test1.c:97-101)"""
+    import scipy.sparse as sp
+    n = int(round(np.sqrt(rows("eps/tests/output/test1_1.out")[0][0])))
+    N = n * n
+    gold = rows("eps/tests/output/test1_1.out")[1]
+    A = O.laplacian_2d(n).tocsr()
+    B = sp.diags(2.0 / np.log(np.arange(N) + 2.0)).tocsr()
+    tol = 1e-10                                                   # PETSC_SMALL, test1.c:24
+    r = O.eps_krylovschur(A, N, nev=4, tol=tol, B=B)
+    assert r.reason > 0 and r.nconv >= 4
+    lam = r.eigr[r.perm]
+    for x, g in zip(lam[:4], gold):
+        assert close5(x, g)
+    X = r.X[:, r.perm[:r.nconv]]
+    assert np.abs(X.T @ (B @ X) - np.eye(r.nconv)).max() < 10 * tol
+
+
+def test_eps_test6_diagonal():
+    """eps/tests/test6.c: diag(1..30), nev=4, tol = PETSC_SMALL: 30, 29, 28, 27"""
+    import scipy.sparse as sp
+    n = int(rows("eps/tests/output/test6_1.out")[0][0])
+    gold = rows("eps/tests/output/test6_1.out")[1]
+    r = O.eps_krylovschur(sp.diags(np.arange(1.0, n + 1)).tocsr(), n, nev=4, tol=1e-10)
+    assert r.nconv >= 4
+    for x, g in zip(np.sort(r.eigr[:r.nconv])[::-1][:4], gold):
+        assert close5(x, g)
+
+
+def test_eps_ex13_generalized_sinvert():
+    import scipy.sparse as sp
+    gold = rows("eps/tutorials/output/ex13_1.out")[2]
+    n = 10
+    r = O.eps_krylovschur(O.laplacian_2d(n), n * n, nev=4, ncv=22, tol=1e-5, B=sp.identity(n * n, format="csr") * 4.0, sigma=0.0, sinvert=True)
+    assert r.nconv >= 4
+    for x, g in zip(r.eigr[r.perm][:4], gold):
+        assert close5(x, g)

@@ -483,3 +483,45 @@ def test_krylov_loop_resumes_after_a_type_run_stretch(kind, pattern):
     assert ref["reason"] > 0 and ref["nconv"] >= 2
     assert (got["its"], got["nconv"], got["reason"]) == (ref["its"], ref["nconv"], ref["reason"])
     assert got["lam"] == ref["lam"] and got["errs"] == ref["errs"]
+
+
+def test_eps_test1_ghep_b_orthonormality_host():
+    """eps/tests/test1.c through the C host driver on the CPU plug-in: golden 21.89996, 21.65898, 21.28794, 20.82229
+    (output/test1_1.out) and B-orthonormal eigenvectors to 10 tol"""
+    import scipy.sparse as sp
+    n = 18
+    N = n * n
+    A = O.laplacian_2d(n).tocsr()
+    B = sp.diags(2.0 / np.log(np.arange(N) + 2.0)).tocsr()
+    Am, Bm = CP.mat_csr(A), CP.mat_csr(B)
+    eps = SL.EPS(Am, hermitian=True, B=Bm)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.EPSSetTolerances(eps.h, 1e-10, SL.PETSC_CURRENT)
+    eps.solve()
+    assert eps.reason > 0 and eps.nconv >= 4
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["21.89996", "21.65898", "21.28794", "20.82229"]
+    ref = O.eps_krylovschur(A, N, nev=4, tol=1e-10, B=B)
+    assert (eps.nconv, eps.its) == (ref.nconv, ref.its)
+    x, _ = Am.create_vecs()
+    X = []
+    for i in range(eps.nconv):
+        S.EPSGetEigenpair(eps.h, i, None, None, x.h, None)
+        X.append(x.get_values().copy())
+    X = np.array(X).T
+    assert np.abs(X.T @ (B @ X) - np.eye(eps.nconv)).max() < 10 * 1e-10
+    for o in (eps, x, Am, Bm):
+        o.destroy()
+
+
+def test_eps_test6_diagonal_host():
+    import scipy.sparse as sp
+    Am = CP.mat_csr(sp.diags(np.arange(1.0, 31.0)).tocsr())
+    eps = SL.EPS(Am, hermitian=True)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.EPSSetTolerances(eps.h, 1e-10, SL.PETSC_CURRENT)
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["30.00000", "29.00000", "28.00000", "27.00000"]   # output/test6_1.out
+    for o in (eps, Am):
+        o.destroy()
