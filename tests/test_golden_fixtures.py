@@ -168,3 +168,22 @@ def test_eps_ex13_generalized_sinvert():
     assert r.nconv >= 4
     for x, g in zip(r.eigr[r.perm][:4], gold):
         assert close5(x, g)
+
+
+def _bidiag_20x22():
+    import scipy.sparse as sp
+    m, n = 20, 22
+    A = sp.lil_matrix((m, n))
+    for i in range(m):
+        A[i, i], A[i, i + 1] = 1.0, 2.0                             # svd/tests/test4.c:57-61
+    return A.tocsr()
+
+
+def test_svd_test4_more_columns_than_rows():
+    """svd/tests/test4.c suffix 1_trlanczos (-svd_ncv 12 -svd_trlanczos_restart 0.6): 20 x 22 bidiagonal matrix, i.e. M < N — SVDSetUp
+    swaps the roles of A and A^T (svdsetup.c:254-263), the oracle is called on the swapped pair; golden 2.99254"""
+    gold = rows("svd/tests/output/test4_1.out")[-1][0]
+    A = _bidiag_20x22()
+    r = O.svd_trlanczos(A.T.tocsr(), A, 22, 20, nsv=1, ncv=12, keep=0.6)
+    assert r.nconv >= 1 and close5(r.sigma[0], gold)
+    assert abs(r.sigma[0] - np.linalg.svd(A.toarray(), compute_uv=False)[0]) < 1e-10 * r.sigma[0]

@@ -525,3 +525,32 @@ def test_eps_test6_diagonal_host():
     assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["30.00000", "29.00000", "28.00000", "27.00000"]   # output/test6_1.out
     for o in (eps, Am):
         o.destroy()
+
+
+def test_svd_test4_more_columns_than_rows_host():
+    """svd/tests/test4.c (1_trlanczos) through the C host driver: M < N, so SVDSetUp works on the transposed pair and hands the
+    vectors back in the caller's roles (u of length 20, v of length 22); golden 2.99254, same restarts as the oracle"""
+    import scipy.sparse as sp
+    m, n = 20, 22
+    A = sp.lil_matrix((m, n))
+    for i in range(m):
+        A[i, i], A[i, i + 1] = 1.0, 2.0
+    A = A.tocsr()
+    Am, ATm = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(Am, ATm)
+    CP.use_cpu_bv(svd)
+    S.SVDSetDimensions(svd.h, 1, 12, SL.PETSC_DETERMINE)
+    S.SVDTRLanczosSetRestart(svd.h, 0.6)
+    svd.solve()
+    ref = O.svd_trlanczos(A.T.tocsr(), A, n, m, nsv=1, ncv=12, keep=0.6)
+    assert (svd.nconv, svd.its) == (ref.nconv, ref.its) and svd.nconv >= 1
+    assert f"{svd.triplet(0):.5f}" == "2.99254"                    # output/test4_1.out
+    assert svd.error(0) < 5e-8
+    v, u = Am.create_vecs()                                        # v: column space (22), u: row space (20)
+    sigma = c_dbl()
+    S.SVDGetSingularTriplet(svd.h, 0, ctypes.byref(sigma), u.h, v.h)
+    uu, vv = u.get_values(), v.get_values()
+    assert len(uu) == m and len(vv) == n
+    assert np.linalg.norm(A @ vv - sigma.value * uu) < 1e-8 and np.linalg.norm(A.T @ uu - sigma.value * vv) < 1e-8
+    for o in (svd, u, v, Am, ATm):
+        o.destroy()
