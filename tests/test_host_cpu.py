@@ -554,3 +554,27 @@ def test_svd_test4_more_columns_than_rows_host():
     assert np.linalg.norm(A @ vv - sigma.value * uu) < 1e-8 and np.linalg.norm(A.T @ uu - sigma.value * vv) < 1e-8
     for o in (svd, u, v, Am, ATm):
         o.destroy()
+
+
+@pytest.mark.parametrize("locking", [0, 1])
+def test_eps_test2_multiple_solves_same_object(locking):
+    """eps/tests/test2.c (suffix 1_ks: -eps_type krylovschur -eps_krylovschur_locking {{0 1}}): several EPSSolve calls on ONE solver
+    object with the same matrix, changing the wanted part of the spectrum in between; goldens output/test2_1.out rows 1 and 2
+    (the interior part uses harmonic extraction, outside this path)"""
+    Am = CP.mat_csr(O.laplacian_1d(30))
+    eps = SL.EPS(Am, hermitian=True)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.EPSKrylovSchurSetLocking(eps.h, locking)
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_LARGEST_REAL)
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_SMALLEST_REAL)
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["0.01026", "0.04094", "0.09172", "0.16208"]
+    assert max(eps.error(i) for i in range(4)) < 5e-8
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_LARGEST_REAL)            # and back: nothing of the previous solve may leak
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    for o in (eps, Am):
+        o.destroy()
