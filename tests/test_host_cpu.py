@@ -578,3 +578,29 @@ def test_eps_test2_multiple_solves_same_object(locking):
     assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
     for o in (eps, Am):
         o.destroy()
+
+
+def test_eps_test3_multiple_solves_different_matrices():
+    """eps/tests/test3.c: EPSSetOperators with a second matrix on the SAME solver object, then EPSSolve again (tridiagonal -1 / random
+    diagonal / -1, n = 30, nev = 4).  The reference's printed values depend on PetscRandom, so the pin is numpy's eigvalsh of the
+    two matrices (1e-10 relative) and the -terse residual criterion"""
+    import scipy.sparse as sp
+    n = 30
+    rng = np.random.default_rng(3)
+    mats = [sp.diags([np.full(n - 1, -1.0), rng.uniform(0, 1, n), np.full(n - 1, -1.0)], [-1, 0, 1], format="csr") for _ in range(2)]
+    Ms = [CP.mat_csr(A) for A in mats]
+    eps = SL.EPS(Ms[0], hermitian=True)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    S.EPSSetTolerances(eps.h, 1e-10, SL.PETSC_CURRENT)
+    for A, M in zip(mats, Ms):
+        S.EPSSetOperators(eps.h, M.h, None)
+        eps.solve()
+        assert eps.reason > 0 and eps.nconv >= 4
+        w = np.linalg.eigvalsh(A.toarray())
+        ref = w[np.argsort(-np.abs(w))][:4]                        # default: largest magnitude
+        lam = np.array([eps.eigenvalue(i)[0] for i in range(4)])
+        assert np.allclose(lam, ref, rtol=1e-10, atol=0), (lam, ref)
+        assert max(eps.error(i) for i in range(4)) < 5e-10
+    for o in [eps] + Ms:
+        o.destroy()
