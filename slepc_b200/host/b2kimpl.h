@@ -187,6 +187,7 @@ struct _p_BV {
 };
 #define BV_BUF(bv, i, j) ((bv)->buffer[(size_t)(i) + (size_t)(j) * ((bv)->nc + (bv)->m)])
 PetscErrorCode BVCreate_B200(BV bv);
+PetscErrorCode BVForgetSizes_Private(BV bv);     /* bv.c: the basis of a solver whose operator changed size */
 /* h += c on rows 0..nc+j-1 (NULL = the buffer: column j += column 0) — BV_AddCoefficients bvimpl.h:308-322 */
 static inline void BV_AddCoefficients(BV bv, PetscInt j, PetscScalar *h, PetscScalar *c)
 {

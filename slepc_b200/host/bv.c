@@ -81,6 +81,21 @@ PetscErrorCode BVDestroy(BV *bv)
   return PETSC_SUCCESS;
 }
 
+/* what EPSReset / SVDReset do to the basis when a solver is given an operator of another size (epssetup.c:441-458,
+   svdsetup.c:107-116: the BV is destroyed and created again at the next set-up): the storage and the sizes go, the type, the
+   orthogonalisation options and the random seed stay */
+PetscErrorCode BVForgetSizes_Private(BV bv)
+{
+  PetscErrorCode (*ctor)(BV) = bv->ctor;
+  PetscCall(BVReset_Private(bv));
+  bv->sizes_set = PETSC_FALSE;
+  bv->n = bv->N = bv->m = 0; bv->l = bv->k = 0; bv->nc = 0; bv->ld = 0; bv->row0 = 0;
+  bv->ci[0] = bv->ci[1] = -1;
+  bv->matrix = NULL;
+  bv->ctor = ctor;                                /* BVConstruct_Private runs it again once the new sizes are known */
+  return PETSC_SUCCESS;
+}
+
 static PetscErrorCode BVAllocateBuffers_Private(BV bv)
 {
   const size_t ldb = (size_t)(bv->nc + bv->m);

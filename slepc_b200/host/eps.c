@@ -49,6 +49,12 @@ PetscErrorCode EPSSetOperators(EPS eps, Mat A, Mat B)
   PetscCheck(A, PETSC_ERR_ARG_NULL, "null matrix");
   PetscCheck(A->M == A->N, PETSC_ERR_ARG_WRONG, "A is a non-square matrix (%d rows, %d cols)", A->M, A->N);
   if (B) PetscCheck(B->M == B->N && B->M == A->M, PETSC_ERR_ARG_WRONG, "Dimensions of A and B do not match (%d, %d)", A->M, B->M);   /* epssetup.c:446-452 */
+  if (eps->V && eps->V->sizes_set && (eps->V->N != A->N || eps->V->n != A->n)) {    /* EPSReset: epssetup.c:441-458 (different dimension) */
+    PetscCall(BVForgetSizes_Private(eps->V));
+    for (int i = 0; i < 5; i++) PetscCall(VecDestroy(&eps->work[i]));
+    PetscCall(VecDestroy(&eps->inivec));
+    eps->nini = 0;
+  }
   Mat mats[2] = {A, B};
   PetscCall(STSetMatrices(eps->st, B ? 2 : 1, mats));
   eps->B = B;

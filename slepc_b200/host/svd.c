@@ -46,6 +46,19 @@ PetscErrorCode SVDSetOperators(SVD svd, Mat A, Mat B)
 {
   PetscCheck(A, PETSC_ERR_ARG_NULL, "null matrix");
   PetscCheck(!B, PETSC_ERR_SUP, "the generalized SVD is outside the Krylov hot path");
+  if (svd->OP && (svd->OP->M != A->M || svd->OP->N != A->N || svd->OP->m != A->m || svd->OP->n != A->n)) {
+    /* SVDReset, svdsetup.c:107-116: another size ⇒ the bases, the work vectors and the initial vectors go; a transpose given for the
+       old matrix cannot belong to the new one */
+    if (svd->owns_AT) { if (svd->swapped) PetscCall(MatDestroy(&svd->A)); else PetscCall(MatDestroy(&svd->AT)); svd->owns_AT = PETSC_FALSE; }
+    svd->A = svd->AT = NULL;
+    if (svd->swapped) { BV bv = svd->V; svd->V = svd->U; svd->U = bv; svd->swapped = PETSC_FALSE; }
+    if (svd->V->sizes_set) PetscCall(BVForgetSizes_Private(svd->V));
+    if (svd->U->sizes_set) PetscCall(BVForgetSizes_Private(svd->U));
+    for (int i = 0; i < 4; i++) PetscCall(VecDestroy(&svd->work[i]));
+    PetscCall(VecDestroy(&svd->iniV));
+    PetscCall(VecDestroy(&svd->iniU));
+    svd->userAT = NULL;
+  }
   svd->OP = A;
   svd->setup_done = PETSC_FALSE; svd->solved = PETSC_FALSE;
   return PETSC_SUCCESS;

@@ -27,6 +27,9 @@ FILES = {
     "eps/tutorials/output/ex5_1.out": ("eps/tutorials/ex5.c", "Markov m=15 nev=4 -eps_largest_real"),
     "svd/tests/output/test3_1.out": ("svd/tests/test3.c", "Grcar-like 35x30 nsv=4 trlanczos"),
     "svd/tutorials/output/ex8_1.out": ("svd/tutorials/ex8.c", "Grcar n=30: sigma_1, sigma_n, condition number"),
+    "svd/tests/output/test8_1.out": ("svd/tests/test8.c", "Grcar n=30 nsv=3 ncv=12 tol=1e-6, solved twice (ncv, ncv+2)"),
+    "svd/tests/output/test9_1.out": ("svd/tests/test9.c", "Grcar n=30 then n=60 on the same SVD object, nsv=3"),
+    "svd/tests/output/test14_1.out": ("svd/tests/test14.c", "two 20x22 bidiagonal matrices on the same SVD object, nsv=3"),
     "svd/tests/output/test4_1.out": ("svd/tests/test4.c", "rectangular bidiagonal 20x22 (more columns than rows), suffix 1_trlanczos: ncv=12 restart 0.6"),
 }
 NUM = re.compile(r"(?<![\w.])[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?(?![\w])")

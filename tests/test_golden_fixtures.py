@@ -187,3 +187,33 @@ def test_svd_test4_more_columns_than_rows():
     r = O.svd_trlanczos(A.T.tocsr(), A, 22, 20, nsv=1, ncv=12, keep=0.6)
     assert r.nconv >= 1 and close5(r.sigma[0], gold)
     assert abs(r.sigma[0] - np.linalg.svd(A.toarray(), compute_uv=False)[0]) < 1e-10 * r.sigma[0]
+
+
+def _bidiag_b_20x22():
+    import scipy.sparse as sp
+    m, n = 20, 22
+    B = sp.lil_matrix((m, n))
+    for i in range(m):
+        if i == 0:
+            B[i, i] = 1.0
+        else:
+            B[i, i - 1], B[i, i] = 2.0, 1.0                         # svd/tests/test14.c:66-70
+    return B.tocsr()
+
+
+def test_svd_test8_test9_test14_values():
+    """the matrices of svd/tests/test8.c, test9.c (Grcar 30 and 60) and test14.c (two 20 x 22 bidiagonals), nsv = 3: the reference's
+    printed singular values (their object-reuse side is tested on the C host driver, tests/test_host_cpu.py)"""
+    g30 = rows("svd/tests/output/test8_1.out")[1]
+    assert g30 == rows("svd/tests/output/test8_1.out")[2] == rows("svd/tests/output/test9_1.out")[1]
+    for n, gold, ncv in ((30, g30, 12), (30, g30, 14), (60, rows("svd/tests/output/test9_1.out")[3], None)):
+        A = O.grcar_rect(n, n)
+        r = O.svd_trlanczos(A, A.T.tocsr(), n, n, nsv=3, ncv=ncv, tol=1e-6)
+        assert r.nconv >= 3
+        for x, g in zip(r.sigma[:3], gold):
+            assert close5(x, g)
+    for A, gold in ((_bidiag_20x22(), rows("svd/tests/output/test14_1.out")[1]), (_bidiag_b_20x22(), rows("svd/tests/output/test14_1.out")[2])):
+        r = O.svd_trlanczos(A.T.tocsr(), A, 22, 20, nsv=3)
+        assert r.nconv >= 3
+        for x, g in zip(r.sigma[:3], gold):
+            assert close5(x, g)

@@ -604,3 +604,82 @@ def test_eps_test3_multiple_solves_different_matrices():
         assert max(eps.error(i) for i in range(4)) < 5e-10
     for o in [eps] + Ms:
         o.destroy()
+
+
+def _svd_values(svd, nsv, ncv=None):
+    S.SVDSetDimensions(svd.h, nsv, ncv or SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    svd.solve()
+    assert svd.nconv >= nsv and max(svd.error(i) for i in range(nsv)) < 5e-6
+    return [f"{svd.triplet(i):.5f}" for i in range(nsv)]
+
+
+def test_svd_test8_resolve_with_larger_subspace():
+    """svd/tests/test8.c: SVDSolve, then SVDSetDimensions(nsv, ncv+2) and SVDSolve again on the same object (output/test8_1.out)"""
+    A = O.grcar_rect(30, 30)
+    Am, ATm = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(Am, ATm)
+    CP.use_cpu_bv(svd)
+    S.SVDSetTolerances(svd.h, 1e-6, 1000)
+    assert _svd_values(svd, 3, 12) == ["3.22149", "3.21754", "3.16696"]
+    assert _svd_values(svd, 3, 14) == ["3.22149", "3.21754", "3.16696"]
+    for o in (svd, Am, ATm):
+        o.destroy()
+
+
+def test_svd_test9_test14_new_operator_on_the_same_object():
+    """svd/tests/test9.c (a matrix of ANOTHER size: SVDSetOperators resets the bases, svdsetup.c:107-116) and test14.c (same size),
+    goldens output/test9_1.out and test14_1.out; then a tall matrix after a wide one (the M < N swap state must not leak)"""
+    import scipy.sparse as sp
+    mats = {}
+    for key, A in (("g30", O.grcar_rect(30, 30)), ("g60", O.grcar_rect(60, 60)), ("tall", O.grcar_rect(35, 30))):
+        mats[key] = (A, CP.mat_csr(A), CP.mat_csr(A.T.tocsr()))
+    m, n = 20, 22
+    A1, B1 = sp.lil_matrix((m, n)), sp.lil_matrix((m, n))
+    for i in range(m):
+        A1[i, i], A1[i, i + 1] = 1.0, 2.0
+        if i == 0:
+            B1[i, i] = 1.0
+        else:
+            B1[i, i - 1], B1[i, i] = 2.0, 1.0
+    for key, A in (("bidA", A1.tocsr()), ("bidB", B1.tocsr())):
+        mats[key] = (A, CP.mat_csr(A), CP.mat_csr(A.T.tocsr()))
+    svd = SL.SVD(mats["g30"][1], mats["g30"][2])
+    CP.use_cpu_bv(svd)
+    S.SVDSetTolerances(svd.h, 1e-6, 1000)
+
+    def switch(key):
+        S.SVDSetOperators(svd.h, mats[key][1].h, None)
+        S.SVDSetTransposeMatrix(svd.h, mats[key][2].h)
+    assert _svd_values(svd, 3) == ["3.22149", "3.21754", "3.16696"]
+    switch("g60")
+    assert _svd_values(svd, 3) == ["3.23585", "3.23548", "3.21932"]            # test9_1.out
+    switch("bidA")
+    assert _svd_values(svd, 3) == ["2.99254", "2.97023", "2.93324"]            # test14_1.out
+    switch("bidB")
+    assert _svd_values(svd, 3) == ["2.99205", "2.96825", "2.92879"]
+    switch("tall")
+    ref = np.linalg.svd(mats["tall"][0].toarray(), compute_uv=False)[:3]
+    assert _svd_values(svd, 3) == [f"{x:.5f}" for x in ref]
+    svd.destroy()
+    for _, a, b in mats.values():
+        a.destroy(); b.destroy()
+
+
+def test_eps_new_operator_of_another_size_on_the_same_object():
+    """EPSSetOperators with a matrix of another dimension (EPSReset, epssetup.c:441-458): the basis is rebuilt at the next set-up"""
+    M1, M2 = CP.mat_csr(O.laplacian_1d(30)), CP.mat_csr(O.laplacian_2d(12))
+    eps = SL.EPS(M1, hermitian=True)
+    CP.use_cpu_bv(eps)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    S.EPSSetOperators(eps.h, M2.h, None)
+    eps.solve()
+    ref = O.eps_krylovschur(O.laplacian_2d(12), 144, nev=4)
+    assert (eps.nconv, eps.its) == (ref.nconv, ref.its)
+    assert np.allclose([eps.eigenvalue(i)[0] for i in range(4)], ref.eigr[:4], rtol=1e-12, atol=0)
+    S.EPSSetOperators(eps.h, M1.h, None)
+    eps.solve()
+    assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
+    for o in (eps, M1, M2):
+        o.destroy()
