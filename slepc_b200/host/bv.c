@@ -728,14 +728,19 @@ PetscErrorCode BVNormVecBegin(BV bv, Vec v, NormType type, PetscReal *val)
 {
   BVCheckSizes(bv);
   PetscCheck(v, PETSC_ERR_ARG_NULL, "null vector");
-  PetscCheck(!bv->matrix, PETSC_ERR_SUP, "split-phase reductions with a non-standard inner product are not available");
-  PetscCall(VecNormBegin(v, type, val));           /* bvglobal.c:602 */
+  if (bv->matrix) {                                /* BVNorm_Begin_Private, bvglobal.c:597-601: sqrt(v' B v), evaluated here */
+    PetscReal d;
+    (void)val;
+    PetscCall(BVNormVec(bv, v, type, &d));
+    PetscCall(EagerPush_Private((void *)v, d));
+  } else PetscCall(VecNormBegin(v, type, val));    /* bvglobal.c:602 */
   return PETSC_SUCCESS;
 }
 PetscErrorCode BVNormVecEnd(BV bv, Vec v, NormType type, PetscReal *val)
 {
   BVCheckSizes(bv);
-  PetscCall(VecNormEnd(v, type, val));             /* bvglobal.c:634 */
+  if (bv->matrix) PetscCall(EagerPop_Private((void *)v, val));
+  else PetscCall(VecNormEnd(v, type, val));        /* bvglobal.c:634 */
   return PETSC_SUCCESS;
 }
 

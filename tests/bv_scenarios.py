@@ -333,6 +333,72 @@ def scenario_test10(make_bv, n=10, k=5):
     X.destroy()
 
 
+def scenario_test3(make_bv, make_mat, n=10, k=5):
+    """bv/tests/test3.c (output/test3_1.out): BV with the non-standard inner product of the tridiagonal B — B-norm of the first
+    column 8.94427, B-orthonormalisation column by column (level of B-orthogonality < 100 eps), then B-norm 1 through the
+    split-phase pair BVNormVecBegin / End"""
+    import scipy.sparse as sp
+    B = make_mat(sp.diags([np.full(n - 1, -1.0), np.full(n, 2.0), np.full(n - 1, -1.0)], [-1, 0, 1], format="csr"))
+    X = make_bv(n, k)
+    S.BVSetMatrix(X.h, B.h, 0)
+    fill_test1(X, k, n)                                   # test3.c:57-66, the fill of test1
+    assert g6(norm_column(X, 0)) == 8.94427
+    nrm = c_dbl()
+    for j in range(k):
+        S.BVOrthogonalizeColumn(X.h, j, None, ctypes.byref(nrm), None)
+        S.BVScaleColumn(X.h, j, 1.0 / nrm.value)
+    M = SL.Mat.seqdense(np.zeros((k, k)))
+    S.BVDot(X.h, X.h, M.h)
+    assert np.abs(M.dense_array() - np.eye(k)).sum(axis=0).max() < 100 * EPS
+    v = ctypes.c_void_p()
+    S.BVGetColumn(X.h, 0, ctypes.byref(v))
+    S.BVNormVecBegin(X.h, v, SL.NORM_1, ctypes.byref(nrm))     # the type is ignored with a matrix (bvglobal.c:569-572)
+    S.BVNormVecEnd(X.h, v, SL.NORM_1, ctypes.byref(nrm))
+    S.BVRestoreColumn(X.h, 0, ctypes.byref(v))
+    assert abs(nrm.value - 1.0) < 100 * EPS                    # the reference prints "1."
+    for o in (X, M, B):
+        o.destroy()
+
+
+def scenario_test7(make_bv, make_mat, m=10, k=5):
+    """bv/tests/test7.c (output/test7_1.out, `Norm of error: 0.` twice; the BVGetMat view in between is a viewer feature): Y(:,2:k+2) =
+    B X with the 1-D Laplacian B and X(:,j) = ones in the first j+1 rows, against the known answer (e_0 + e_j - e_{j+1}); then the
+    same product one column at a time (BVMatMultColumn on a shifted copy)"""
+    import scipy.sparse as sp
+    n = m
+    Bs = sp.diags([np.full(n - 1, -1.0), np.full(n, 2.0), np.full(n - 1, -1.0)], [-1, 0, 1], format="csr")
+    B = make_mat(Bs)
+    X0 = np.zeros((n, k))
+    for j in range(k):
+        X0[:j + 1, j] = 1.0
+    X, Y = make_bv(n, k), make_bv(m, k + 4)
+    X.from_numpy(X0)
+    Y.from_numpy(np.zeros((m, k + 4)))
+    Y.set_active(2, k + 2)
+    S.BVMatMult(X.h, B.h, Y.h)
+    Z0 = np.zeros((m, k))
+    for j in range(k):
+        Z0[0, j] += 1.0
+        if j < n:
+            Z0[j, j] += 1.0
+        if j + 1 < n:
+            Z0[j + 1, j] += -1.0
+    Yn = Y.to_numpy()
+    assert np.abs(Yn[:, 2:k + 2] - Z0).max() == 0.0           # "Norm of error: 0."
+    assert np.abs(Yn[:, :2]).max() == 0.0 and np.abs(Yn[:, k + 2:]).max() == 0.0      # the columns outside the active window are untouched
+    assert np.array_equal(Z0, Bs @ X0)
+    # column by column: W(:,j+1) = B W(:,j)
+    W = make_bv(n, 3)
+    W0 = np.zeros((n, 3)); W0[:, 0] = np.arange(1.0, n + 1)
+    W.from_numpy(W0)
+    S.BVMatMultColumn(W.h, B.h, 0)
+    S.BVMatMultColumn(W.h, B.h, 1)
+    Wn = W.to_numpy()
+    assert np.array_equal(Wn[:, 1], Bs @ W0[:, 0]) and np.array_equal(Wn[:, 2], Bs @ (Bs @ W0[:, 0]))
+    for o in (X, Y, W, B):
+        o.destroy()
+
+
 def scenario_test12(make_bv, n=20, k=8):
     """bv/tests/test12.c (output/test12_1.out, -bv_orthog_block gs): block orthogonalisation of a RANK-DEFICIENT basis — column k/2
     depends on columns 0 and 1, column k-1 on columns 1 and k/2+1.  BVOrthogonalize_GS (bvorthog.c:506-550) does not ask for

@@ -73,6 +73,14 @@ def test_bv_test10_split_reductions():
     SC.scenario_test10(make_bv)
 
 
+def test_bv_test3_nonstandard_inner_product():
+    SC.scenario_test3(make_bv, CP.mat_csr)
+
+
+def test_bv_test7_matmult():
+    SC.scenario_test7(make_bv, CP.mat_csr)
+
+
 def test_bv_test12_rank_deficient_block_gs():
     SC.scenario_test12(make_bv)
 
