@@ -691,3 +691,27 @@ def test_eps_new_operator_of_another_size_on_the_same_object():
     assert [f"{eps.eigenvalue(i)[0]:.5f}" for i in range(4)] == ["3.98974", "3.95906", "3.90828", "3.83792"]
     for o in (eps, M1, M2):
         o.destroy()
+
+
+def test_svd_ex15_lauchli_breakdown_in_the_first_cycle():
+    """svd/tutorials/ex15.c (output/ex15_1.out: 101 x 100 Lauchli matrix, mu = 1e-7, nsv = 1): the matrix has two distinct singular
+    values, so the bidiagonalisation breaks down inside the first cycle and TRLanczos accepts everything it has: `Number of
+    iterations of the method: 1`, `Number of converged approximate singular triplets: 10`, sigma_1 = 10.000000, the rest = mu"""
+    import scipy.sparse as sp
+    n, mu = 100, 1e-7
+    A = sp.lil_matrix((n + 1, n))
+    A[0, :] = 1.0
+    for i in range(1, n + 1):
+        A[i, i - 1] = mu                                          # ex15.c:43-48
+    A = A.tocsr()
+    Am, ATm = CP.mat_csr(A), CP.mat_csr(A.T.tocsr())
+    svd = SL.SVD(Am, ATm)
+    CP.use_cpu_bv(svd)
+    S.SVDSetDimensions(svd.h, 1, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    svd.solve()
+    ref = O.svd_trlanczos(A, A.T.tocsr(), n + 1, n, nsv=1)
+    assert (svd.nconv, svd.its) == (10, 1) == (ref.nconv, ref.its)
+    assert f"{svd.triplet(0):.6f}" == "10.000000"
+    assert all(f"{svd.triplet(i):.6f}" == "0.000000" and abs(svd.triplet(i) - mu) < 1e-12 for i in range(1, 10))
+    for o in (svd, Am, ATm):
+        o.destroy()
