@@ -715,3 +715,28 @@ def test_svd_ex15_lauchli_breakdown_in_the_first_cycle():
     assert all(f"{svd.triplet(i):.6f}" == "0.000000" and abs(svd.triplet(i) - mu) < 1e-12 for i in range(1, 10))
     for o in (svd, Am, ATm):
         o.destroy()
+
+
+def test_eps_ex19_3d_laplacian_smallest_with_multiplicities():
+    """eps/tutorials/ex19.c (output/ex19_1.out, -eps_nev 8 -eps_type krylovschur -eps_ncv 64): the 7-point Laplacian on a 10^3 grid — the
+    stencil of BASELINE configs[2] — smallest eigenvalues, the triple ones found with their multiplicity; the tutorial itself
+    compares with the analytic spectrum (ex19.c:25-45), so does this test"""
+    n = 10
+    A = O.laplacian_3d(n).tocsr()
+    Am = CP.mat_csr(A)
+    eps = SL.EPS(Am, hermitian=True)
+    CP.use_cpu_bv(eps)
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_SMALLEST_REAL)
+    S.EPSSetDimensions(eps.h, 8, 64, SL.PETSC_DETERMINE)
+    eps.solve()
+    assert eps.reason > 0 and eps.nconv >= 8
+    lam = [eps.eigenvalue(i)[0] for i in range(8)]
+    assert [f"{x:.5f}" for x in lam] == ["0.24304", "0.47952", "0.47952", "0.47952", "0.71600", "0.71600", "0.71600", "0.85231"]
+    th = 2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    exact = np.sort((th[:, None, None] + th[None, :, None] + th[None, None, :]).ravel())[:8]
+    assert np.allclose(lam, exact, rtol=1e-10, atol=0)
+    ref = O.eps_krylovschur(A, n ** 3, nev=8, ncv=64, which="smallest_real")
+    assert (eps.nconv, eps.its) == (ref.nconv, ref.its)
+    assert np.allclose(lam, ref.eigr[ref.perm][:8], rtol=1e-12, atol=0)
+    for o in (eps, Am):
+        o.destroy()
