@@ -740,3 +740,30 @@ def test_eps_ex19_3d_laplacian_smallest_with_multiplicities():
     assert np.allclose(lam, ref.eigr[ref.perm][:8], rtol=1e-12, atol=0)
     for o in (eps, Am):
         o.destroy()
+
+
+def test_eps_ex9_brusselator_complex_pairs():
+    """eps/tutorials/ex9.c (output/ex9_1.out, -n 50 -eps_nev 4, krylovschur, EPS_LARGEST_REAL): the Brusselator wave model, a real
+    non-symmetric 100 x 100 operator [tau1 T + (beta-1) I, alpha^2 I; -beta I, tau2 T - alpha^2 I] (ex9.c:191-225, assembled here instead
+    of the tutorial's MatShell) whose rightmost eigenvalues are complex conjugate pairs: 0.00007+-2.13946i, -0.67386+-2.52812i"""
+    import scipy.sparse as sp
+    N, alpha, beta, d1, d2, L = 50, 2.0, 5.45, 0.008, 0.004, 0.51302
+    h = 1.0 / (N + 1)
+    tau1, tau2 = d1 / (h * L) ** 2, d2 / (h * L) ** 2
+    T = sp.diags([np.ones(N - 1), -2 * np.ones(N), np.ones(N - 1)], [-1, 0, 1])
+    I = sp.identity(N)
+    A = sp.bmat([[tau1 * T + (beta - 1) * I, alpha ** 2 * I], [-beta * I, tau2 * T - alpha ** 2 * I]]).tocsr()
+    Am = CP.mat_csr(A)
+    eps = SL.EPS(Am, hermitian=False)
+    CP.use_cpu_bv(eps)
+    S.EPSSetWhichEigenpairs(eps.h, SL.EPS_LARGEST_REAL)
+    S.EPSSetDimensions(eps.h, 4, SL.PETSC_DETERMINE, SL.PETSC_DETERMINE)
+    eps.solve()
+    assert eps.reason > 0 and eps.nconv >= 4
+    got = ["%.5f%+.5fi" % eps.eigenvalue(i) for i in range(4)]
+    assert got == ["0.00007+2.13946i", "0.00007-2.13946i", "-0.67386+2.52812i", "-0.67386-2.52812i"]
+    assert max(eps.error(i) for i in range(4)) < 5e-8
+    ref = O.eps_krylovschur(A, 2 * N, nev=4, which="largest_real", hermitian=False)
+    assert (eps.nconv, eps.its) == (ref.nconv, ref.its)
+    for o in (eps, Am):
+        o.destroy()
